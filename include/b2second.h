@@ -1,0 +1,180 @@
+/*
+ * b2second.h -- C ABI of libb2second.so: the B200 (sm_100a) implementation of the native layer that
+ * second.pytorch reaches through the external `spconv` 1.x package on its LiDAR-inference hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is marked "host";
+ *   - all counts that depend on data live in device memory (`*_dev`); no entry point synchronises,
+ *     allocates, or keeps global mutable state; the caller owns all memory and passes workspaces;
+ *   - `stream` is the caller's cudaStream_t (as void*), e.g. torch.cuda.current_stream().cuda_stream;
+ *   - return 0 on success, negative on error; b2s_last_error() (thread-local) gives the message;
+ *   - data-dependent overflow of a caller-sized buffer never writes out of bounds: it raises bit(s)
+ *     in the caller's `status_dev` word (B2S_STATUS_*), which the caller reads when it next syncs;
+ *   - coordinates are int32 rows (b, z, y, x); features are fp32 row-major [rows, channels].
+ *
+ * What each entry point replaces (paths relative to the reference root; the spconv symbols are the
+ * ones those call sites bind -- spconv itself is not vendored in the reference):
+ *
+ *   b2s_voxelize        spconv.utils.VoxelGeneratorV2.generate / generate_multi_gpu
+ *                       (second/builder/voxel_builder.py:23-32, second/data/preprocess.py:303-315)
+ *                       + fused SimpleVoxel / SimpleVoxelRadius mean
+ *                       (second/pytorch/models/voxel_encoder.py:206-255)
+ *   b2s_hash_build,
+ *   b2s_rulebook_subm,
+ *   b2s_rulebook_conv   torch.ops.spconv.get_indice_pairs as used by spconv.SubMConv3d / SparseConv3d
+ *                       (second/pytorch/models/middle.py:146-189)
+ *   b2s_sparse_conv     torch.ops.spconv.indice_conv (+ the BatchNorm1d/ReLU that always follow,
+ *                       middle.py:146-191, folded into scale/shift/relu)
+ *   b2s_to_bev          spconv.SparseConvTensor.dense() + view (middle.py:206-209) and
+ *                       PointPillarsScatter.forward (second/pytorch/models/pointpillars.py:444-476)
+ *   b2s_pfn             PillarFeatureNet.forward (pointpillars.py:203-237, single PFNLayer :51-65)
+ *   b2s_decode_filter   box_coder.decode_torch + sigmoid + score threshold
+ *                       (second/pytorch/models/voxelnet.py:413-414,444,560-576,
+ *                        second/pytorch/core/box_torch_ops.py:56-102)
+ *   b2s_nms             torch.topk + spconv.utils.rotate_non_max_suppression_cpu /
+ *                       spconv.utils.non_max_suppression (box_torch_ops.py:454-515,
+ *                       second/core/non_max_suppression/nms_cpu.py:20-31, nms_gpu.py:10-19)
+ *                       + direction / range epilogue (voxelnet.py:598-628)
+ *   b2s_nms_aligned_host, b2s_nms_rotated_host
+ *                       the numpy-facing spconv.utils.non_max_suppression /
+ *                       rotate_non_max_suppression_cpu signatures (host arrays in, keep list out)
+ */
+#ifndef B2SECOND_H_
+#define B2SECOND_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2S_VERSION 100
+
+/* status bits raised in *status_dev */
+#define B2S_STATUS_VOXEL_OVERFLOW 1u   /* more voxels than max_voxels (extra voxels dropped, as spconv) */
+#define B2S_STATUS_ROWS_OVERFLOW 2u    /* strided conv produced more rows than cap_out (rows dropped)   */
+#define B2S_STATUS_HASH_FULL 4u        /* hash table too small                                            */
+#define B2S_STATUS_CAND_OVERFLOW 8u    /* more score-threshold survivors than cand_cap (lowest dropped)  */
+
+int b2s_version(void);
+const char *b2s_last_error(void);
+
+/* ---- voxelizer -------------------------------------------------------------------------------- */
+/* VFE modes fused into the voxelizer */
+#define B2S_VFE_NONE 0
+#define B2S_VFE_MEAN 1        /* SimpleVoxel: mean of the first num_features point features          */
+#define B2S_VFE_MEAN_RADIUS 2 /* SimpleVoxelRadius: [norm(mean xy), mean[2:num_features]]            */
+
+size_t b2s_voxelize_workspace_bytes(int num_points, int batch, int max_voxels, int max_points);
+int b2s_voxelize_hash_capacity(int num_points);
+
+/* points [P,F] fp32 for `batch` frames stored back to back; frame_offsets_dev [batch+1] int32 (may be
+ * NULL when batch==1).  Frame-major first-come voxel ids, at most max_voxels per frame; rows of all
+ * frames are compacted back to back (frame 0 first), exactly the layout merge_second_batch builds
+ * (second/data/preprocess.py:21-55).
+ * outputs (row capacity = batch*max_voxels):
+ *   coors [cap,4] (b,z,y,x); num_points_per_voxel [cap]; point_slots [cap,T] point indices (-1 pad),
+ *   voxels [cap,T,F] zero padded (may be NULL); vfe_out [cap,vfe_channels] (NULL if vfe_mode==NONE);
+ *   num_voxels_dev [1+batch]: total then per-frame counts;
+ *   hash_keys [hash_cap] u64 / hash_vals [hash_cap] i32: coordinate -> row locator of the result. */
+int b2s_voxelize(const float *points, const int *frame_offsets_dev, int num_points, int num_feat,
+                 int batch, const float *range_lo /*host[3] xyz*/, const float *voxel_size /*host[3]*/,
+                 const int *grid /*host[3] xyz*/, int max_points, int max_voxels, int *coors,
+                 int *num_points_per_voxel, int *point_slots, float *voxels, int vfe_mode,
+                 int vfe_num_features, float *vfe_out, int *num_voxels_dev,
+                 unsigned long long *hash_keys, int *hash_vals, int hash_cap, void *workspace,
+                 size_t workspace_bytes, unsigned *status_dev, void *stream);
+
+/* ---- rulebook --------------------------------------------------------------------------------- */
+/* coordinate -> row hash over `shape` (D,H,W).  hash_cap must be a power of two >= 2*cap_rows. */
+int b2s_hash_build(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape /*host[3]*/,
+                   unsigned long long *hash_keys, int *hash_vals, int hash_cap, unsigned *status_dev,
+                   void *stream);
+
+/* submanifold conv rulebook: nbr[row][k] = input row at coor + (k - k//2)*dil, or -1.
+ * k index row-major over (kz,ky,kx); K = kz*ky*kx. */
+int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape,
+                      const int *ksize /*host[3]*/, const int *dilation /*host[3]*/,
+                      const unsigned long long *hash_keys, const int *hash_vals, int hash_cap,
+                      int *nbr /*[cap_rows,K]*/, void *stream);
+
+size_t b2s_rulebook_conv_workspace_bytes(int batch, const int *out_shape /*host[3]*/);
+/* strided ("regular") sparse conv rulebook.  Output rows are emitted sorted ascending by flat
+ * (b,z,y,x) key.  out_shape must be (in + 2p - d(k-1) - 1)/s + 1 per dim.
+ * Builds the out-coordinate hash as well (hash_cap_out power of two >= 2*cap_out). */
+int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int cap_in, int batch,
+                      const int *in_shape, const int *out_shape, const int *ksize, const int *stride,
+                      const int *padding, const int *dilation, const unsigned long long *hash_keys_in,
+                      const int *hash_vals_in, int hash_cap_in, int *coors_out /*[cap_out,4]*/,
+                      int *num_out_dev, int cap_out, int *nbr /*[cap_out,K]*/,
+                      unsigned long long *hash_keys_out, int *hash_vals_out, int hash_cap_out,
+                      void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream);
+
+/* pair-list view of a neighbour table (spconv's indice_pairs [K,2,L] + indice_pair_num [K]) --
+ * only for parity checks / API completeness; the conv kernels consume `nbr` directly. */
+int b2s_rulebook_pairs(const int *nbr, const int *num_out_dev, int cap_out, int K, int L,
+                       int *indice_pairs /*[K,2,L] prefilled -1*/, int *indice_pair_num /*[K] zeroed*/,
+                       void *stream);
+
+/* ---- sparse convolution ------------------------------------------------------------------------ */
+/* out[o,:] = act( (sum_k W[k]^T in[nbr[o,k],:]) * scale + shift ),  W = [K,Cin,Cout] fp32
+ * (the reference's weight [kD,kH,kW,Cin,Cout] viewed flat).  scale/shift may be NULL (identity);
+ * a conv bias is passed as shift with scale NULL.  Accumulation order: k ascending, fp32. */
+int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const int *nbr, int K,
+                    const int *num_out_dev, int cap_out, const float *scale, const float *shift,
+                    int relu, float *feat_out, int cout, void *stream);
+
+/* ---- dense BEV map ----------------------------------------------------------------------------- */
+#define B2S_LAYOUT_NCHW 0 /* out[b, c*D+z, y, x]  (== dense() [B,C,D,H,W] viewed [B,C*D,H,W]) */
+#define B2S_LAYOUT_NHWC 1 /* out[b, y, x, c*D+z] */
+int b2s_to_bev(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C,
+               int batch, int D, int H, int W, float *out, int layout, void *stream);
+
+/* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
+int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,
+            const int *coors, const int *num_rows_dev, int cap_rows, int max_points,
+            const float *weight /*[Cout, F+5]*/, const float *scale, const float *shift, int cout,
+            float vx, float vy, float x_offset, float y_offset, float *out /*[cap_rows,Cout]*/,
+            void *stream);
+
+/* ---- box decode + score filter ------------------------------------------------------------------ */
+/* Head tensors in the RPN's NCHW conv-output layout: box [B, A_loc*code, H, W], cls [B, A_loc*ncls, H, W],
+ * dir [B, A_loc*nbins, H, W] (dir may be NULL).  anchors [A_loc*H*W, code] in (a_loc, y, x) order.
+ * anchors_mask [B, A] uint8 may be NULL.  Candidates (score >= thresh) are appended per frame:
+ *   cand_box [B,cand_cap,code] decoded, cand_score [B,cand_cap], cand_label/cand_dir [B,cand_cap] int32,
+ *   cand_anchor [B,cand_cap] int32 (anchor index, the deterministic tie-break key), cand_count_dev [B]. */
+int b2s_decode_filter(const float *box, const float *cls, const float *dir, const float *anchors,
+                      const uint8_t *anchors_mask, int batch, int a_loc, int H, int W, int code,
+                      int ncls, int nbins, float score_thresh, float *cand_box, float *cand_score,
+                      int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev,
+                      int cand_cap, unsigned *status_dev, void *stream);
+
+/* ---- top-k + NMS + direction/range epilogue ------------------------------------------------------ */
+size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max);
+/* rotated != 0: polygon IoU of BEV boxes (x,y,w,l,r), skip pair when stand-up boxes do not overlap,
+ *               suppress when IoU >= iou_thresh;
+ * rotated == 0: stand-up boxes of the rotated boxes, IoU with +1 on width/height, suppress when > thresh.
+ * Descending score order, ties -> lower anchor index.  Kept boxes (<= post_max per frame), after the
+ * direction fix-up and post_center_range test (range_host NULL = no test), are written to
+ *   det [B, post_max, code+2] = (box[code], score, label) and det_count_dev [B]. */
+int b2s_nms(const float *cand_box, const float *cand_score, const int *cand_label, const int *cand_dir,
+            const int *cand_anchor, const int *cand_count_dev, int batch, int cand_cap, int code,
+            int rotated, int pre_max, int post_max, float iou_thresh, int use_dir, float dir_offset,
+            float dir_limit_offset, int num_dir_bins, const float *range_host /*host[6] or NULL*/,
+            float *det, int *det_count_dev, void *workspace, size_t workspace_bytes, void *stream);
+
+/* numpy-facing spconv.utils signatures: HOST arrays in/out, internal H2D/D2H + sync (like upstream's
+ * non_max_suppression, which takes a device_id and does its own copies). */
+/* eps=1, inclusive=0: spconv.utils.non_max_suppression ("+1" IoU, suppress if IoU > thresh);
+ * eps given, inclusive=1: spconv.utils.non_max_suppression_cpu (suppress if IoU >= thresh). */
+int b2s_nms_aligned_host(const float *sorted_dets /*host [N,5]*/, int n, float thresh, float eps,
+                         int inclusive, int *keep_out /*host [N]*/, int device_id);
+int b2s_nms_rotated_host(const float *corners /*host [N,4,2]*/, const int *order /*host [N]*/,
+                         const float *standup_iou /*host [N,N]*/, int n, float thresh,
+                         int *keep_out /*host [N]*/, int device_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SECOND_H_ */

@@ -1,0 +1,330 @@
+// rulebook.cu -- sparse-convolution rulebooks as dense neighbour tables (b2s_hash_build,
+// b2s_rulebook_subm, b2s_rulebook_conv, b2s_rulebook_pairs; see include/b2second.h).
+//
+// Instead of spconv's per-offset pair lists (gather / GEMM / scatter-add per offset, one D2H sync per
+// layer) the rulebook is OUTPUT-STATIONARY: nbr[o][k] = input row feeding output row o through kernel
+// offset k (or -1).  A conv is then one pass with one write per output row and no atomics.
+//   cross-correlation: out[o] = sum_k W[k]^T in[o*s - p + k*d],  k row-major over (kz,ky,kx).
+//
+// Strided conv output set: {o : exists k, o*s - p + k*d is active}, emitted sorted ascending by flat
+// (b,z,y,x) key (the order upstream's GPU path produces with thrust sort+unique).  Here dedup + sort
+// are one step: an occupancy bitmap over the output grid plus a popcount prefix scan gives every
+// active output cell its sorted rank directly.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kScanThreads = 1024;
+
+struct ConvGeom {
+    int in_shape[3], out_shape[3], k[3], s[3], p[3], d[3];
+    int K;
+};
+
+__global__ void k_hash_build(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
+                             int D, int H, int W, unsigned long long *keys, int *vals, int mask,
+                             unsigned *status)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_dev, cap_rows);
+    if (i >= n) return;
+    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)i * 4);
+    unsigned long long key = b2s_flat_key(c.x, c.y, c.z, c.w, D, H, W);
+    int h = b2s_hash_insert(keys, mask, key);
+    if (h < 0) { atomicOr(status, B2S_STATUS_HASH_FULL); return; }
+    vals[h] = i;
+}
+
+// one thread per (row, k)
+__global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
+                           ConvGeom g, const unsigned long long *__restrict__ keys,
+                           const int *__restrict__ vals, int mask, int *nbr)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_dev, cap_rows);
+    if (gid >= (long long)n * g.K) return;
+    int row = (int)(gid / g.K), k = (int)(gid % g.K);
+    int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
+    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
+    int z = c.y + (kz - g.k[0] / 2) * g.d[0];
+    int y = c.z + (ky - g.k[1] / 2) * g.d[1];
+    int x = c.w + (kx - g.k[2] / 2) * g.d[2];
+    int r = -1;
+    if (z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1] && x >= 0 && x < g.in_shape[2]) {
+        if (kz == g.k[0] / 2 && ky == g.k[1] / 2 && kx == g.k[2] / 2) r = row;
+        else r = b2s_hash_find(keys, vals, mask,
+                               b2s_flat_key(c.x, z, y, x, g.in_shape[0], g.in_shape[1], g.in_shape[2]));
+    }
+    nbr[gid] = r;
+}
+
+// one thread per (input row, k): mark candidate output cells
+__global__ void k_conv_mark(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
+                            ConvGeom g, unsigned *bitmap)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_dev, cap_rows);
+    if (gid >= (long long)n * g.K) return;
+    int row = (int)(gid / g.K), k = (int)(gid % g.K);
+    int kk[3] = {k / (g.k[2] * g.k[1]), (k / g.k[2]) % g.k[1], k % g.k[2]};
+    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
+    int ic[3] = {c.y, c.z, c.w};
+    int o[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        int num = ic[j] + g.p[j] - kk[j] * g.d[j];
+        if (num < 0) return;
+        if (num % g.s[j] != 0) return;
+        o[j] = num / g.s[j];
+        if (o[j] >= g.out_shape[j]) return;
+    }
+    unsigned long long key = b2s_flat_key(c.x, o[0], o[1], o[2], g.out_shape[0], g.out_shape[1], g.out_shape[2]);
+    atomicOr(&bitmap[key >> 5], 1u << (key & 31));
+}
+
+__global__ void k_popc_scan(const unsigned *__restrict__ bitmap, long long nwords, int *word_prefix,
+                            int *block_sums)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int v = i < nwords ? __popc(bitmap[i]) : 0;
+    int total;
+    int ex = b2s_block_exscan(v, &total);
+    if (i < nwords) word_prefix[i] = ex;
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void k_scan_sums(int *block_sums, int nblk, int *num_out_dev, int cap_out, unsigned *status)
+{
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblk; base += blockDim.x) {
+        int idx = base + threadIdx.x;
+        int v = idx < nblk ? block_sums[idx] : 0;
+        int total;
+        int ex = b2s_block_exscan(v, &total);
+        int c = carry;
+        if (idx < nblk) block_sums[idx] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int n = carry;
+        if (n > cap_out) { atomicOr(status, B2S_STATUS_ROWS_OVERFLOW); n = cap_out; }
+        *num_out_dev = n;
+    }
+}
+
+// one thread per bitmap word: emit sorted output coordinates + out hash
+__global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nwords,
+                            const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
+                            ConvGeom g, int cap_out, int *coors_out, unsigned long long *keys_out,
+                            int *vals_out, int mask_out, unsigned *status)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    unsigned bits = bitmap[i];
+    if (bits == 0) return;
+    int row = block_prefix[i / kScanThreads] + word_prefix[i];
+    const unsigned long long W = g.out_shape[2], H = g.out_shape[1], D = g.out_shape[0];
+    while (bits) {
+        int bit = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (row < cap_out) {
+            unsigned long long key = ((unsigned long long)i << 5) + bit;
+            int x = (int)(key % W);
+            unsigned long long r = key / W;
+            int y = (int)(r % H);
+            r /= H;
+            int z = (int)(r % D);
+            int b = (int)(r / D);
+            *reinterpret_cast<int4 *>(coors_out + (size_t)row * 4) = make_int4(b, z, y, x);
+            int h = b2s_hash_insert(keys_out, mask_out, key);
+            if (h < 0) atomicOr(status, B2S_STATUS_HASH_FULL);
+            else vals_out[h] = row;
+        }
+        ++row;
+    }
+}
+
+// one thread per (output row, k): neighbour lookup in the input hash
+__global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restrict__ n_out_dev, int cap_out,
+                           ConvGeom g, const unsigned long long *__restrict__ keys_in,
+                           const int *__restrict__ vals_in, int mask_in, int *nbr)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_out_dev, cap_out);
+    if (gid >= (long long)n * g.K) return;
+    int row = (int)(gid / g.K), k = (int)(gid % g.K);
+    int kk[3] = {k / (g.k[2] * g.k[1]), (k / g.k[2]) % g.k[1], k % g.k[2]};
+    int4 c = *reinterpret_cast<const int4 *>(coors_out + (size_t)row * 4);
+    int oc[3] = {c.y, c.z, c.w};
+    int ic[3];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ic[j] = oc[j] * g.s[j] - g.p[j] + kk[j] * g.d[j];
+        if (ic[j] < 0 || ic[j] >= g.in_shape[j]) ok = false;
+    }
+    int r = -1;
+    if (ok)
+        r = b2s_hash_find(keys_in, vals_in, mask_in,
+                          b2s_flat_key(c.x, ic[0], ic[1], ic[2], g.in_shape[0], g.in_shape[1], g.in_shape[2]));
+    nbr[gid] = r;
+}
+
+__global__ void k_pairs(const int *__restrict__ nbr, const int *__restrict__ n_out_dev, int cap_out, int K,
+                        int L, int *pairs, int *pair_num)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_out_dev, cap_out);
+    if (gid >= (long long)n * K) return;
+    int row = (int)(gid / K), k = (int)(gid % K);
+    int r = nbr[gid];
+    if (r < 0) return;
+    int pos = atomicAdd(&pair_num[k], 1);
+    if (pos < L) {
+        pairs[((size_t)k * 2 + 0) * L + pos] = r;
+        pairs[((size_t)k * 2 + 1) * L + pos] = row;
+    }
+}
+
+struct ConvWorkspace {
+    unsigned *bitmap;
+    int *word_prefix;
+    int *block_sums;
+    long long nwords;
+    int nblk;
+};
+
+size_t carve(ConvWorkspace *w, char *base, int batch, const int *out_shape)
+{
+    long long cells = (long long)batch * out_shape[0] * out_shape[1] * out_shape[2];
+    long long nwords = (cells + 31) / 32;
+    int nblk = b2s_cdiv(nwords > 0 ? nwords : 1, kScanThreads);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += b2s_align(bytes); return base ? base + o : nullptr; };
+    unsigned *bitmap = (unsigned *)take(sizeof(unsigned) * (size_t)nwords);
+    int *wp = (int *)take(sizeof(int) * (size_t)nwords);
+    int *bs = (int *)take(sizeof(int) * (size_t)(nblk + 1));
+    if (w) { w->bitmap = bitmap; w->word_prefix = wp; w->block_sums = bs; w->nwords = nwords; w->nblk = nblk; }
+    return off;
+}
+
+int fill_geom(ConvGeom *g, const int *in_shape, const int *out_shape, const int *ksize, const int *stride,
+              const int *padding, const int *dilation)
+{
+    for (int j = 0; j < 3; ++j) {
+        g->in_shape[j] = in_shape[j];
+        g->out_shape[j] = out_shape ? out_shape[j] : in_shape[j];
+        g->k[j] = ksize[j];
+        g->s[j] = stride ? stride[j] : 1;
+        g->p[j] = padding ? padding[j] : 0;
+        g->d[j] = dilation ? dilation[j] : 1;
+        if (g->k[j] < 1 || g->s[j] < 1 || g->d[j] < 1 || g->in_shape[j] < 1 || g->out_shape[j] < 1) return -1;
+    }
+    g->K = g->k[0] * g->k[1] * g->k[2];
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b2s_hash_build(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape,
+                              unsigned long long *hash_keys, int *hash_vals, int hash_cap,
+                              unsigned *status_dev, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE((hash_cap & (hash_cap - 1)) == 0 && hash_cap >= 2 * cap_rows && hash_cap >= 2,
+                "b2s_hash_build: hash_cap must be a power of two >= 2*cap_rows");
+    B2S_CUDA_OK(cudaMemsetAsync(hash_keys, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(hash_vals, 0xFF, sizeof(int) * (size_t)hash_cap, stream));
+    if (cap_rows > 0) {
+        k_hash_build<<<b2s_cdiv(cap_rows, kThreads), kThreads, 0, stream>>>(
+            coors, num_rows_dev, cap_rows, shape[0], shape[1], shape[2], hash_keys, hash_vals, hash_cap - 1,
+            status_dev);
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}
+
+extern "C" int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape,
+                                 const int *ksize, const int *dilation, const unsigned long long *hash_keys,
+                                 const int *hash_vals, int hash_cap, int *nbr, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ConvGeom g;
+    B2S_REQUIRE(fill_geom(&g, shape, nullptr, ksize, nullptr, nullptr, dilation) == 0,
+                "b2s_rulebook_subm: bad geometry");
+    B2S_REQUIRE((g.k[0] & 1) && (g.k[1] & 1) && (g.k[2] & 1), "b2s_rulebook_subm: kernel sizes must be odd");
+    if (cap_rows > 0) {
+        k_subm_nbr<<<b2s_cdiv((long long)cap_rows * g.K, kThreads), kThreads, 0, stream>>>(
+            coors, num_rows_dev, cap_rows, g, hash_keys, hash_vals, hash_cap - 1, nbr);
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}
+
+extern "C" size_t b2s_rulebook_conv_workspace_bytes(int batch, const int *out_shape)
+{
+    return carve(nullptr, nullptr, batch, out_shape);
+}
+
+extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int cap_in, int batch,
+                                 const int *in_shape, const int *out_shape, const int *ksize,
+                                 const int *stride, const int *padding, const int *dilation,
+                                 const unsigned long long *hash_keys_in, const int *hash_vals_in,
+                                 int hash_cap_in, int *coors_out, int *num_out_dev, int cap_out, int *nbr,
+                                 unsigned long long *hash_keys_out, int *hash_vals_out, int hash_cap_out,
+                                 void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ConvGeom g;
+    B2S_REQUIRE(fill_geom(&g, in_shape, out_shape, ksize, stride, padding, dilation) == 0,
+                "b2s_rulebook_conv: bad geometry");
+    for (int j = 0; j < 3; ++j) {
+        int expect = (g.in_shape[j] + 2 * g.p[j] - g.d[j] * (g.k[j] - 1) - 1) / g.s[j] + 1;
+        B2S_REQUIRE(expect == g.out_shape[j], "b2s_rulebook_conv: out_shape[%d]=%d, expected %d", j,
+                    g.out_shape[j], expect);
+    }
+    B2S_REQUIRE((hash_cap_out & (hash_cap_out - 1)) == 0 && hash_cap_out >= 2 * cap_out && hash_cap_out >= 2,
+                "b2s_rulebook_conv: hash_cap_out must be a power of two >= 2*cap_out");
+    ConvWorkspace w;
+    size_t need = carve(&w, (char *)workspace, batch, out_shape);
+    B2S_REQUIRE(workspace_bytes >= need, "b2s_rulebook_conv: workspace too small (%zu < %zu)", workspace_bytes, need);
+    B2S_CUDA_OK(cudaMemsetAsync(w.bitmap, 0, sizeof(unsigned) * (size_t)w.nwords, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(hash_keys_out, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap_out, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(hash_vals_out, 0xFF, sizeof(int) * (size_t)hash_cap_out, stream));
+    if (cap_in > 0) {
+        k_conv_mark<<<b2s_cdiv((long long)cap_in * g.K, kThreads), kThreads, 0, stream>>>(
+            coors_in, num_in_dev, cap_in, g, w.bitmap);
+        B2S_LAUNCH_OK();
+    }
+    k_popc_scan<<<w.nblk, kScanThreads, 0, stream>>>(w.bitmap, w.nwords, w.word_prefix, w.block_sums);
+    B2S_LAUNCH_OK();
+    k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblk, num_out_dev, cap_out, status_dev);
+    B2S_LAUNCH_OK();
+    k_conv_emit<<<w.nblk, kScanThreads, 0, stream>>>(w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out,
+                                                    coors_out, hash_keys_out, hash_vals_out, hash_cap_out - 1,
+                                                    status_dev);
+    B2S_LAUNCH_OK();
+    if (cap_out > 0) {
+        k_conv_nbr<<<b2s_cdiv((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
+            coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}
+
+extern "C" int b2s_rulebook_pairs(const int *nbr, const int *num_out_dev, int cap_out, int K, int L,
+                                  int *indice_pairs, int *indice_pair_num, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (cap_out > 0 && K > 0) {
+        k_pairs<<<b2s_cdiv((long long)cap_out * K, kThreads), kThreads, 0, stream>>>(nbr, num_out_dev, cap_out, K,
+                                                                                 L, indice_pairs, indice_pair_num);
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}

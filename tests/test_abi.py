@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/b2second.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+from conftest import REPO
+
+
+def _header_symbols():
+    text = open(os.path.join(REPO, "include", "b2second.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2s_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported():
+    from spconv import _lib
+    lib = _lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), "libb2second.so does not export %s" % s
+
+
+def test_bindings_cover_header():
+    from spconv import _lib
+    assert sorted(_lib.SIGNATURES) == _header_symbols()
+
+
+def test_header_arity_matches_bindings():
+    from spconv import _lib
+    text = open(os.path.join(REPO, "include", "b2second.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, text, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("void", "") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, binding %d" % (name, n, len(args))
+
+
+def test_version_and_error_string():
+    from spconv import _lib
+    lib = _lib.load()
+    assert lib.b2s_version() >= 100
+    assert isinstance(lib.b2s_last_error(), bytes)
+
+
+def test_workspace_queries_are_host_only():
+    from spconv import _lib
+    lib = _lib.load()
+    assert lib.b2s_voxelize_hash_capacity(20000) == 65536
+    assert lib.b2s_voxelize_workspace_bytes(20000, 1, 40000, 5) > 0
+    assert lib.b2s_rulebook_conv_workspace_bytes(1, (ctypes.c_int * 3)(21, 800, 704)) > 0
+    assert lib.b2s_nms_workspace_bytes(1, 4096, 1000) > 0
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import pytest
+    import torch
+    import spconv
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = spconv.SparseConvTensor(torch.zeros(3, 4), torch.zeros(3, 4, dtype=torch.int32), [8, 8, 8], 1)
+    with pytest.raises(RuntimeError):
+        spconv.SubMConv3d(4, 16, 3, bias=False)(x)
+    with pytest.raises(RuntimeError):
+        x.dense()
+    with pytest.raises(RuntimeError):
+        spconv.utils.VoxelGeneratorV2([0.1] * 3, [0, 0, 0, 1, 1, 1], 5).generate(torch.zeros(4, 4).numpy(), 100)

@@ -1,0 +1,165 @@
+"""Oracle NMS functions against independent restatements:
+* rotated IoU: corners-inside + edge-edge intersections + angular sort + shoelace, fp64 -- the algorithm the
+  reference states in-tree (second/core/non_max_suppression/nms_gpu.py:329-401), different from the oracle's
+  Sutherland-Hodgman clip;
+* aligned NMS: the literal python of nms_gpu.py:21-32,109-126 (+1 IoU, '>') and nms_cpu.py:34-63 (eps, '>=')."""
+import numpy as np
+import pytest
+
+from b2second import box_ops
+
+
+def _inside(pt, quad):
+    # convex quad, any orientation
+    s = []
+    for i in range(4):
+        a, b = quad[i], quad[(i + 1) % 4]
+        s.append((b[0] - a[0]) * (pt[1] - a[1]) - (b[1] - a[1]) * (pt[0] - a[0]))
+    s = np.array(s)
+    return np.all(s >= 0) or np.all(s <= 0)
+
+
+def _seg_inter(p1, p2, q1, q2):
+    d1, d2 = p2 - p1, q2 - q1
+    den = d1[0] * d2[1] - d1[1] * d2[0]
+    if abs(den) < 1e-14:
+        return None
+    t = ((q1[0] - p1[0]) * d2[1] - (q1[1] - p1[1]) * d2[0]) / den
+    u = ((q1[0] - p1[0]) * d1[1] - (q1[1] - p1[1]) * d1[0]) / den
+    if 0 <= t <= 1 and 0 <= u <= 1:
+        return p1 + t * d1
+    return None
+
+
+def independent_inter_area(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    pts = [p for p in a if _inside(p, b)] + [p for p in b if _inside(p, a)]
+    for i in range(4):
+        for j in range(4):
+            r = _seg_inter(a[i], a[(i + 1) % 4], b[j], b[(j + 1) % 4])
+            if r is not None:
+                pts.append(r)
+    if len(pts) < 3:
+        return 0.0
+    pts = np.array(pts)
+    c = pts.mean(0)
+    ang = np.arctan2(pts[:, 1] - c[1], pts[:, 0] - c[0])
+    pts = pts[np.argsort(ang)]
+    x, y = pts[:, 0], pts[:, 1]
+    return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+
+
+def random_rboxes(rng, n, spread=20.0):
+    xy = rng.uniform(0, spread, (n, 2))
+    wl = rng.uniform(1.0, 5.0, (n, 2))
+    r = rng.uniform(-np.pi, np.pi, (n, 1))
+    return np.concatenate([xy, wl, r], 1).astype(np.float32)
+
+
+def test_quad_intersection_matches_independent(oracle):
+    rng = np.random.default_rng(0)
+    rb = random_rboxes(rng, 60, 12.0)
+    corners = box_ops.corners_2d_np(rb[:, :2], rb[:, 2:4], rb[:, 4])
+    worst = 0.0
+    for i in range(60):
+        for j in range(60):
+            got = oracle.utils.quad_intersection_area(corners[i], corners[j])
+            ref = independent_inter_area(corners[i], corners[j])
+            worst = max(worst, abs(got - ref))
+    assert worst < 1e-6
+    # self intersection = own area
+    assert abs(oracle.utils.quad_intersection_area(corners[0], corners[0]) - rb[0, 2] * rb[0, 3]) < 1e-4
+
+
+def python_rotate_nms(corners, order, standup_iou, thresh):
+    n = corners.shape[0]
+    sup = np.zeros(n, bool)
+    keep = []
+    area = [abs(independent_inter_area(c, c)) for c in corners]
+    near = 0
+    for _i in range(n):
+        i = order[_i]
+        if sup[i]:
+            continue
+        keep.append(int(i))
+        for _j in range(_i + 1, n):
+            j = order[_j]
+            if sup[j] or standup_iou[i, j] <= 0:
+                continue
+            inter = independent_inter_area(corners[i], corners[j])
+            if inter <= 0:
+                continue
+            iou = inter / (area[i] + area[j] - inter)
+            near += abs(iou - thresh) < 1e-6
+            if iou >= thresh:
+                sup[j] = True
+    return keep, near
+
+
+@pytest.mark.parametrize("thresh", [0.01, 0.1, 0.5])
+def test_rotate_nms_matches_bruteforce(oracle, thresh):
+    rng = np.random.default_rng(int(thresh * 100))
+    rb = random_rboxes(rng, 150)
+    scores = rng.uniform(0, 1, 150).astype(np.float32)
+    order = np.argsort(-scores, kind="stable").astype(np.int32)
+    corners = box_ops.corners_2d_np(rb[:, :2], rb[:, 2:4], rb[:, 4])
+    siou = box_ops.standup_iou_np(box_ops.standup_np(corners), 0.0)
+    keep = oracle.utils.rotate_non_max_suppression_cpu(corners, order, siou, thresh)
+    ref, near = python_rotate_nms(corners, order, siou, thresh)
+    assert near == 0, "test data has near-threshold pairs; change the seed"
+    assert keep == ref
+    assert 0 < len(keep) < 150
+
+
+def test_aligned_nms_variants(oracle):
+    rng = np.random.default_rng(5)
+    n = 200
+    xy = rng.uniform(0, 30, (n, 2))
+    wh = rng.uniform(0.5, 6, (n, 2))
+    scores = np.sort(rng.uniform(0, 1, n))[::-1]
+    dets = np.concatenate([xy, xy + wh, scores[:, None]], 1).astype(np.float32)
+    # GPU flavour: sorted dets, +1 IoU, '>'
+    keep = np.zeros(n, np.int32)
+    num = oracle.utils.non_max_suppression(dets, keep, 0.5, 0)
+    ref, removed = [], np.zeros(n, bool)
+    for i in range(n):
+        if removed[i]:
+            continue
+        ref.append(i)
+        for j in range(i + 1, n):
+            a, b = dets[i], dets[j]
+            w = max(min(a[2], b[2]) - max(a[0], b[0]) + 1, 0.0)
+            h = max(min(a[3], b[3]) - max(a[1], b[1]) + 1, 0.0)
+            inter = w * h
+            sa = (a[2] - a[0] + 1) * (a[3] - a[1] + 1)
+            sb = (b[2] - b[0] + 1) * (b[3] - b[1] + 1)
+            if inter / (sa + sb - inter) > 0.5:
+                removed[j] = True
+    assert keep[:num].tolist() == ref
+    # CPU flavour: eps, '>='
+    order = np.arange(n, dtype=np.int32)[::-1].copy()
+    got = oracle.utils.non_max_suppression_cpu(dets, order, 0.3, 0.0)
+    ref, sup = [], np.zeros(n, bool)
+    for _i in range(n):
+        i = order[_i]
+        if sup[i]:
+            continue
+        ref.append(int(i))
+        for _j in range(_i + 1, n):
+            j = order[_j]
+            if sup[j]:
+                continue
+            a, b = dets[i], dets[j]
+            w = max(min(a[2], b[2]) - max(a[0], b[0]), 0.0)
+            h = max(min(a[3], b[3]) - max(a[1], b[1]), 0.0)
+            inter = w * h
+            ovr = inter / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter)
+            if ovr >= 0.3:
+                sup[j] = True
+    assert got == ref
+
+
+def test_empty_inputs(oracle):
+    assert oracle.utils.rotate_non_max_suppression_cpu(np.zeros((0, 4, 2), np.float32), np.zeros(0, np.int32),
+                                                       np.zeros((0, 0), np.float32), 0.1) == []
+    assert oracle.utils.non_max_suppression(np.zeros((0, 5), np.float32), np.zeros(0, np.int32), 0.5, 0) == 0
