@@ -70,7 +70,8 @@ size_t b2s_voxelize_workspace_bytes(int num_points, int batch, int max_voxels, i
 int b2s_voxelize_hash_capacity(int num_points);
 
 /* points [P,F] fp32 for `batch` frames stored back to back; frame_offsets_dev [batch+1] int32 (may be
- * NULL when batch==1).  Frame-major first-come voxel ids, at most max_voxels per frame; rows of all
+ * NULL when batch==1; when given, frame_offsets_dev[batch] is the live point count and num_points is
+ * only the buffer capacity -- points beyond it are ignored).  Frame-major first-come voxel ids, at most max_voxels per frame; rows of all
  * frames are compacted back to back (frame 0 first), exactly the layout merge_second_batch builds
  * (second/data/preprocess.py:21-55).
  * outputs (row capacity = batch*max_voxels):

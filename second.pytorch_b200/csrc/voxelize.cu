@@ -29,7 +29,7 @@ struct VoxParams {
 
 __device__ __forceinline__ int frame_of(const int *__restrict__ offsets, int batch, int i)
 {
-    if (offsets == nullptr || batch <= 1) return 0;
+    if (offsets == nullptr) return 0;
     int lo = 0, hi = batch;  // find f with offsets[f] <= i < offsets[f+1]
     while (hi - lo > 1) {
         int mid = (lo + hi) >> 1;
@@ -44,6 +44,8 @@ __global__ void k_insert(const float *__restrict__ pts, const int *__restrict__ 
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    // with frame offsets, offsets[batch] is the live point count (P is then only the buffer capacity)
+    if (offsets != nullptr && i >= __ldg(&offsets[batch])) { pslot[i] = -1; return; }
     const float *p = pts + (size_t)i * F;
     int c[3];
     bool ok = true;
@@ -106,7 +108,7 @@ __global__ void k_scan_sums_and_frames(int *block_sums, int nblk, const int *__r
     const int total_cells = carry;
     // global first-come rank at each frame start = number of first-points with index < offsets[f]
     for (int f = threadIdx.x; f <= batch; f += blockDim.x) {
-        int off = (offsets == nullptr || batch <= 1) ? (f == 0 ? 0 : P) : offsets[f];
+        int off = (offsets == nullptr) ? (f == 0 ? 0 : P) : offsets[f];
         int r;
         if (off >= P) r = total_cells;
         else {

@@ -1,0 +1,104 @@
+"""GPU parity: b2s_voxelize (through the spconv.utils.VoxelGeneratorV2 drop-in) vs the CPU oracle.
+Bar: coordinates / counts / voxels bit-exact (integer + copy work)."""
+import numpy as np
+import pytest
+import torch
+
+from b2second import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def cloud(rng, n, lo=(-0.5, -4.5, -3.5, 0), hi=(7.5, 4.5, 1.5, 1)):
+    pts = rng.uniform(lo, hi, (n, 4)).astype(np.float32)
+    if n > 20:
+        pts[::7] = pts[3]
+        pts[5::11, :3] = pts[2, :3]
+    return pts
+
+
+CASES = [  # (voxel_size, range, T, max_voxels, n_points)
+    ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 20000, 5000),
+    ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 1, 20000, 5000),
+    ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 3, 700, 5000),     # cap hit: extra voxels dropped
+    ([0.16, 0.16, 4], [0, -4, -3, 7.04, 4, 1], 100, 12000, 30000),  # pillars, > T points per pillar
+    ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 100, 0),        # empty cloud
+    ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 100, 1),
+]
+
+
+@pytest.mark.parametrize("vs,rng_,T,mv,n", CASES)
+def test_generate_matches_oracle(product, oracle, vs, rng_, T, mv, n):
+    rng = np.random.default_rng(n + T)
+    pts = cloud(rng, n)
+    a = product.utils.VoxelGeneratorV2(vs, rng_, T, mv).generate(pts, mv)
+    b = oracle.utils.VoxelGeneratorV2(vs, rng_, T, mv).generate(pts, mv)
+    assert a["voxel_num"] == b["voxel_num"]
+    np.testing.assert_array_equal(a["coordinates"], b["coordinates"])
+    np.testing.assert_array_equal(a["num_points_per_voxel"], b["num_points_per_voxel"])
+    np.testing.assert_array_equal(a["voxels"], b["voxels"])
+    assert a["coordinates"].dtype == np.int32 and a["voxels"].dtype == np.float32
+
+
+def test_kitti_size_cloud_full_grid(product, oracle):
+    """BASELINE size: car.fhd grid 1408x1600x40, ~17k voxels."""
+    pts = synth.kitti_cloud(1, 29000)
+    vs, r = [0.05, 0.05, 0.1], [0, -40, -3, 70.4, 40, 1]
+    a = product.utils.VoxelGeneratorV2(vs, r, 5, 40000).generate(pts, 40000)
+    b = oracle.utils.VoxelGeneratorV2(vs, r, 5, 40000).generate(pts, 40000)
+    assert a["voxel_num"] == b["voxel_num"] and 14000 < a["voxel_num"] < 22000
+    np.testing.assert_array_equal(a["coordinates"], b["coordinates"])
+    np.testing.assert_array_equal(a["num_points_per_voxel"], b["num_points_per_voxel"])
+    np.testing.assert_array_equal(a["voxels"], b["voxels"])
+    # size-independent properties: every kept point lies in its voxel; counts sum <= P; ids first-come
+    vox, co, num = a["voxels"], a["coordinates"], a["num_points_per_voxel"]
+    lo = np.array(r[:3], np.float32)
+    c = np.floor((vox[:, 0, :3] - lo) / np.array(vs, np.float32)).astype(np.int32)[:, ::-1]
+    np.testing.assert_array_equal(c, co)
+    assert num.min() >= 1 and num.max() <= 5 and num.sum() <= pts.shape[0]
+    assert len({tuple(x) for x in co.tolist()}) == co.shape[0]
+
+
+def test_generate_multi_gpu_padded(product, oracle):
+    rng = np.random.default_rng(9)
+    pts = cloud(rng, 3000)
+    args = ([0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 20000)
+    a = product.utils.VoxelGeneratorV2(*args).generate_multi_gpu(pts, 4000)
+    b = oracle.utils.VoxelGeneratorV2(*args).generate_multi_gpu(pts, 4000)
+    for k in ("voxels", "coordinates", "num_points_per_voxel"):
+        np.testing.assert_array_equal(a[k], b[k])
+    assert a["voxel_num"] == b["voxel_num"]
+
+
+@pytest.mark.parametrize("vfe_mode,nf", [(1, 4), (2, 4), (1, 3)])
+def test_batched_device_path_and_fused_mean(product, oracle, vfe_mode, nf):
+    rng = np.random.default_rng(11)
+    frames = [cloud(rng, n) for n in (4000, 0, 2500, 1)]
+    vs, r, T, mv = [0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 3000
+    gen = product.utils.VoxelGeneratorV2(vs, r, T, mv)
+    offs = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int32)
+    pts = torch.from_numpy(np.concatenate(frames, 0)).cuda()
+    res = gen.generate_device(pts, mv, frame_offsets=torch.from_numpy(offs).cuda(), batch=len(frames),
+                              vfe_mode=vfe_mode, vfe_num_features=nf)
+    torch.cuda.synchronize()
+    assert int(res["status"].item()) == 1  # frame 0 overflows max_voxels=3000 -> VOXEL_OVERFLOW bit
+    counts = res["num_voxels"].cpu().numpy()
+    og = oracle.utils.VoxelGeneratorV2(vs, r, T, mv)
+    row = 0
+    for b, f in enumerate(frames):
+        ref = og.generate(f, mv)
+        n = ref["voxel_num"]
+        assert counts[1 + b] == n
+        co = res["coordinates"][row:row + n].cpu().numpy()
+        np.testing.assert_array_equal(co[:, 0], np.full(n, b))
+        np.testing.assert_array_equal(co[:, 1:], ref["coordinates"])
+        np.testing.assert_array_equal(res["voxels"][row:row + n].cpu().numpy(), ref["voxels"])
+        np.testing.assert_array_equal(res["num_points_per_voxel"][row:row + n].cpu().numpy(),
+                                      ref["num_points_per_voxel"])
+        mean = ref["voxels"][:, :, :nf].sum(1) / ref["num_points_per_voxel"][:, None].astype(np.float32)
+        if vfe_mode == 2:
+            mean = np.concatenate([np.sqrt(mean[:, :1] ** 2 + mean[:, 1:2] ** 2), mean[:, 2:]], 1)
+        np.testing.assert_allclose(res["vfe"][row:row + n].cpu().numpy(), mean, rtol=1e-6, atol=1e-6)
+        # locator: every coordinate maps back to its row
+        row += n
+    assert counts[0] == row
