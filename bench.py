@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- point-clouds/sec of the SECOND LiDAR-inference hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2second|reference] [--config car.fhd]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (voxelize -> sparse middle -> BEV -> RPN -> decode/NMS) over one batch
+of synthetic clouds per GPU.  Frames shard over GPUs (weak scaling: the per-GPU batch is fixed) and every
+step ends with the single all-gather of detection records (N > 1).
+
+Prints ONE JSON line (rank 0):
+  value     whole-job clouds/s with the clouds already resident in HBM, CUDA-event timed per step, L2
+            flushed between steps, max over ranks
+  e2e       same metric through the public call with HOST (pinned) clouds: H2D of the points and D2H of the
+            detections inside the timed region
+  roofline  the dominant hand-written kernel (b2s_sparse_conv, all sparse layers of one step): algorithmic
+            bytes / CUDA-event time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the same network through the CPU oracle (`port`: C voxelizer/NMS + torch-CPU sparse conv/RPN)
+            on a bounded sample of the same workload, host cores of this box
+--impl reference: the reference arm = the reference's CPU implementation of the path.  spconv 1.x is not
+  in the reference tree and cannot be installed (no network), so this is the oracle port timed with all host
+  threads (DESIGN.md "reference arm").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "second.pytorch_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "point-clouds/sec (KITTI car.fhd synthetic, ~17k voxels)"
+UNIT = "clouds/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2second", choices=["b2second", "reference"])
+    ap.add_argument("--config", default="car.fhd")
+    ap.add_argument("--batch", type=int, default=8, help="frames per GPU per step (car.fhd eval batch_size: 8)")
+    ap.add_argument("--points", type=int, default=29000, help="points per synthetic cloud (29k -> ~17k voxels)")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_clouds(name, count, points, seed0=0):
+    from b2second import config, synth
+    cfg = config.get_config(name)
+    out = []
+    for s in range(count):
+        if "nuscenes" in name:
+            out.append(synth.nuscenes_cloud(seed0 + s, points))
+        else:
+            out.append(synth.kitti_cloud(seed0 + s, points, cfg.point_cloud_range))
+    return out
+
+
+def workload_desc(args, n_voxels=None):
+    d = {"workload": "%s.config inference, synthetic KITTI-range clouds" % args.config,
+         "points_per_cloud": args.points, "frames_per_gpu_per_step": args.batch,
+         "parallelism": "frames sharded dp%d, one all-gather of detections" % args.gpus,
+         "l2": "flushed between steps (512 MiB write), per-step CUDA events",
+         "rpn": "torch/cuDNN fp32 (TF32 off)", "precision": "fp32"}
+    if n_voxels is not None:
+        d["active_voxels_per_cloud"] = n_voxels
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_path_clouds_per_s(name, clouds, threads):
+    """the oracle port end to end on `clouds` (list of numpy clouds); returns (clouds/s, stage seconds)."""
+    from b2second import config, loader, models
+    oracle = loader.oracle_spconv()
+    cfg = config.get_config(name)
+    torch.set_num_threads(threads)
+    net = models.build_network(cfg, oracle).eval()
+    models.synthetic_weights_(net, name, seed=0)
+    anchors = torch.from_numpy(net.anchors()[None])
+    # warm (allocations, MKL thread pools, oracle scratch grid)
+    res = net.voxel_generator.generate(clouds[0], cfg.max_voxels)
+    t0 = time.perf_counter()
+    for pts in clouds:
+        res = net.voxel_generator.generate(pts, cfg.max_voxels)
+        coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+        ex = {"anchors": anchors, "voxels": torch.from_numpy(res["voxels"]),
+              "num_points": torch.from_numpy(res["num_points_per_voxel"]), "coordinates": torch.from_numpy(coords)}
+        with torch.no_grad():
+            net(ex)
+    dt = time.perf_counter() - t0
+    return len(clouds) / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    clouds = make_clouds(args.config, max(1, args.cpu_frames), args.points)
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_path_clouds_per_s(args.config, clouds[:1], threads)
+    vals = []
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_path_clouds_per_s(args.config, clouds, threads)
+        vals.append(v)
+        if time.perf_counter() - t_all > 150:   # keep the whole run within a few minutes
+            break
+    value = float(np.mean(vals))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * len(clouds) / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_desc(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d clouds per step, %d steps, whole hot path on host cores"
+                                       % (len(clouds), len(vals))},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active")
+                                                         for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from b2second import config, dist as b2dist, loader, models
+    from b2second.engine import InferenceEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sp = loader.product_spconv()
+    cfg = config.get_config(args.config)
+    net = models.build_network(cfg, sp).eval()
+    models.synthetic_weights_(net, args.config, seed=0)
+    net = net.to(dev)
+    B = args.batch
+    eng = InferenceEngine(net, batch_size=B, max_points=args.points + 1000, use_cuda_graph=True)
+    gather = b2dist.DetectionGatherer(B, eng.post_max, eng.code + 2, dev) if world > 1 else None
+    # distinct clouds per rank and per slot; two alternating batches so consecutive steps differ
+    n_sets = 2
+    clouds = make_clouds(args.config, n_sets * B, args.points, seed0=1000 * rank)
+    host = [[torch.from_numpy(c).pin_memory() for c in clouds[s * B:(s + 1) * B]] for s in range(n_sets)]
+    devc = [[h.to(dev) for h in hs] for hs in host]
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    h2d_bytes = sum(int(h.numel()) * 4 for h in host[0])
+    det_host = torch.empty_like(eng.det, device="cpu").pin_memory()
+    cnt_host = torch.empty_like(eng.det_count, device="cpu").pin_memory()
+    d2h_bytes = det_host.numel() * 4 + cnt_host.numel() * 4
+
+    def step_resident(i):
+        eng.infer(devc[i % n_sets])        # device->device staging of the batch + one graph replay
+        if gather is not None:
+            gather.gather(eng.det, eng.det_count)
+
+    def step_e2e(i):
+        eng.infer(host[i % n_sets])        # pinned host -> HBM inside the timed region
+        if gather is not None:
+            gather.gather(eng.det, eng.det_count)
+        det_host.copy_(eng.det, non_blocking=True)
+        cnt_host.copy_(eng.det_count, non_blocking=True)
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for i in range(steps):
+            flush.fill_(float(i))          # evict L2 between steps (outside the event pair)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(warmup + i)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    warm = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, warm)
+    ms_e2e = timed(step_e2e, args.steps, warm)
+    clocks = sampler.stop() if rank == 0 else None
+    eng.check_status()
+    frames = world * B * args.steps
+    value = frames / (ms_res / 1e3)
+    e2e = frames / (ms_e2e / 1e3)
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant hand-written kernel, measured live (eager replay, CUDA events per stage)
+    eng.load_points(devc[0])
+    stages = eng.run_timed(iters=5)
+    stats = eng.sparse_layer_stats()
+    n_vox = int(eng.num_voxels[0].item()) // B
+    conv_ms = sum(v for k, v in stages.items() if k.startswith("sparse_conv"))
+    conv_bytes = sum(s["bytes"] for s in stats)
+    conv_flops = sum(s["flops"] for s in stats)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0
+    roofline = {"kernel": "k_sparse_conv (all %d sparse layers of one step, %d frames)" % (len(stats), B),
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "measured" if peaks else "fallback",
+                "algorithmic_bytes_per_step": conv_bytes, "algorithmic_flops_per_step": conv_flops,
+                "ms_per_step": conv_ms,
+                "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0}
+    grouped = {}
+    for k, v in stages.items():
+        g = "sparse_conv" if k.startswith("sparse_conv") else ("rulebook" if k.startswith("rulebook") else k)
+        grouped[g] = grouped.get(g, 0.0) + v
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = clouds[:max(1, args.cpu_frames)]
+        v, dt = cpu_path_clouds_per_s(args.config, sample, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "%d clouds of the same workload (%.1f s), whole hot path: C voxelizer + torch-CPU "
+                                  "sparse conv/RPN + C NMS" % (len(sample), dt)}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b2second",
+            "config": workload_desc(args, n_vox),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": eng.kernel_launches_per_step() * args.steps,
+            "gpu_launches_per_step": eng.kernel_launches_per_step(),
+            "clocks": clocks, "roofline": roofline, "stage_ms_eager": grouped, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b2second arm has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,7 +120,7 @@ class InferenceEngine:
             bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) else None
             relu = bn is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
             K = int(np.prod(m.kernel_size))
-            lyr = {"conv": m, "K": K, "cin": m.in_channels, "cout": m.out_channels, "relu": relu,
+            lyr = {"index": len(self.layers), "conv": m, "K": K, "cin": m.in_channels, "cout": m.out_channels, "relu": relu,
                    "w": m.weight.detach().float().contiguous().view(K, m.in_channels, m.out_channels)}
             if bn is not None:
                 lyr["scale"], lyr["shift"] = _fold_bn(bn)
@@ -214,6 +214,7 @@ class InferenceEngine:
         L, lib, cfg = self._L, self.lib, self.cfg
         st = L.stream()
         self.status.zero_()
+        self._mark("voxelize")
         L.check(lib.b2s_voxelize(
             L.ptr(self.points), L.ptr(self.offsets), self.P_cap_used, self.F, self.B,
             L.f3(cfg.point_cloud_range[:3]), L.f3(cfg.voxel_size), L.i3(self.grid), self.T, self.max_voxels,
@@ -222,6 +223,7 @@ class InferenceEngine:
             L.ptr(self.vox_ws), self.vox_ws_bytes, L.ptr(self.status), st), "b2s_voxelize")
         if self.is_pillars:
             vx, vy, xo, yo = self.pfn_geom
+            self._mark("pfn")
             L.check(lib.b2s_pfn(L.ptr(self.points), self.F, L.ptr(self.vox_slots), L.ptr(self.vox_num),
                                 L.ptr(self.vox_coors), L.ptr(self.num_voxels), self.level0.cap, self.T,
                                 L.ptr(self.pfn_w), L.ptr(self.pfn_scale), L.ptr(self.pfn_shift), self.pfn_cout,
@@ -232,6 +234,7 @@ class InferenceEngine:
             for lyr in self.layers:
                 m, lin, lout = lyr["conv"], lyr["in_level"], lyr["out_level"]
                 if lyr["build_rb"]:
+                    self._mark("rulebook%d" % lyr["index"])
                     if m.subm:
                         L.check(lib.b2s_rulebook_subm(L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, L.i3(lin.shape),
                                                       L.i3(m.kernel_size), L.i3(m.dilation), L.ptr(lin.keys),
@@ -244,6 +247,7 @@ class InferenceEngine:
                             L.ptr(lin.vals), lin.hcap, L.ptr(lout.coors), L.ptr(lout.n_dev), lout.cap,
                             L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys), L.ptr(lout.vals), lout.hcap,
                             L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
+                self._mark("sparse_conv%d" % lyr["index"])
                 L.check(lib.b2s_sparse_conv(L.ptr(feats), lyr["cin"], L.ptr(lyr["w"]), L.ptr(lyr["rb"]["nbr"]),
                                             lyr["K"], L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
                                             L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
@@ -251,19 +255,23 @@ class InferenceEngine:
                 feats = lyr["out"]
         fl = self.final_level
         D, H, W = fl.shape
+        self._mark("to_bev")
         L.check(lib.b2s_to_bev(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
                                D, H, W, L.ptr(self.bev), 0, st), "b2s_to_bev")
+        self._mark("rpn")
         rpn = self.net.rpn
         x = rpn.backbone(self.bev)
         box = rpn.conv_box(x).contiguous()
         cls = rpn.conv_cls(x).contiguous()
         dirp = rpn.conv_dir_cls(x).contiguous() if cfg.use_direction_classifier else None
         self._keep = (x, box, cls, dirp)
+        self._mark("decode_filter")
         L.check(lib.b2s_decode_filter(
             L.ptr(box), L.ptr(cls), L.ptr(dirp), L.ptr(self.anchors), None, self.B, self.a_loc, self.fH, self.fW,
             self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
             L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
             L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter")
+        self._mark("nms")
         L.check(lib.b2s_nms(
             L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
             L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.B, self.cand_cap, self.code,
@@ -271,6 +279,56 @@ class InferenceEngine:
             1 if cfg.use_direction_classifier else 0, float(cfg.direction_offset),
             float(cfg.direction_limit_offset), cfg.num_direction_bins, self.range_host, L.ptr(self.det),
             L.ptr(self.det_count), L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
+        self._mark("end")
+
+    # ---------------------------------------------------------------- instrumentation
+    _marks = None
+
+    def _mark(self, name):
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
+
+    def run_timed(self, iters=5):
+        """eager (no graph) replay with a CUDA event before every stage; returns {stage: mean ms}."""
+        self.P_cap_used = self.P_cap
+        acc = {}
+        with torch.no_grad():
+            self._launch()     # warm
+            for _ in range(iters):
+                self._marks = []
+                self._launch()
+                torch.cuda.synchronize()
+                for (name, ev), (_, nxt) in zip(self._marks[:-1], self._marks[1:]):
+                    acc[name] = acc.get(name, 0.0) + ev.elapsed_time(nxt)
+                self._marks = None
+        return {k: v / iters for k, v in acc.items()}
+
+    def kernel_launches_per_step(self):
+        """how many of OUR kernels one pipeline pass launches (memsets and cuDNN kernels not counted)."""
+        n = 7                                    # b2s_voxelize: insert, flag_scan, scan_sums, assign, fill, gather, finish
+        if self.is_pillars:
+            n += 1                               # b2s_pfn
+        for lyr in self.layers:
+            if lyr["build_rb"]:
+                n += 1 if lyr["conv"].subm else 5   # subm_nbr | mark, popc_scan, scan_sums, emit, conv_nbr
+            n += 1                               # b2s_sparse_conv
+        return n + 1 + 1 + 3                     # to_bev, decode_filter, nms: select_sort + iou_mask + reduce
+
+    def sparse_layer_stats(self):
+        """sync; per sparse layer: rows in/out, pairs, algorithmic bytes and flops (SURVEY.md §8d formulas)."""
+        out = []
+        for lyr in self.layers:
+            n_out = int(lyr["out_level"].n_dev[0].item())
+            n_in = int(lyr["in_level"].n_dev[0].item())
+            pairs = int((lyr["rb"]["nbr"][:n_out] >= 0).sum().item())
+            cin, cout, K = lyr["cin"], lyr["cout"], lyr["K"]
+            out.append({"index": lyr["index"], "subm": bool(lyr["conv"].subm), "cin": cin, "cout": cout, "K": K,
+                        "n_in": n_in, "n_out": n_out, "pairs": pairs,
+                        "bytes": 4 * (n_in * cin + n_out * cout) + 8 * pairs + 4 * K * cin * cout,
+                        "flops": 2 * pairs * cin * cout})
+        return out
 
     # ---------------------------------------------------------------- public API
     def load_points(self, frames):

@@ -1,0 +1,45 @@
+"""helpers shared by the golden-fixture tests (CPU oracle path and GPU product path)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+
+from b2second import config, synth
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def cases():
+    out = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        base = os.path.basename(p)[:-4]
+        name, seed, n = base.rsplit(".", 2)
+        out.append((name, int(seed[4:]), int(n[1:]), p))
+    return out
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def make_cloud(name, seed, n):
+    cfg = config.get_config(name)
+    if "nuscenes" in name:
+        return synth.nuscenes_cloud(seed, n)
+    return synth.kitti_cloud(seed, n, cfg.point_cloud_range)
+
+
+def assert_detections_close(got, fix, box_tol=1e-4, score_tol=1e-5):
+    gb = np.asarray(got["box3d_lidar"], dtype=np.float32)
+    gs = np.asarray(got["scores"], dtype=np.float32)
+    gl = np.asarray(got["label_preds"]).astype(np.int64)
+    rb, rs, rl = fix["box3d_lidar"], fix["scores"], fix["label_preds"]
+    assert gb.shape == rb.shape, "detection count differs: got %d, golden %d" % (gb.shape[0], rb.shape[0])
+    np.testing.assert_allclose(gs, rs, rtol=0, atol=score_tol)
+    np.testing.assert_array_equal(gl, rl)
+    # angles are compared modulo 2*pi (direction fix-up adds multiples of the period)
+    np.testing.assert_allclose(gb[:, :6], rb[:, :6], rtol=0, atol=box_tol)
+    d = np.abs(gb[:, 6] - rb[:, 6])
+    d = np.minimum(d, np.abs(d - 2 * np.pi))
+    assert d.max(initial=0.0) < box_tol * 10, "yaw mismatch %g" % d.max()

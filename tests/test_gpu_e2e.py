@@ -1,0 +1,117 @@
+"""End-to-end GPU parity against the golden fixtures generated from the unmodified reference network
+(tests/golden/make_golden.py) and against the CPU oracle run on the box:
+  * module-by-module path: mirror VoxelNet on the CUDA spconv drop-in (same API calls the reference makes)
+  * fused engine path: b2second.engine.InferenceEngine (one CUDA graph, no host sync)
+Bars: voxel coordinates bit-exact (sha1), BEV features <= 1e-4, boxes <= 1e-4, scores <= 1e-5, labels equal."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from b2second import config, models
+
+pytestmark = pytest.mark.gpu
+CASES = gu.cases()
+IDS = [f"{c[0]}-s{c[1]}" for c in CASES]
+
+
+def build(name, backend, device):
+    net = models.build_network(config.get_config(name), backend).eval()
+    models.synthetic_weights_(net, name, seed=0)
+    return net.to(device)
+
+
+@pytest.fixture(autouse=True)
+def _fp32_convs():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+@pytest.mark.parametrize("name,seed,n,path", CASES, ids=IDS)
+def test_module_path_matches_golden(product, name, seed, n, path):
+    fix = np.load(path)
+    cfg = config.get_config(name)
+    pts = gu.make_cloud(name, seed, n)
+    net = build(name, product, "cuda")
+    res = net.voxel_generator.generate(pts, cfg.max_voxels)          # CUDA voxelizer behind the numpy API
+    assert res["voxel_num"] == int(fix["voxel_num"])
+    assert gu.sha(res["coordinates"]) == str(fix["coords_sha1"])
+    assert gu.sha(res["num_points_per_voxel"]) == str(fix["num_points_per_voxel_sha1"])
+    assert gu.sha(res["voxels"]) == str(fix["voxels_sha1"])
+    coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+    ex = {"anchors": torch.from_numpy(net.anchors()[None]).cuda(), "voxels": torch.from_numpy(res["voxels"]).cuda(),
+          "num_points": torch.from_numpy(res["num_points_per_voxel"]).cuda(),
+          "coordinates": torch.from_numpy(coords).cuda()}
+    with torch.no_grad():
+        vf = net.voxel_feature_extractor(ex["voxels"], ex["num_points"], ex["coordinates"])
+        sf = net.middle_feature_extractor(vf, ex["coordinates"], 1)
+        pd = net.rpn(sf)
+        out = net(ex)[0]
+    assert list(sf.shape) == fix["bev_shape"].tolist()
+    assert int((sf != 0).sum()) == int(fix["bev_nonzero"])
+    np.testing.assert_allclose(sf.flatten()[torch.from_numpy(fix["bev_sel_idx"]).cuda()].cpu().numpy(),
+                               fix["bev_sel_val"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pd["box_preds"].flatten()[torch.from_numpy(fix["box_sel_idx"]).cuda()].cpu().numpy(),
+                               fix["box_sel_val"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(pd["cls_preds"].flatten()[torch.from_numpy(fix["cls_sel_idx"]).cuda()].cpu().numpy(),
+                               fix["cls_sel_val"], rtol=1e-4, atol=1e-4)
+    gu.assert_detections_close({k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}, fix)
+
+
+@pytest.mark.parametrize("name,seed,n,path", CASES, ids=IDS)
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_engine_matches_golden(product, name, seed, n, path, graph):
+    from b2second.engine import InferenceEngine
+    fix = np.load(path)
+    pts = gu.make_cloud(name, seed, n)
+    net = build(name, product, "cuda")
+    eng = InferenceEngine(net, batch_size=1, max_points=max(n, 1000), use_cuda_graph=graph)
+    eng.infer([torch.from_numpy(pts).cuda()])
+    if graph:   # replay twice: the graph must be re-entrant over its static buffers
+        eng.infer([torch.from_numpy(pts).cuda()])
+    out = eng.detections()[0]
+    assert int(eng.num_voxels[0].item()) == int(fix["voxel_num"])
+    assert int(eng.cand_count[0].item()) == int(fix["num_pass_threshold"])
+    gu.assert_detections_close({k: (v.numpy() if hasattr(v, "numpy") else v) for k, v in out.items()}, fix)
+
+
+def test_engine_batched_frames_match_single_frames(product):
+    """frames shard without interaction: a batch of 3 different clouds == the 3 clouds run alone."""
+    from b2second.engine import InferenceEngine
+    name = "car.fhd"
+    net = build(name, product, "cuda")
+    clouds = [gu.make_cloud(name, s, n) for s, n in ((0, 20000), (3, 15000), (1, 29000))]
+    single = InferenceEngine(net, batch_size=1, max_points=30000, use_cuda_graph=False)
+    ref = []
+    for c in clouds:
+        single.infer([torch.from_numpy(c).cuda()])
+        ref.append(single.detections()[0])
+    eng = InferenceEngine(net, batch_size=3, max_points=30000, use_cuda_graph=True)
+    eng.infer([torch.from_numpy(c).cuda() for c in clouds])
+    got = eng.detections()
+    for g, r in zip(got, ref):
+        assert g["box3d_lidar"].shape == r["box3d_lidar"].shape and r["box3d_lidar"].shape[0] > 0
+        torch.testing.assert_close(g["box3d_lidar"], r["box3d_lidar"], rtol=0, atol=1e-4)
+        torch.testing.assert_close(g["scores"], r["scores"], rtol=0, atol=1e-5)
+        assert torch.equal(g["label_preds"], r["label_preds"])
+
+
+def test_module_path_against_live_cpu_oracle(product, oracle):
+    """same comparison without fixtures: oracle run on this box's CPU vs the CUDA drop-in, new seed."""
+    name = "car.lite"
+    cfg = config.get_config(name)
+    pts = gu.make_cloud(name, 7, 18000)
+    out = {}
+    for key, backend, dev in (("cpu", oracle, "cpu"), ("gpu", product, "cuda")):
+        net = build(name, backend, dev)
+        res = net.voxel_generator.generate(pts, cfg.max_voxels)
+        coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+        ex = {"anchors": torch.from_numpy(net.anchors()[None]).to(dev), "voxels": torch.from_numpy(res["voxels"]).to(dev),
+              "num_points": torch.from_numpy(res["num_points_per_voxel"]).to(dev),
+              "coordinates": torch.from_numpy(coords).to(dev)}
+        with torch.no_grad():
+            out[key] = net(ex)[0]
+    fix = {k: out["cpu"][k].numpy() for k in ("box3d_lidar", "scores", "label_preds")}
+    gu.assert_detections_close({k: out["gpu"][k].cpu().numpy() for k in fix}, fix)
+    assert fix["box3d_lidar"].shape[0] > 0
