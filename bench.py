@@ -100,11 +100,21 @@ def cpu_path_clouds_per_s(name, clouds, threads):
     return len(clouds) / dt, dt
 
 
+def cpu_threads():
+    """torch-CPU intra-op threads for the CPU arm.  The sparse middle is thousands of tiny gather/mm/index_add
+    calls; on the 128-core GPU host, 128 intra-op threads made the same path ~200x SLOWER than 8-16 threads
+    (measured round 1), so the arm uses the thread count that the path can actually exploit."""
+    env = os.environ.get("B2S_CPU_THREADS")
+    if env:
+        return int(env)
+    return min(os.cpu_count() or 1, 16)
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     clouds = make_clouds(args.config, max(1, args.cpu_frames), args.points)
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_path_clouds_per_s(args.config, clouds[:1], threads)
@@ -279,7 +289,7 @@ def run_gpu_arm(args):
         grouped[g] = grouped.get(g, 0.0) + v
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = cpu_threads()
         sample = clouds[:max(1, args.cpu_frames)]
         v, dt = cpu_path_clouds_per_s(args.config, sample, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",

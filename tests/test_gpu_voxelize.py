@@ -74,7 +74,7 @@ def test_generate_multi_gpu_padded(product, oracle):
 def test_batched_device_path_and_fused_mean(product, oracle, vfe_mode, nf):
     rng = np.random.default_rng(11)
     frames = [cloud(rng, n) for n in (4000, 0, 2500, 1)]
-    vs, r, T, mv = [0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 2000
+    vs, r, T, mv = [0.05, 0.05, 0.1], [0, -4, -3, 7.04, 4, 1], 5, 1500
     gen = product.utils.VoxelGeneratorV2(vs, r, T, mv)
     offs = np.cumsum([0] + [f.shape[0] for f in frames]).astype(np.int32)
     pts = torch.from_numpy(np.concatenate(frames, 0)).cuda()
