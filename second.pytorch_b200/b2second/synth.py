@@ -66,7 +66,7 @@ def nuscenes_cloud(seed, num_points=300000, sweeps=10, pc_range=(-50, -50, -5, 5
     """-> float32 [P,4] (x,y,z,dt): 10 merged 360-degree sweeps, ego drifting forward."""
     rng = np.random.default_rng(seed)
     elev = np.linspace(-30.0, 10.0, 32)
-    azim = np.arange(-180.0, 180.0, 0.33)
+    azim = np.arange(-180.0, 180.0, 0.28)
     per = []
     for s in range(sweeps):
         rs = np.random.default_rng(seed)  # same scene, shifted ego

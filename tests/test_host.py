@@ -1,0 +1,108 @@
+"""Host-side logic that needs neither GPU nor reference: config dataclasses / prototxt reader, anchors, model
+structure (state-dict key convention second.pytorch checkpoints use), synthetic data."""
+import numpy as np
+import pytest
+import torch
+
+from b2second import anchors, config, models, synth
+
+PROTO = """
+model: { second: {
+  voxel_generator { point_cloud_range : [0, -40, -3, 70.4, 40, 1]  voxel_size : [0.05, 0.05, 0.1]
+                    max_number_of_points_per_voxel : 5 }   # a comment
+  voxel_feature_extractor: { module_class_name: "SimpleVoxel" num_filters: [16] with_distance: false num_input_features: 4 }
+  middle_feature_extractor: { module_class_name: "SpMiddleFHD" downsample_factor: 8 num_input_features: 4 }
+  rpn: { module_class_name: "RPNV2" layer_nums: [5] layer_strides: [1] num_filters: [128] upsample_strides: [1]
+         num_upsample_filters: [128] use_groupnorm: false num_groups: 32 num_input_features: 128 }
+  num_point_features: 4 use_sigmoid_score: true encode_background_as_zeros: true use_direction_classifier: true
+  num_direction_bins: 2 direction_limit_offset: 1 post_center_limit_range: [0, -40, -2.2, 70.4, 40, 0.8]
+  target_assigner: { class_settings: {
+      anchor_generator_range: { sizes: [1.6, 3.9, 1.56] anchor_ranges: [0, -40.0, -1.00, 70.4, 40.0, -1.00] rotations: [0, 1.57] }
+      class_name: "Car" use_rotate_nms: true use_multi_class_nms: false nms_pre_max_size: 1000 nms_post_max_size: 100
+      nms_score_threshold: 0.3 nms_iou_threshold: 0.01 } }
+}}
+eval_input_reader: { batch_size: 8 preprocess: { max_number_of_voxels: 40000 anchor_area_threshold: -1 } }
+"""
+
+
+def test_prototxt_reader_matches_builtin():
+    parsed = config.ModelConfig.from_prototxt(PROTO, "car.fhd")
+    builtin = config.get_config("car.fhd")
+    for f in builtin.__dataclass_fields__:
+        assert getattr(parsed, f) == getattr(builtin, f), f
+
+
+def test_derived_sizes():
+    sizes = {"car.fhd": ([1408, 1600, 40], [1, 200, 176], 70400, 2),
+             "car.lite": ([1056, 1280, 40], [1, 160, 132], 42240, 2),
+             "all.fhd": ([1056, 1280, 40], [1, 160, 132], 168960, 8),
+             "pointpillars.car.xyres_16": ([432, 496, 1], [1, 248, 216], 107136, 2),
+             "nuscenes.all.pp.largea": ([400, 400, 1], [1, 50, 50], 30000, 12)}
+    for name, (grid, fmap, A, aloc) in sizes.items():
+        c = config.get_config(name)
+        assert c.grid_size.tolist() == grid and c.feature_map_size == fmap
+        assert c.num_anchors_per_loc == aloc
+        a = anchors.generate_anchors(c)
+        assert a.shape == (A, 7) and a.dtype == np.float32
+
+
+def test_anchor_layout_matches_head_layout():
+    c = config.get_config("car.fhd")
+    a = anchors.generate_anchors(c).reshape(2, 200, 176, 7)          # (rot, y, x)
+    assert np.all(a[0, :, :, 6] == 0) and np.allclose(a[1, :, :, 6], 1.57)
+    assert a[0, 0, 0, 0] == 0 and np.isclose(a[0, 0, -1, 0], 70.4) and np.isclose(a[0, -1, 0, 1], 40.0)
+    assert np.all(np.diff(a[0, 0, :, 0]) > 0) and np.all(np.diff(a[0, :, 0, 1]) > 0)
+    assert np.allclose(a[..., 3:6], [1.6, 3.9, 1.56]) and np.allclose(a[..., 2], -1.0)
+
+
+@pytest.mark.parametrize("name,nkeys", [("car.fhd", 133), ("pointpillars.car.xyres_16", 127)])
+def test_state_dict_keys_follow_reference_convention(oracle, name, nkeys):
+    net = models.build_network(name, oracle)
+    sd = net.state_dict()
+    assert len(sd) == nkeys                      # reference has +16 training-metric buffers
+    assert "global_step" in sd and "rpn.conv_cls.bias" in sd and "rpn.blocks.0.1.weight" in sd
+    if name == "car.fhd":
+        assert sd["middle_feature_extractor.middle_conv.0.weight"].shape == (3, 3, 3, 4, 16)
+        assert sd["middle_feature_extractor.middle_conv.39.weight"].shape == (3, 1, 1, 64, 64)
+        assert sd["rpn.deblocks.0.0.weight"].shape == (128, 128, 1, 1)
+    else:
+        assert sd["voxel_feature_extractor.pfn_layers.0.linear.weight"].shape == (64, 9)
+        assert sd["rpn.deblocks.2.0.weight"].shape == (256, 128, 4, 4)
+
+
+def test_synthetic_weights_are_reproducible(oracle):
+    a = models.synthetic_weights_(models.build_network("car.lite", oracle), "car.lite")
+    b = models.synthetic_weights_(models.build_network("car.lite", oracle), "car.lite")
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
+
+
+def test_synthetic_clouds():
+    p = synth.kitti_cloud(0, 20000)
+    assert p.shape == (20000, 4) and p.dtype == np.float32
+    assert p[:, 0].min() >= 0 and p[:, 0].max() < 70.4 and np.abs(p[:, 1]).max() <= 40
+    assert np.array_equal(p, synth.kitti_cloud(0, 20000)) and not np.array_equal(p, synth.kitti_cloud(1, 20000))
+    q = synth.nuscenes_cloud(0, 50000)
+    assert q.shape == (50000, 4) and np.allclose(np.unique(q[:, 3]), 0.05 * np.arange(10), atol=1e-6)
+
+
+def test_forward_contract_on_oracle(oracle):
+    """dict in, list of dicts out; empty cloud -> zero-length tensors (voxelnet.py:629-643)."""
+    cfg = config.get_config("car.lite")
+    net = models.synthetic_weights_(models.build_network(cfg, oracle).eval(), "car.lite")
+    pts = synth.kitti_cloud(2, 3000, cfg.point_cloud_range)
+    res = net.voxel_generator.generate(pts, cfg.max_voxels)
+    coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+    ex = {"anchors": torch.from_numpy(net.anchors()[None]), "voxels": torch.from_numpy(res["voxels"]),
+          "num_points": torch.from_numpy(res["num_points_per_voxel"]), "coordinates": torch.from_numpy(coords),
+          "metadata": [{"image_idx": 7}]}
+    with torch.no_grad():
+        out = net(ex)
+    assert isinstance(out, list) and len(out) == 1
+    assert set(out[0]) == {"box3d_lidar", "scores", "label_preds", "metadata"}
+    assert out[0]["metadata"] == {"image_idx": 7} and out[0]["box3d_lidar"].shape[1] == 7
+    assert out[0]["label_preds"].dtype == torch.int64
+    with pytest.raises(AssertionError, match="num_anchors"):
+        bad = dict(ex)
+        bad["anchors"] = ex["anchors"][:, :100]
+        net(bad)

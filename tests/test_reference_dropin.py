@@ -1,0 +1,100 @@
+"""Container-only (needs /root/reference): the UNMODIFIED reference code against this repository.
+  * the hand-written config dataclasses equal the parsed reference config files
+  * anchors equal the reference's TargetAssigner output bit for bit
+  * the mirror network has the reference's state-dict keys/shapes and gives the same detections on the oracle
+  * the reference's own builders construct VoxelNet on top of the CUDA drop-in `spconv` (import-level drop-in;
+    running it needs a GPU, which this container does not have)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from b2second import config, loader, models, refcompat, synth
+
+pytestmark = pytest.mark.skipif(not refcompat.reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref_env():
+    # the reference imports its plugin by the name `spconv`: make that name the CPU oracle for this module's
+    # tests (other test modules in the same process use the CUDA drop-in under that name), then restore
+    saved = {k: v for k, v in sys.modules.items() if k == "spconv" or k.startswith("spconv.")}
+    for k in saved:
+        del sys.modules[k]
+    saved_path = list(sys.path)
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != os.path.abspath(loader.PRODUCT_DIR)] + \
+        [loader.PRODUCT_DIR]
+    refcompat.install(loader.ORACLE_DIR)
+    import spconv
+    assert getattr(spconv, "__oracle__", False)
+    yield spconv
+    for k in [k for k in sys.modules if k == "spconv" or k.startswith("spconv.")]:
+        del sys.modules[k]
+    sys.modules.update(saved)
+    sys.path[:] = saved_path
+
+
+@pytest.mark.parametrize("name", sorted(config.BUILTIN))
+def test_builtin_config_equals_reference_file(name):
+    path = os.path.join(refcompat.REFERENCE_ROOT, "second", "configs", config.REFERENCE_FILES[name])
+    parsed = config.ModelConfig.from_file(path, name)
+    builtin = config.get_config(name)
+    for f in builtin.__dataclass_fields__:
+        assert getattr(parsed, f) == getattr(builtin, f), f
+
+
+@pytest.mark.parametrize("name", ["car.fhd", "all.fhd", "pointpillars.car.xyres_16", "nuscenes.all.pp.largea"])
+def test_mirror_equals_reference_network(ref_env, name):
+    cfgp = refcompat.load_config(config.REFERENCE_FILES[name])
+    ref = refcompat.build_network(cfgp.model.second).eval()
+    mine = models.build_network(name, ref_env).eval()
+    sd_r, sd_m = ref.state_dict(), mine.state_dict()
+    assert set(sd_m) <= set(sd_r)
+    assert all(k.split(".")[0].startswith("rpn_") for k in set(sd_r) - set(sd_m))   # training metric buffers only
+    for k in sd_m:
+        assert sd_m[k].shape == sd_r[k].shape and sd_m[k].dtype == sd_r[k].dtype, k
+    models.synthetic_weights_(ref, name)
+    mine.load_reference_state_dict(ref.state_dict())            # reference checkpoints load unchanged
+    a_ref = refcompat.generate_anchors(ref, cfgp.model.second)
+    assert np.array_equal(a_ref, mine.anchors())
+    if name != "car.fhd":
+        return                                                   # forward equality: one config is enough here
+    b = config.get_config(name)
+    pts = synth.kitti_cloud(4, 12000, b.point_cloud_range)
+    res = ref.voxel_generator.generate(pts, b.max_voxels)
+    coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+
+    def ex():
+        return {"anchors": torch.from_numpy(a_ref[None].copy()), "voxels": torch.from_numpy(res["voxels"]),
+                "num_points": torch.from_numpy(res["num_points_per_voxel"]), "coordinates": torch.from_numpy(coords)}
+    with torch.no_grad():
+        o_r, o_m = ref(ex())[0], mine(ex())[0]
+    assert o_r["box3d_lidar"].shape == o_m["box3d_lidar"].shape and o_r["box3d_lidar"].shape[0] > 0
+    assert torch.allclose(o_r["box3d_lidar"], o_m["box3d_lidar"], atol=1e-6)
+    assert torch.equal(o_r["label_preds"], o_m["label_preds"])
+
+
+def test_reference_builds_on_cuda_dropin_in_subprocess():
+    """`import spconv` == second.pytorch_b200/spconv; the reference's second_builder constructs VoxelNet on it."""
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+from b2second import refcompat, loader, config
+refcompat.install(loader.PRODUCT_DIR)
+import spconv
+assert not getattr(spconv, "__oracle__", False) and spconv.__version__.endswith("b2second")
+for f in ("car.fhd.config", "car.lite.config", "pointpillars/car/xyres_16.config"):
+    cfg = refcompat.load_config(f)
+    net = refcompat.build_network(cfg.model.second)
+    mods = [m for m in net.modules() if isinstance(m, spconv.SparseConvolution)]
+    print(f, type(net).__module__, len(net.state_dict()), len(mods))
+    assert type(net).__module__ == "second.pytorch.models.voxelnet"
+print("OK")
+""" % loader.PRODUCT_DIR
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+    assert "car.fhd.config second.pytorch.models.voxelnet 149 14" in r.stdout
