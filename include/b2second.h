@@ -84,8 +84,10 @@ int b2s_voxelize(const float *points, const int *frame_offsets_dev, int num_poin
                  const int *grid /*host[3] xyz*/, int max_points, int max_voxels, int *coors,
                  int *num_points_per_voxel, int *point_slots, float *voxels, int vfe_mode,
                  int vfe_num_features, float *vfe_out, int *num_voxels_dev,
-                 unsigned long long *hash_keys, int *hash_vals, int hash_cap, void *workspace,
-                 size_t workspace_bytes, unsigned *status_dev, void *stream);
+                 unsigned long long *hash_keys, int *hash_vals, int hash_cap,
+                 int hash_key_depth /*D of the flat (b,z,y,x) hash key = spatial_shape[0] of the tensor that will
+                                      look rows up (SECOND: grid_z + 1, middle.py:139); 0 = grid z*/,
+                 void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream);
 
 /* ---- rulebook --------------------------------------------------------------------------------- */
 /* coordinate -> row hash over `shape` (D,H,W).  hash_cap must be a power of two >= 2*cap_rows. */
@@ -132,6 +134,23 @@ int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const in
 int b2s_to_bev(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C,
                int batch, int D, int H, int W, float *out, int layout, void *stream);
 
+/* BEV map for the tensor-core RPN: NHWC with a one-pixel zero halo, [B, H+2, W+2, C*D], as two planes
+ * hi = tf32-rounded value, lo = value - hi (the 3xTF32 split b2s_conv2d_tc consumes). */
+int b2s_to_bev_tc(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch,
+                  int D, int H, int W, float *out_hi, float *out_lo, void *stream);
+
+/* ---- dense RPN convolution on the tensor pipe (second/pytorch/models/rpn.py:467-497 blocks, :264-299 deblocks,
+ *      :386-391 heads): 3x3 stride-1 pad-1 (taps=9) or 1x1 (taps=1) conv + per-channel scale/shift (+ReLU).
+ * tcgen05 implicit GEMM, fp32-grade accuracy through the 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi).
+ *   in_hi/in_lo  [B, H+2, W+2, Cin]   NHWC + zero halo, hi/lo planes (Cin multiple of 32)
+ *   w_hi/w_lo    [taps, n_pad, Cin]   tap = ky*3+kx, w[tap][co][ci] = W_torch[co][ci][ky][kx]; rows >= Cout zero;
+ *                                     n_pad in {32, 64, 128}
+ *   out_hi       [B, H+2, W+2, out_stride] interior only (out_padded=1) or [B, H, W, out_stride] (out_padded=0);
+ *   out_lo       same shape or NULL (then out_hi holds the full fp32 value, e.g. for the heads). */
+int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int batch, int H, int W, int Cin, const float *w_hi,
+                  const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
+                  int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream);
+
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,
             const int *coors, const int *num_rows_dev, int cap_rows, int max_points,
@@ -150,6 +169,16 @@ int b2s_decode_filter(const float *box, const float *cls, const float *dir, cons
                       int ncls, int nbins, float score_thresh, float *cand_box, float *cand_score,
                       int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev,
                       int cand_cap, unsigned *status_dev, void *stream);
+
+/* same, for head tensors with arbitrary strides (elements): value(b, ch, pixel) = t[b*batch_stride + ch*ch_stride
+ * + pixel*pix_stride]; e.g. the packed NHWC record b2s_conv2d_tc writes (box at +0, cls at +14, dir at +16 of a
+ * 32-float pixel record: ch_stride 1, pix_stride 32, batch_stride H*W*32 for all three). */
+int b2s_decode_filter_strided(const float *box, const float *cls, const float *dir, long long box_batch_stride,
+                              long long cls_batch_stride, long long dir_batch_stride, int ch_stride, int pix_stride,
+                              const float *anchors, const uint8_t *anchors_mask, int batch, int a_loc, int H, int W,
+                              int code, int ncls, int nbins, float score_thresh, float *cand_box,
+                              float *cand_score, int *cand_label, int *cand_dir, int *cand_anchor,
+                              int *cand_count_dev, int cand_cap, unsigned *status_dev, void *stream);
 
 /* ---- top-k + NMS + direction/range epilogue ------------------------------------------------------ */
 size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max);

@@ -18,6 +18,8 @@ capacity-sized buffers, so the whole frame batch is ONE CUDA graph:
 Output per batch: ``det [B, post_max, code+2]`` (box, score, label) + ``det_count [B]`` -- the fixed-stride
 record the multi-GPU path all-gathers.
 """
+import ctypes
+
 import numpy as np
 import torch
 from torch import nn
@@ -38,6 +40,10 @@ def _fold_bn(bn):
     return scale, shift
 
 
+def ctypes_ptr(addr):
+    return ctypes.c_void_p(int(addr))
+
+
 class _Level:
     """one active-site set: coordinates, device count, coordinate->row hash, row capacity."""
     __slots__ = ("coors", "n_dev", "keys", "vals", "hcap", "cap", "shape")
@@ -45,7 +51,7 @@ class _Level:
 
 class InferenceEngine:
     def __init__(self, net, batch_size=1, max_points=None, max_voxels=None, row_cap_factor=2.0,
-                 cand_cap=None, use_cuda_graph=True):
+                 cand_cap=None, use_cuda_graph=True, rpn_impl="auto"):
         import spconv as sp                      # the CUDA drop-in: fails loudly if the library is missing
         assert not getattr(sp, "__oracle__", False), "the engine is the product path; it never runs on the oracle"
         self.sp = sp
@@ -69,8 +75,18 @@ class InferenceEngine:
         self.code = cfg.box_code_size
         self.use_graph = use_cuda_graph
         self._graph = None
+        # RPN: "tc" = hand-written tcgen05 implicit GEMM (csrc/conv_tc.cu, 3xTF32), "cudnn" = torch/cuDNN fp32.
+        from . import tc as _tc
+        if rpn_impl == "auto":
+            rpn_impl = "tc" if _tc.supported(net.rpn) else "cudnn"
+        assert rpn_impl in ("tc", "cudnn")
+        if rpn_impl == "tc" and not _tc.supported(net.rpn):
+            raise ValueError("rpn_impl='tc': this RPN has strided/upsampling stages (cuDNN only this round)")
+        self.rpn_impl = rpn_impl
         self._plan_middle(row_cap_factor)
         self._alloc_voxel_buffers()
+        if rpn_impl == "tc":
+            self._alloc_tc_rpn(_tc)
         self._alloc_detect_buffers(cand_cap)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -185,6 +201,27 @@ class InferenceEngine:
         D, H, W = self.final_level.shape
         self.bev = torch.zeros(self.B, C * D, H, W, dtype=torch.float32, device=dev)
 
+    def _alloc_tc_rpn(self, _tc):
+        """buffers of the tensor-core RPN: NHWC halo-padded hi/lo planes (halo zero-filled once, never written)."""
+        dev, B = self.dev, self.B
+        D, H, W = self.final_level.shape
+        C = self.feat_final_c * D
+        self.tc_plan = _tc.plan_rpn(self.net.rpn)
+        assert self.tc_plan[0]["cin"] == C, "BEV channels %d != RPN input %d" % (C, self.tc_plan[0]["cin"])
+
+        def plane(c):
+            return (torch.zeros(B, H + 2, W + 2, c, dtype=torch.float32, device=dev),
+                    torch.zeros(B, H + 2, W + 2, c, dtype=torch.float32, device=dev))
+        self.tc_bev = plane(C)
+        cmax = max(l["cout"] for l in self.tc_plan[:-1])
+        self.tc_ping, self.tc_pong = plane(cmax), plane(cmax)
+        for l in self.tc_plan[:-1]:
+            assert l["cout"] == cmax, "engine: uniform channel width expected in the tensor-core RPN"
+        self.tc_head_stride = 32
+        assert self.tc_plan[-1]["cout"] <= 32
+        self.tc_heads = torch.zeros(B, H, W, self.tc_head_stride, dtype=torch.float32, device=dev)
+        self.tc_hw = (H, W)
+
     def _alloc_detect_buffers(self, cand_cap):
         cfg, dev = self.cfg, self.dev
         anchors = torch.from_numpy(self.net.anchors()).to(dev)
@@ -220,6 +257,7 @@ class InferenceEngine:
             L.f3(cfg.point_cloud_range[:3]), L.f3(cfg.voxel_size), L.i3(self.grid), self.T, self.max_voxels,
             L.ptr(self.vox_coors), L.ptr(self.vox_num), L.ptr(self.vox_slots), None, self.vfe_mode, self.vfe_nf,
             L.ptr(self.vfe_out), L.ptr(self.num_voxels), L.ptr(self.vox_keys), L.ptr(self.vox_vals), self.vox_hcap,
+            int(self.level0.shape[0]),       # hash keys in the middle encoder's shape (grid_z + 1, middle.py:139)
             L.ptr(self.vox_ws), self.vox_ws_bytes, L.ptr(self.status), st), "b2s_voxelize")
         if self.is_pillars:
             vx, vy, xo, yo = self.pfn_geom
@@ -255,6 +293,9 @@ class InferenceEngine:
                 feats = lyr["out"]
         fl = self.final_level
         D, H, W = fl.shape
+        if self.rpn_impl == "tc":
+            self._launch_tc_tail(feats)
+            return
         self._mark("to_bev")
         L.check(lib.b2s_to_bev(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
                                D, H, W, L.ptr(self.bev), 0, st), "b2s_to_bev")
@@ -271,6 +312,57 @@ class InferenceEngine:
             self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
             L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
             L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter")
+        self._mark("nms")
+        L.check(lib.b2s_nms(
+            L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
+            L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.B, self.cand_cap, self.code,
+            1 if cfg.use_rotate_nms else 0, self.pre_max, self.post_max, float(cfg.nms_iou_threshold),
+            1 if cfg.use_direction_classifier else 0, float(cfg.direction_offset),
+            float(cfg.direction_limit_offset), cfg.num_direction_bins, self.range_host, L.ptr(self.det),
+            L.ptr(self.det_count), L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
+        self._mark("end")
+
+    def _launch_tc_tail(self, feats):
+        """BEV (NHWC, halo, hi/lo) -> tcgen05 RPN layers -> packed heads -> decode/filter -> NMS."""
+        L, lib, cfg = self._L, self.lib, self.cfg
+        st = L.stream()
+        fl = self.final_level
+        D, H, W = fl.shape
+        self._mark("to_bev")
+        L.check(lib.b2s_to_bev_tc(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
+                                  D, H, W, L.ptr(self.tc_bev[0]), L.ptr(self.tc_bev[1]), st), "b2s_to_bev_tc")
+        self._mark("rpn")
+        src = self.tc_bev
+        bufs = [self.tc_ping, self.tc_pong]
+        for i, lyr in enumerate(self.tc_plan[:-1]):
+            dst = bufs[i % 2]
+            L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, lyr["cin"], L.ptr(lyr["w_hi"]),
+                                      L.ptr(lyr["w_lo"]), lyr["taps"], lyr["cout"], lyr["n_pad"], L.ptr(lyr["scale"]),
+                                      L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(dst[0]), L.ptr(dst[1]), 1,
+                                      lyr["cout"], st), "b2s_conv2d_tc")
+            src = dst
+        hd = self.tc_plan[-1]
+        S = self.tc_head_stride
+        L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, hd["cin"], L.ptr(hd["w_hi"]),
+                                  L.ptr(hd["w_lo"]), 1, hd["cout"], hd["n_pad"], None, L.ptr(hd["shift"]), 0,
+                                  L.ptr(self.tc_heads), None, 0, S, st), "b2s_conv2d_tc(heads)")
+        self._mark("decode_filter")
+        offs = hd["head_offsets"]
+        heads = self.tc_heads
+        esz = heads.element_size()
+        box_p = ctypes_ptr(heads.data_ptr() + offs[0] * esz)
+        cls_p = ctypes_ptr(heads.data_ptr() + offs[1] * esz)
+        dir_p = ctypes_ptr(heads.data_ptr() + offs[2] * esz) if cfg.use_direction_classifier else None
+        bs = H * W * S
+        L.check(lib.b2s_decode_filter_strided(
+            box_p, cls_p, dir_p, bs, bs, bs, 1, S, L.ptr(self.anchors), None, self.B, self.a_loc, self.fH, self.fW,
+            self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
+            L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
+            L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter_strided")
+        self._launch_nms(st)
+
+    def _launch_nms(self, st):
+        L, lib, cfg = self._L, self.lib, self.cfg
         self._mark("nms")
         L.check(lib.b2s_nms(
             L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
@@ -314,6 +406,8 @@ class InferenceEngine:
             if lyr["build_rb"]:
                 n += 1 if lyr["conv"].subm else 5   # subm_nbr | mark, popc_scan, scan_sums, emit, conv_nbr
             n += 1                               # b2s_sparse_conv
+        if self.rpn_impl == "tc":
+            n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
         return n + 1 + 1 + 3                     # to_bev, decode_filter, nms: select_sort + iou_mask + reduce
 
     def sparse_layer_stats(self):

@@ -28,6 +28,29 @@ __global__ void k_to_bev(const float *__restrict__ feat, const int *__restrict__
     out[idx] = v;
 }
 
+// tensor-core RPN input: NHWC + one-pixel zero halo, hi/lo (3xTF32) planes
+__global__ void k_to_bev_tc(const float *__restrict__ feat, const int *__restrict__ coors,
+                            const int *__restrict__ n_dev, int cap_rows, int C, int batch, int D, int H, int W,
+                            float *__restrict__ out_hi, float *__restrict__ out_lo)
+{
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = min(*n_dev, cap_rows);
+    if (gid >= (long long)n * C) return;
+    int row = (int)(gid / C), c = (int)(gid % C);
+    int4 q = __ldg(reinterpret_cast<const int4 *>(coors + (size_t)row * 4));  // b,z,y,x
+    if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
+        (unsigned)q.w >= (unsigned)W)
+        return;
+    float v = __ldg(&feat[gid]);
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    float hi = __uint_as_float(u);
+    size_t CD = (size_t)C * D;
+    size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
+    out_hi[idx] = hi;
+    out_lo[idx] = v - hi;
+}
+
 // PointPillars PFN (single layer): one warp per pillar; lane l owns output channels l, l+32, ...
 // decorate each point with (xyz - mean xyz) and (xy - pillar centre), Linear(F+5 -> COUT), BN, ReLU,
 // max over the T slots (padded slots contribute relu(shift), exactly like the masked zero rows upstream).
@@ -111,6 +134,22 @@ extern "C" int b2s_to_bev(const float *feat, const int *coors, const int *num_ro
     if (cap_rows > 0) {
         k_to_bev<<<b2s_cdiv((long long)cap_rows * C, kThreads), kThreads, 0, stream>>>(
             feat, coors, num_rows_dev, cap_rows, C, batch, D, H, W, out, layout);
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}
+
+extern "C" int b2s_to_bev_tc(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C,
+                             int batch, int D, int H, int W, float *out_hi, float *out_lo, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(C >= 1 && batch >= 1 && D >= 1 && H >= 1 && W >= 1, "b2s_to_bev_tc: bad sizes");
+    size_t total = (size_t)batch * (H + 2) * (W + 2) * C * D;
+    B2S_CUDA_OK(cudaMemsetAsync(out_hi, 0, sizeof(float) * total, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(out_lo, 0, sizeof(float) * total, stream));
+    if (cap_rows > 0) {
+        k_to_bev_tc<<<b2s_cdiv((long long)cap_rows * C, kThreads), kThreads, 0, stream>>>(
+            feat, coors, num_rows_dev, cap_rows, C, batch, D, H, W, out_hi, out_lo);
         B2S_LAUNCH_OK();
     }
     return 0;

@@ -1,0 +1,400 @@
+// conv_tc.cu -- dense RPN convolution as a tcgen05 implicit GEMM with fp32-grade accuracy (b2s_conv2d_tc).
+//
+// second.pytorch's RPNV2 (second/pytorch/models/rpn.py:467-497, forward :314-331,393-420) is a stack of
+// Conv2d(3x3, pad 1)+BatchNorm2d+ReLU blocks, 1x1 (de)conv blocks and 1x1 heads: 63.6 GFLOP/frame at car.fhd,
+// the FLOP majority of the frame.  cuDNN runs it in fp32 SIMT (the parity bar is fp32, TF32 is off).  Here it is
+//
+//     D[M = 128 pixels, N = Cout] += A[M, K = 32 channels of one tap] * B[N, K]^T        (tcgen05.mma, kind::tf32)
+//
+// with the **3xTF32 split** that keeps fp32-grade accuracy on the tensor pipe: every operand is stored as
+// hi = tf32-rounded value and lo = value - hi (exact in fp32), and each K step issues
+//     A_lo*B_hi + A_hi*B_lo + A_hi*B_hi            (the dropped A_lo*B_lo term is ~2^-22 relative)
+// accumulating in fp32 in TMEM.
+//
+// Layout: activations NHWC fp32 with a one-pixel zero halo, [B, H+2, W+2, C] (hi and lo planes), so every
+// filter tap is a plain shifted box and TMA (cp.async.bulk.tensor.4d, SWIZZLE_128B) fetches the
+// [8 rows x 16 cols x 32 channels] A tile of a tap directly into the K-major UMMA layout; image borders come
+// from the halo, partial tiles from TMA's out-of-bounds zero fill.  Weights are pre-arranged [tap][Cout][Cin].
+//
+// CTA = 8 warps, persistent over output tiles (static round robin):
+//   warp 0  TMA producer   : per K block (tap, 32-channel chunk) 4 bulk-tensor loads into a 3-stage smem ring
+//   warp 1  MMA issuer     : one elected lane issues 3 x 4 tcgen05.mma per K block, tcgen05.commit frees the stage
+//   warp 2  TMEM allocator : 2 accumulator stages x N columns
+//   warps 4-7 epilogue     : tcgen05.ld accumulator -> BN scale/shift -> ReLU -> hi/lo split -> NHWC stores
+// mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), so the epilogue of
+// tile i overlaps the main loop of tile i+1.
+//
+// Every mbarrier wait is bounded: on a (never expected) protocol error the kernel traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;   // 8 rows x 16 cols of output pixels
+constexpr int TILE_H = 8, TILE_W = 16;
+constexpr int BLOCK_K = 32;    // 32 fp32 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA K step
+constexpr int kThreads = 256;
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: ~seconds of spinning, then trap (a protocol bug must not hang the device)
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
+                                            int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major): 1
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // layout type: SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float to_tf32_rn(float v)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+struct ConvParams {
+    int B, H, W, Cin, Cout, taps, relu;
+    int tiles_h, tiles_w, num_tiles;
+    int out_padded;          // 1: out is [B,H+2,W+2,Cout] (interior written), 0: [B,H,W,Cout]
+    int out_stride;          // channels per output pixel row (>= Cout; lets heads write a packed record)
+    const float *scale, *shift;
+    float *out_hi, *out_lo;
+};
+
+template <int N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+          const ConvParams p)
+{
+    constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
+    constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
+    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N for M=128");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_scale[N], s_shift[N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / BLOCK_K;
+    const int num_kb = p.taps * kchunks;
+
+    if (threadIdx.x < N) {
+        int c = threadIdx.x;
+        s_scale[c] = (p.scale && c < p.Cout) ? p.scale[c] : 1.f;
+        s_shift[c] = (p.shift && c < p.Cout) ? p.shift[c] : 0.f;
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int tw = tile % p.tiles_w;
+                int th = (tile / p.tiles_w) % p.tiles_h;
+                int b = tile / (p.tiles_w * p.tiles_h);
+                int h0 = th * TILE_H, w0 = tw * TILE_W;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    int tap = kb / kchunks, chunk = kb - tap * kchunks;
+                    int dy = (p.taps == 9) ? tap / 3 : 1, dx = (p.taps == 9) ? tap % 3 : 1;
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&bar_full[stage], STAGE_BYTES);
+                    tma_load_4d(st, &map_a_hi, &bar_full[stage], chunk * BLOCK_K, w0 + dx, h0 + dy, b);
+                    tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &bar_full[stage], chunk * BLOCK_K, w0 + dx, h0 + dy, b);
+                    tma_load_3d(st + 2 * A_TILE_BYTES, &map_b_hi, &bar_full[stage], chunk * BLOCK_K, 0, tap);
+                    tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, &bar_full[stage], chunk * BLOCK_K, 0,
+                                tap);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                        umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                        umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                    }
+                    umma_commit(&bar_empty[stage]);              // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&bar_tfull[acc]);                    // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                 // == warp % 4: the TMEM lane quarter this warp may read
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int tw = tile % p.tiles_w;
+            int th = (tile / p.tiles_w) % p.tiles_h;
+            int b = tile / (p.tiles_w * p.tiles_h);
+            const int m = ew * 32 + lane;                      // accumulator row == pixel inside the tile
+            const int h = th * TILE_H + m / TILE_W, w = tw * TILE_W + m % TILE_W;
+            const bool valid = (h < p.H) && (w < p.W);
+            size_t pix;
+            if (p.out_padded) pix = ((size_t)b * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+            else pix = ((size_t)b * p.H + h) * p.W + w;
+            float *oh = p.out_hi + pix * p.out_stride;
+            float *ol = p.out_lo ? p.out_lo + pix * p.out_stride : nullptr;
+            mbar_wait(&bar_tfull[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll 1
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                tmem_ld_wait();
+                if (valid && c0 < p.Cout) {
+                    float v[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (ol) { float hi = to_tf32_rn(x); lo[j] = x - hi; x = hi; }
+                        v[j] = x;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        if (c0 + j < p.Cout) {
+                            *reinterpret_cast<float4 *>(oh + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (ol)
+                                *reinterpret_cast<float4 *>(ol + c0 + j) =
+                                    make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = (PFN_encodeTiled)p;
+    return fn;
+}
+
+int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *strides_bytes,
+             const cuuint32_t *box)
+{
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { b2s_set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, dims, strides_bytes, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { b2s_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    return 0;
+}
+
+template <int N, int STAGES>
+int launch(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &b_hi, const CUtensorMap &b_lo,
+           const ConvParams &p, int num_sms, cudaStream_t stream)
+{
+    constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)N * BLOCK_K * 4;
+    size_t smem = stage * STAGES + 1024;
+    static bool attr = false;
+    if (!attr) {
+        B2S_CUDA_OK(cudaFuncSetAttribute(k_conv_tc<N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    k_conv_tc<N, STAGES><<<grid, kThreads, smem, stream>>>(a_hi, a_lo, b_hi, b_lo, p);
+    B2S_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
+                             const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
+                             int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(taps == 1 || taps == 9, "b2s_conv2d_tc: taps must be 1 or 9");
+    B2S_REQUIRE(Cin % BLOCK_K == 0 && Cin >= BLOCK_K, "b2s_conv2d_tc: Cin must be a multiple of 32");
+    B2S_REQUIRE(n_pad >= Cout && Cout % 4 == 0 && out_stride >= Cout && out_stride % 4 == 0,
+                "b2s_conv2d_tc: Cout/out_stride must be multiples of 4, n_pad >= Cout");
+    B2S_REQUIRE(B >= 1 && H >= 1 && W >= 1, "b2s_conv2d_tc: bad sizes");
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        B2S_CUDA_OK(cudaGetDevice(&dev));
+        B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    CUtensorMap a_hi, a_lo, b_hi, b_lo;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)(W + 2) * Cin * 4, (cuuint64_t)(H + 2) * (W + 2) * Cin * 4};
+        cuuint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+        if (make_map(&a_hi, in_hi, 4, dims, str, box) || make_map(&a_lo, in_lo, 4, dims, str, box)) return -1;
+    }
+    {
+        // weights [taps][n_pad][Cin] (rows >= Cout are zero)
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)n_pad, (cuuint64_t)taps};
+        cuuint64_t str[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)n_pad * Cin * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)n_pad, 1};
+        if (make_map(&b_hi, w_hi, 3, dims, str, box) || make_map(&b_lo, w_lo, 3, dims, str, box)) return -1;
+    }
+    ConvParams p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.relu = relu;
+    p.tiles_h = (H + TILE_H - 1) / TILE_H;
+    p.tiles_w = (W + TILE_W - 1) / TILE_W;
+    p.num_tiles = B * p.tiles_h * p.tiles_w;
+    p.out_padded = out_padded; p.out_stride = out_stride;
+    p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
+    switch (n_pad) {
+        case 128: return launch<128, 3>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+        case 64: return launch<64, 4>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+        case 32: return launch<32, 4>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);
+        default: break;
+    }
+    b2s_set_error("b2s_conv2d_tc: n_pad=%d not built (32, 64, 128)", n_pad);
+    return -2;
+}

@@ -18,8 +18,14 @@ constexpr int kMaxCode = 16;
 // ------------------------------------------------------------------------------------------------
 // decode + filter
 // ------------------------------------------------------------------------------------------------
+// head element (b, channel ch, pixel hw) lives at t[b*batch_stride + ch*cs + hw*ps]
+struct HeadStrides {
+    long long box_b, cls_b, dir_b;
+    int cs, ps;
+};
+
 __global__ void k_decode_filter(const float *__restrict__ box, const float *__restrict__ cls,
-                                const float *__restrict__ dir, const float *__restrict__ anchors,
+                                const float *__restrict__ dir, HeadStrides hs, const float *__restrict__ anchors,
                                 const uint8_t *__restrict__ amask, int batch, int a_loc, int H, int W,
                                 int code, int ncls, int nbins, float thresh, float *cand_box,
                                 float *cand_score, int *cand_label, int *cand_dir, int *cand_anchor,
@@ -32,24 +38,25 @@ __global__ void k_decode_filter(const float *__restrict__ box, const float *__re
     const int b = (int)(gid / A), a = (int)(gid % A);
     if (amask != nullptr && amask[gid] == 0) return;
     const int al = a / HW, hw = a % HW;
-    // class scores: sigmoid is monotonic, so max score = sigmoid(max logit); first max wins ties
-    const float *cp = cls + ((size_t)b * a_loc * ncls + (size_t)al * ncls) * HW + hw;
-    float best = __ldg(cp);
+    const size_t cs = (size_t)hs.cs, ps = (size_t)hs.ps;
+    // class scores: the reference takes max/argmax over the SIGMOID scores (voxelnet.py:444,554-555), so
+    // saturated or fp32-equal scores tie and the first class wins -- compare scores, not logits.
+    const float *cp = cls + (size_t)b * hs.cls_b + (size_t)al * ncls * cs + (size_t)hw * ps;
+    float score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-__ldg(cp))));
     int label = 0;
     for (int c = 1; c < ncls; ++c) {
-        float v = __ldg(cp + (size_t)c * HW);
-        if (v > best) { best = v; label = c; }
+        float s = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-__ldg(cp + (size_t)c * cs))));
+        if (s > score) { score = s; label = c; }
     }
-    const float score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-best)));
     if (!(score >= thresh)) return;
     int pos = atomicAdd(&cand_count[b], 1);
     if (pos >= cand_cap) { atomicOr(status, B2S_STATUS_CAND_OVERFLOW); return; }
     const size_t slot = (size_t)b * cand_cap + pos;
     // box decode (second_box_decode): separate mul/add like the elementwise reference ops
-    const float *bp = box + ((size_t)b * a_loc * code + (size_t)al * code) * HW + hw;
+    const float *bp = box + (size_t)b * hs.box_b + (size_t)al * code * cs + (size_t)hw * ps;
     const float *an = anchors + (size_t)a * code;
     float t[kMaxCode], q[kMaxCode];
-    for (int i = 0; i < code; ++i) { t[i] = __ldg(bp + (size_t)i * HW); q[i] = __ldg(&an[i]); }
+    for (int i = 0; i < code; ++i) { t[i] = __ldg(bp + (size_t)i * cs); q[i] = __ldg(&an[i]); }
     const float xa = q[0], ya = q[1], za = q[2], wa = q[3], la = q[4], ha = q[5], ra = q[6];
     const float diag = sqrtf(__fadd_rn(__fmul_rn(la, la), __fmul_rn(wa, wa)));
     float o[kMaxCode];
@@ -67,10 +74,10 @@ __global__ void k_decode_filter(const float *__restrict__ box, const float *__re
     cand_label[slot] = label;
     int dl = 0;
     if (dir != nullptr) {
-        const float *dp = dir + ((size_t)b * a_loc * nbins + (size_t)al * nbins) * HW + hw;
+        const float *dp = dir + (size_t)b * hs.dir_b + (size_t)al * nbins * cs + (size_t)hw * ps;
         float bd = __ldg(dp);
         for (int c = 1; c < nbins; ++c) {
-            float v = __ldg(dp + (size_t)c * HW);
+            float v = __ldg(dp + (size_t)c * cs);
             if (v > bd) { bd = v; dl = c; }
         }
     }
@@ -467,23 +474,58 @@ size_t carve(NmsWorkspace *w, char *base, int batch, int pre_max)
 
 }  // namespace
 
+static int decode_filter_launch(const float *box, const float *cls, const float *dir, HeadStrides hs,
+                                const float *anchors, const uint8_t *anchors_mask, int batch, int a_loc, int H, int W,
+                                int code, int ncls, int nbins, float score_thresh, float *cand_box, float *cand_score,
+                                int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev, int cand_cap,
+                                unsigned *status_dev, cudaStream_t stream)
+{
+    B2S_REQUIRE(code >= 7 && code <= kMaxCode && ncls >= 1 && batch >= 1 && a_loc >= 1 && cand_cap >= 1,
+                "b2s_decode_filter: bad sizes");
+    B2S_CUDA_OK(cudaMemsetAsync(cand_count_dev, 0, sizeof(int) * (size_t)batch, stream));
+    long long total = (long long)batch * a_loc * H * W;
+    k_decode_filter<<<b2s_cdiv(total, 256), 256, 0, stream>>>(box, cls, dir, hs, anchors, anchors_mask, batch, a_loc,
+                                                             H, W, code, ncls, nbins, score_thresh, cand_box,
+                                                             cand_score, cand_label, cand_dir, cand_anchor,
+                                                             cand_count_dev, cand_cap, status_dev);
+    B2S_LAUNCH_OK();
+    return 0;
+}
+
 extern "C" int b2s_decode_filter(const float *box, const float *cls, const float *dir, const float *anchors,
                                  const uint8_t *anchors_mask, int batch, int a_loc, int H, int W, int code,
                                  int ncls, int nbins, float score_thresh, float *cand_box, float *cand_score,
                                  int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev,
                                  int cand_cap, unsigned *status_dev, void *stream_)
 {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    B2S_REQUIRE(code >= 7 && code <= kMaxCode && ncls >= 1 && batch >= 1 && a_loc >= 1 && cand_cap >= 1,
-                "b2s_decode_filter: bad sizes");
-    B2S_CUDA_OK(cudaMemsetAsync(cand_count_dev, 0, sizeof(int) * (size_t)batch, stream));
-    long long total = (long long)batch * a_loc * H * W;
-    k_decode_filter<<<b2s_cdiv(total, 256), 256, 0, stream>>>(box, cls, dir, anchors, anchors_mask, batch, a_loc, H,
-                                                             W, code, ncls, nbins, score_thresh, cand_box,
-                                                             cand_score, cand_label, cand_dir, cand_anchor,
-                                                             cand_count_dev, cand_cap, status_dev);
-    B2S_LAUNCH_OK();
-    return 0;
+    // NCHW conv outputs: channel stride H*W, pixel stride 1
+    HeadStrides hs;
+    const long long HW = (long long)H * W;
+    hs.box_b = (long long)a_loc * code * HW;
+    hs.cls_b = (long long)a_loc * ncls * HW;
+    hs.dir_b = (long long)a_loc * nbins * HW;
+    hs.cs = (int)HW;
+    hs.ps = 1;
+    return decode_filter_launch(box, cls, dir, hs, anchors, anchors_mask, batch, a_loc, H, W, code, ncls, nbins,
+                                score_thresh, cand_box, cand_score, cand_label, cand_dir, cand_anchor, cand_count_dev,
+                                cand_cap, status_dev, (cudaStream_t)stream_);
+}
+
+extern "C" int b2s_decode_filter_strided(const float *box, const float *cls, const float *dir,
+                                         long long box_batch_stride, long long cls_batch_stride,
+                                         long long dir_batch_stride, int ch_stride, int pix_stride,
+                                         const float *anchors, const uint8_t *anchors_mask, int batch, int a_loc,
+                                         int H, int W, int code, int ncls, int nbins, float score_thresh,
+                                         float *cand_box, float *cand_score, int *cand_label, int *cand_dir,
+                                         int *cand_anchor, int *cand_count_dev, int cand_cap, unsigned *status_dev,
+                                         void *stream_)
+{
+    HeadStrides hs;
+    hs.box_b = box_batch_stride; hs.cls_b = cls_batch_stride; hs.dir_b = dir_batch_stride;
+    hs.cs = ch_stride; hs.ps = pix_stride;
+    return decode_filter_launch(box, cls, dir, hs, anchors, anchors_mask, batch, a_loc, H, W, code, ncls, nbins,
+                                score_thresh, cand_box, cand_score, cand_label, cand_dir, cand_anchor, cand_count_dev,
+                                cand_cap, status_dev, (cudaStream_t)stream_);
 }
 
 extern "C" size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max)

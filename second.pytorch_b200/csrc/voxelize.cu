@@ -25,6 +25,8 @@ struct VoxParams {
     float lo[3];
     float vs[3];
     int grid[3];  // x,y,z
+    int key_depth;  // depth D used in the flat (b,z,y,x) hash key: the consumer's spatial shape[0] (>= grid z;
+                    // SECOND's middle encoders use grid_z + 1, middle.py:139)
 };
 
 __device__ __forceinline__ int frame_of(const int *__restrict__ offsets, int batch, int i)
@@ -58,7 +60,7 @@ __global__ void k_insert(const float *__restrict__ pts, const int *__restrict__ 
     }
     if (!ok) { pslot[i] = -1; return; }
     int b = frame_of(offsets, batch, i);
-    unsigned long long key = b2s_flat_key(b, c[2], c[1], c[0], prm.grid[2], prm.grid[1], prm.grid[0]);
+    unsigned long long key = b2s_flat_key(b, c[2], c[1], c[0], prm.key_depth, prm.grid[1], prm.grid[0]);
     int h = b2s_hash_insert(keys, mask, key);
     if (h < 0) { atomicOr(status, B2S_STATUS_HASH_FULL); pslot[i] = -1; return; }
     pslot[i] = h;
@@ -153,7 +155,7 @@ __global__ void k_assign(const int *__restrict__ pslot, const int *__restrict__ 
     int h = pslot[i];
     int g = block_prefix[i / kScanThreads] + rl;
     unsigned long long key = keys[h];
-    const unsigned long long W = prm.grid[0], H = prm.grid[1], D = prm.grid[2];
+    const unsigned long long W = prm.grid[0], H = prm.grid[1], D = prm.key_depth;
     int x = (int)(key % W);
     unsigned long long r = key / W;
     int y = (int)(r % H);
@@ -290,11 +292,13 @@ extern "C" int b2s_voxelize(const float *points, const int *frame_offsets_dev, i
                             int max_points, int max_voxels, int *coors, int *num_points_per_voxel,
                             int *point_slots, float *voxels, int vfe_mode, int vfe_num_features,
                             float *vfe_out, int *num_voxels_dev, unsigned long long *hash_keys,
-                            int *hash_vals, int hash_cap, void *workspace, size_t workspace_bytes,
-                            unsigned *status_dev, void *stream_)
+                            int *hash_vals, int hash_cap, int hash_key_depth, void *workspace,
+                            size_t workspace_bytes, unsigned *status_dev, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     const int P = num_points, F = num_feat, T = max_points;
+    B2S_REQUIRE(hash_key_depth == 0 || hash_key_depth >= grid[2],
+                "b2s_voxelize: hash_key_depth must be 0 (= grid z) or >= grid z");
     B2S_REQUIRE(P >= 0 && F >= 3 && batch >= 1 && T >= 1 && max_voxels >= 1, "b2s_voxelize: bad sizes");
     B2S_REQUIRE((hash_cap & (hash_cap - 1)) == 0 && hash_cap >= 2 * (P > 0 ? P : 1),
                 "b2s_voxelize: hash_cap must be a power of two >= 2*num_points");
@@ -306,6 +310,7 @@ extern "C" int b2s_voxelize(const float *points, const int *frame_offsets_dev, i
     B2S_REQUIRE(workspace_bytes >= need, "b2s_voxelize: workspace too small (%zu < %zu)", workspace_bytes, need);
     VoxParams prm;
     for (int j = 0; j < 3; ++j) { prm.lo[j] = range_lo[j]; prm.vs[j] = voxel_size[j]; prm.grid[j] = grid[j]; }
+    prm.key_depth = hash_key_depth > 0 ? hash_key_depth : grid[2];
     const size_t cap_rows = (size_t)batch * max_voxels;
     B2S_CUDA_OK(cudaMemsetAsync(hash_keys, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap, stream));
     B2S_CUDA_OK(cudaMemsetAsync(hash_vals, 0xFF, sizeof(int) * (size_t)hash_cap, stream));

@@ -26,7 +26,7 @@ SIGNATURES = {
     "b2s_voxelize_hash_capacity": (c_int, [c_int]),
     "b2s_voxelize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                             c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+                             c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b2s_hash_build": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_rulebook_subm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p, c_void_p]),
@@ -44,6 +44,14 @@ SIGNATURES = {
     "b2s_decode_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_void_p, c_void_p]),
+    "b2s_to_bev_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_void_p]),
+    "b2s_conv2d_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "b2s_decode_filter_strided": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_longlong,
+                                          ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b2s_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                         c_int, c_float, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

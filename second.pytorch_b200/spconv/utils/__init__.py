@@ -41,7 +41,7 @@ class VoxelGeneratorV2:
 
     # -- device-resident API (no host round trip) -------------------------------------------------
     def generate_device(self, points, max_voxels=None, frame_offsets=None, batch=1, vfe_mode=0,
-                        vfe_num_features=4, want_voxels=True):
+                        vfe_num_features=4, want_voxels=True, hash_key_depth=0):
         """points: CUDA float32 [P,F] (``batch`` frames back to back, ``frame_offsets`` int32 [batch+1]).
 
         Returns a dict of CUDA tensors with capacity rows ``batch*max_voxels`` (NOT sliced):
@@ -78,7 +78,8 @@ class VoxelGeneratorV2:
             _lib.f3(self._voxel_size), _lib.i3(self._grid_size), T, mv, _lib.ptr(out["coordinates"]),
             _lib.ptr(out["num_points_per_voxel"]), _lib.ptr(out["point_slots"]), _lib.ptr(out["voxels"]),
             int(vfe_mode), int(vfe_num_features), _lib.ptr(out["vfe"]), _lib.ptr(out["num_voxels"]),
-            _lib.ptr(keys), _lib.ptr(vals), hcap, _lib.ptr(ws), ws_bytes, _lib.ptr(out["status"]), _lib.stream()),
+            _lib.ptr(keys), _lib.ptr(vals), hcap, int(hash_key_depth), _lib.ptr(ws), ws_bytes,
+            _lib.ptr(out["status"]), _lib.stream()),
             "b2s_voxelize")
         out["hash"] = (keys, vals, hcap)
         out["_keepalive"] = (pts, ws)
