@@ -13,10 +13,16 @@ from torch import nn
 def split_tf32(t):
     """fp32 tensor -> (hi, lo): hi = value rounded to tf32 (10-bit mantissa, round half away), lo = t - hi (exact)."""
     t = t.detach().float().contiguous()
-    i = t.view(torch.int32)
-    hi = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
-    hi = torch.where(torch.isfinite(hi), hi, t)
-    return hi.contiguous(), (t - hi).contiguous()
+
+    def rn(x):
+        r = ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+        return torch.where(torch.isfinite(r), r, x)
+
+    hi = rn(t)
+    # lo is ALSO rounded to tf32: the tensor core then sees exactly representable operands, so no hardware
+    # truncation (a biased error that accumulates ~K instead of ~sqrt(K)) can occur; |t - hi - lo| <= 2^-23 |t|.
+    lo = rn(t - hi)
+    return hi.contiguous(), lo.contiguous()
 
 
 def _fold_bn2d(bn):

@@ -48,7 +48,9 @@ __global__ void k_to_bev_tc(const float *__restrict__ feat, const int *__restric
     size_t CD = (size_t)C * D;
     size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
     out_hi[idx] = hi;
-    out_lo[idx] = v - hi;
+    unsigned ul;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
+    out_lo[idx] = __uint_as_float(ul);
 }
 
 // PointPillars PFN (single layer): one warp per pillar; lane l owns output channels l, l+32, ...

@@ -152,12 +152,19 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 {
     constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64) ? 64 : (2 * N <= 128) ? 128 : (2 * N <= 256) ? 256 : 512;
-    static_assert(N % 16 == 0 && N >= 16 && N <= 256, "UMMA N for M=128");
+    // The tensor core's fp32 accumulate is not round-to-nearest: a long accumulation chain (432 MMAs for a
+    // 3x3x128 tap stack) showed a systematic ~2e-5 relative error (measured, round 1).  So every filter TAP is
+    // accumulated in its own short chain (48 MMAs) into one of ACC_SLOTS TMEM accumulators, and the epilogue
+    // warps drain the per-tap partial sums into fp32 registers with round-to-nearest adds while the tensor core
+    // already works on the next tap.
+    constexpr int ACC_SLOTS = 4;
+    constexpr uint32_t TMEM_COLS = (ACC_SLOTS * N <= 32) ? 32 : (ACC_SLOTS * N <= 64) ? 64 : (ACC_SLOTS * N <= 128) ? 128
+                                   : (ACC_SLOTS * N <= 256) ? 256 : 512;
+    static_assert(N % 16 == 0 && N >= 16 && ACC_SLOTS * N <= 512, "UMMA N for M=128 / TMEM capacity");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[ACC_SLOTS], bar_tempty[ACC_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
 
@@ -172,7 +179,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -219,28 +226,30 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                    const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                    const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
-                    const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                    for (int chunk = 0; chunk < kchunks; ++chunk) {
+                        mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                        const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
+                        const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                        umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | k) != 0);
-                        umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
-                        umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (chunk | k) != 0);
+                            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                        }
+                        umma_commit(&bar_empty[stage]);              // frees the smem stage when the MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&bar_empty[stage]);              // frees the smem stage when the MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit(&bar_tfull[acc]);                    // this tap's partial sum is complete
+                    if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
                 }
-                umma_commit(&bar_tfull[acc]);                    // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -260,38 +269,45 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             else pix = ((size_t)b * p.H + h) * p.W + w;
             float *oh = p.out_hi + pix * p.out_stride;
             float *ol = p.out_lo ? p.out_lo + pix * p.out_stride : nullptr;
-            mbar_wait(&bar_tfull[acc], acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
-#pragma unroll 1
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                tmem_ld_wait();
-                if (valid && c0 < p.Cout) {
-                    float v[16], lo[16];
+            // drain the per-tap partial sums into fp32 registers (round-to-nearest adds)
+            float sum[N];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float x = fmaf(__uint_as_float(r[j]), s_scale[c0 + j], s_shift[c0 + j]);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (ol) { float hi = to_tf32_rn(x); lo[j] = x - hi; x = hi; }
-                        v[j] = x;
-                    }
+            for (int j = 0; j < N; ++j) sum[j] = 0.f;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                mbar_wait(&bar_tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        if (c0 + j < p.Cout) {
-                            *reinterpret_cast<float4 *>(oh + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (ol)
-                                *reinterpret_cast<float4 *>(ol + c0 + j) =
-                                    make_float4(lo[j], lo[j + 1], lo[j + 2], lo[j + 3]);
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+                if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
+            }
+            if (valid) {
+#pragma unroll
+                for (int c0 = 0; c0 < N; c0 += 4) {
+                    if (c0 < p.Cout) {
+                        float v[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x = fmaf(sum[c0 + j], s_scale[c0 + j], s_shift[c0 + j]);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            // both planes exactly tf32-representable (round-to-nearest)
+                            if (ol) { float hi = to_tf32_rn(x); lo[j] = to_tf32_rn(x - hi); x = hi; }
+                            v[j] = x;
                         }
+                        *reinterpret_cast<float4 *>(oh + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (ol) *reinterpret_cast<float4 *>(ol + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
