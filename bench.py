@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--points", type=int, default=29000, help="points per synthetic cloud (29k -> ~17k voxels)")
     ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sparse", default="tc", choices=["tc", "fma"],
+                    help="sparse-conv inner product: tc = tcgen05 3xTF32 (wide layers), fma = fp32 FMA tiles")
     ap.add_argument("--rpn", default="auto", choices=["auto", "tc", "cudnn"],
                     help="RPN implementation: tc = hand-written tcgen05 3xTF32 implicit GEMM, cudnn = torch fp32")
     return ap.parse_args()
@@ -72,7 +74,7 @@ def workload_desc(args, n_voxels=None):
          "points_per_cloud": args.points, "frames_per_gpu_per_step": args.batch,
          "parallelism": "frames sharded dp%d, one all-gather of detections" % args.gpus,
          "l2": "flushed between steps (512 MiB write), per-step CUDA events",
-         "rpn": args.rpn, "precision": "fp32 (RPN tc = 3xTF32 split on tcgen05, fp32-grade)"}
+         "rpn": args.rpn, "sparse_conv": args.sparse, "precision": "fp32 (RPN tc = 3xTF32 split on tcgen05, fp32-grade)"}
     if n_voxels is not None:
         d["active_voxels_per_cloud"] = n_voxels
     return d
@@ -198,7 +200,8 @@ def run_gpu_arm(args):
     models.synthetic_weights_(net, args.config, seed=0)
     net = net.to(dev)
     B = args.batch
-    eng = InferenceEngine(net, batch_size=B, max_points=args.points + 1000, use_cuda_graph=True, rpn_impl=args.rpn)
+    eng = InferenceEngine(net, batch_size=B, max_points=args.points + 1000, use_cuda_graph=True, rpn_impl=args.rpn,
+                          sparse_impl=args.sparse)
     args.rpn = eng.rpn_impl
     gather = b2dist.DetectionGatherer(B, eng.post_max, eng.code + 2, dev) if world > 1 else None
     # distinct clouds per rank and per slot; two alternating batches so consecutive steps differ

@@ -128,6 +128,20 @@ int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const in
                     const int *num_out_dev, int cap_out, const float *scale, const float *shift,
                     int relu, float *feat_out, int cout, void *stream);
 
+/* same contraction on the tensor pipe (tcgen05, 3xTF32 hi/lo split, fp32-grade): Cin, Cout in {32, 64}.
+ *   feat_hi/lo [rows_in, Cin] hi/lo planes; w_hi/lo [K, Cout, Cin] (the reference weight [K,Cin,Cout] transposed);
+ *   out_hi/out_lo [cap_out, Cout] (out_lo NULL -> out_hi holds the full fp32 value). */
+int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int cin, const float *w_hi, const float *w_lo,
+                       const int *nbr, int K, const int *num_out_dev, int cap_out, const float *scale,
+                       const float *shift, int relu, float *out_hi, float *out_lo, int cout, void *stream);
+
+/* fp32 rows <-> hi/lo planes (hi = tf32 round-to-nearest, lo = tf32-rounded remainder; hi + lo is exact in fp32).
+ * rows = *num_rows_dev (NULL: cap_rows); row_floats multiple of 4. */
+int b2s_split_tf32(const float *x, float *hi, float *lo, const int *num_rows_dev, int cap_rows, int row_floats,
+                   void *stream);
+int b2s_merge_hilo(const float *hi, const float *lo, float *x, const int *num_rows_dev, int cap_rows,
+                   int row_floats, void *stream);
+
 /* ---- dense BEV map ----------------------------------------------------------------------------- */
 #define B2S_LAYOUT_NCHW 0 /* out[b, c*D+z, y, x]  (== dense() [B,C,D,H,W] viewed [B,C*D,H,W]) */
 #define B2S_LAYOUT_NHWC 1 /* out[b, y, x, c*D+z] */

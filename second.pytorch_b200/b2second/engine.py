@@ -51,7 +51,7 @@ class _Level:
 
 class InferenceEngine:
     def __init__(self, net, batch_size=1, max_points=None, max_voxels=None, row_cap_factor=2.0,
-                 cand_cap=None, use_cuda_graph=True, rpn_impl="auto"):
+                 cand_cap=None, use_cuda_graph=True, rpn_impl="auto", sparse_impl="tc"):
         import spconv as sp                      # the CUDA drop-in: fails loudly if the library is missing
         assert not getattr(sp, "__oracle__", False), "the engine is the product path; it never runs on the oracle"
         self.sp = sp
@@ -83,6 +83,8 @@ class InferenceEngine:
         if rpn_impl == "tc" and not _tc.supported(net.rpn):
             raise ValueError("rpn_impl='tc': this RPN has strided/upsampling stages (cuDNN only this round)")
         self.rpn_impl = rpn_impl
+        assert sparse_impl in ("tc", "fma")       # sparse-conv inner product: tcgen05 3xTF32 | fp32 FMA tiles
+        self.sparse_impl = sparse_impl
         self._plan_middle(row_cap_factor)
         self._alloc_voxel_buffers()
         if rpn_impl == "tc":
@@ -164,8 +166,31 @@ class InferenceEngine:
                 max_ws = max(max_ws, self.lib.b2s_rulebook_conv_workspace_bytes(self.B, self._L.i3(out_shape)))
                 level = new
             lyr["out"] = torch.zeros(lyr["out_level"].cap, m.out_channels, dtype=torch.float32, device=self.dev)
+            # tensor-pipe core (csrc/sparse_conv_tc.cu) for the wide layers; thin layers stay on the fp32 FMA core
+            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in (32, 64) and m.out_channels in (32, 64))
             self.layers.append(lyr)
             i += 1 + (1 if bn is not None else 0) + (1 if relu else 0)
+        # once a layer runs on the tensor pipe all later ones must too (hi/lo planes flow forward)
+        seen_tc = False
+        for lyr in self.layers:
+            if seen_tc and not lyr["tc"]:
+                for l2 in self.layers:
+                    l2["tc"] = False
+                break
+            seen_tc = seen_tc or lyr["tc"]
+        from . import tc as _tc
+        for j, lyr in enumerate(self.layers):
+            if lyr["tc"]:
+                lyr["w_hi"], lyr["w_lo"] = _tc.split_tf32(lyr["w"].transpose(1, 2).contiguous())   # [K, Cout, Cin]
+                lyr["out_lo"] = torch.zeros_like(lyr["out"])
+                if j == 0 or not self.layers[j - 1]["tc"]:
+                    # first tensor-pipe layer: its fp32 input rows are split into hi/lo planes first
+                    lyr["in_split"] = (torch.zeros(lyr["in_level"].cap, lyr["cin"], dtype=torch.float32, device=self.dev),
+                                       torch.zeros(lyr["in_level"].cap, lyr["cin"], dtype=torch.float32, device=self.dev))
+        self.any_sparse_tc = any(l["tc"] for l in self.layers)
+        if self.any_sparse_tc:
+            last = self.layers[-1]
+            self.merged_out = torch.zeros_like(last["out"])
         self.rb_ws = torch.empty(max(max_ws, 1), dtype=torch.uint8, device=self.dev)
         self.rb_ws_bytes = max_ws
         self.final_level = level
@@ -268,7 +293,7 @@ class InferenceEngine:
                                 vx, vy, xo, yo, L.ptr(self.pfn_out), st), "b2s_pfn")
             feats = self.pfn_out
         else:
-            feats = self.vfe_out
+            feats, feats_lo = self.vfe_out, None
             for lyr in self.layers:
                 m, lin, lout = lyr["conv"], lyr["in_level"], lyr["out_level"]
                 if lyr["build_rb"]:
@@ -286,11 +311,29 @@ class InferenceEngine:
                             L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys), L.ptr(lout.vals), lout.hcap,
                             L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
                 self._mark("sparse_conv%d" % lyr["index"])
-                L.check(lib.b2s_sparse_conv(L.ptr(feats), lyr["cin"], L.ptr(lyr["w"]), L.ptr(lyr["rb"]["nbr"]),
-                                            lyr["K"], L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
-                                            L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
-                                            lyr["cout"], st), "b2s_sparse_conv")
-                feats = lyr["out"]
+                if lyr["tc"]:
+                    if "in_split" in lyr:
+                        hi, lo = lyr["in_split"]
+                        L.check(lib.b2s_split_tf32(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
+                                                   lyr["cin"], st), "b2s_split_tf32")
+                        feats, feats_lo = hi, lo
+                    L.check(lib.b2s_sparse_conv_tc(L.ptr(feats), L.ptr(feats_lo), lyr["cin"], L.ptr(lyr["w_hi"]),
+                                                   L.ptr(lyr["w_lo"]), L.ptr(lyr["rb"]["nbr"]), lyr["K"],
+                                                   L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
+                                                   L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
+                                                   L.ptr(lyr["out_lo"]), lyr["cout"], st), "b2s_sparse_conv_tc")
+                    feats, feats_lo = lyr["out"], lyr["out_lo"]
+                else:
+                    L.check(lib.b2s_sparse_conv(L.ptr(feats), lyr["cin"], L.ptr(lyr["w"]), L.ptr(lyr["rb"]["nbr"]),
+                                                lyr["K"], L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
+                                                L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
+                                                lyr["cout"], st), "b2s_sparse_conv")
+                    feats, feats_lo = lyr["out"], None
+            if feats_lo is not None:      # back to plain fp32 rows for the BEV scatter (hi + lo is exact)
+                lout = self.layers[-1]["out_level"]
+                L.check(lib.b2s_merge_hilo(L.ptr(feats), L.ptr(feats_lo), L.ptr(self.merged_out), L.ptr(lout.n_dev),
+                                           lout.cap, self.layers[-1]["cout"], st), "b2s_merge_hilo")
+                feats = self.merged_out
         fl = self.final_level
         D, H, W = fl.shape
         if self.rpn_impl == "tc":
@@ -405,7 +448,11 @@ class InferenceEngine:
         for lyr in self.layers:
             if lyr["build_rb"]:
                 n += 1 if lyr["conv"].subm else 5   # subm_nbr | mark, popc_scan, scan_sums, emit, conv_nbr
-            n += 1                               # b2s_sparse_conv
+            n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc
+            if lyr.get("in_split") is not None:
+                n += 1                           # b2s_split_tf32
+        if getattr(self, "any_sparse_tc", False):
+            n += 1                               # b2s_merge_hilo
         if self.rpn_impl == "tc":
             n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
         return n + 1 + 1 + 3                     # to_bev, decode_filter, nms: select_sort + iou_mask + reduce

@@ -1,0 +1,279 @@
+// sparse_conv_tc.cu -- sparse convolution inner product on the tensor pipe (b2s_sparse_conv_tc).
+//
+// Same output-stationary formulation as sparse_conv.cu (one CTA owns 128 output rows and walks the K kernel
+// offsets; nbr[o][k] names the input row feeding output row o through offset k), but the per-offset product
+//     D[128 rows, Cout] += A[128 gathered rows, 32 channels] * W[k][Cout, 32 channels]^T
+// is a tcgen05.mma (kind::tf32) on the 3xTF32 hi/lo split (see conv_tc.cu), accumulating in TMEM.
+//
+// Warp roles (12 warps):
+//   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
+//   warp 1      MMA issuer (one elected lane)
+//   warp 2      TMEM allocator
+//   warps 4-7   gather producers: thread r copies row nbr[tile*128+r][k] (hi and lo planes) with 16-byte
+//               cp.async into the K-major SWIZZLE_128B A tile (zero-fill for missing neighbours) and signals the
+//               stage's mbarrier with cp.async.mbarrier.arrive.noinc
+//   warps 8-11  epilogue: drain per-group partial sums from TMEM (round-to-nearest adds in registers, the
+//               tensor core's own accumulate is not RN -- see conv_tc.cu), BN scale/shift + ReLU, hi/lo split,
+//               one contiguous row store per thread
+// K block = (kernel offset, 32-channel chunk); accumulation group = GROUP offsets (short chains).
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace b2s_tc;
+constexpr int kThreads = 384;
+constexpr int GROUP = 3;        // kernel offsets per accumulation chain
+constexpr int ACC_SLOTS = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct SpParams {
+    const float *in_hi, *in_lo;
+    const int *nbr;
+    const int *n_out_dev;
+    int cap_out, K, relu;
+    const float *scale, *shift;
+    float *out_hi, *out_lo;
+};
+
+// CIN in {32, 64}; COUT (= UMMA N) in {32, 64}
+template <int CIN, int COUT, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                 const SpParams p)
+{
+    constexpr int N = COUT;
+    constexpr int KCH = CIN / BLOCK_K;                        // 32-channel chunks per offset
+    constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
+    constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    constexpr uint32_t TMEM_COLS = (ACC_SLOTS * N <= 128) ? 128 : (ACC_SLOTS * N <= 256) ? 256 : 512;
+    static_assert(N % 16 == 0 && ACC_SLOTS * N <= 512, "TMEM capacity");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[ACC_SLOTS], bar_tempty[ACC_SLOTS];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ float s_scale[N], s_shift[N];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_out = min(*p.n_out_dev, p.cap_out);
+    const int num_tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
+    const int K = p.K;
+    const int num_groups = (K + GROUP - 1) / GROUP;
+
+    if (threadIdx.x < N) {
+        s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
+        s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 128 + 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== weight TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int k = 0; k < K; ++k)
+                    for (int ch = 0; ch < KCH; ++ch) {
+                        mbar_wait(&bar_empty[stage], phase ^ 1);
+                        uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
+                        tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], ch * BLOCK_K, 0, k);
+                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], ch * BLOCK_K, 0, k);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int g = 0; g < num_groups; ++g) {
+                    mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                    const int k_end = min(K, (g + 1) * GROUP);
+                    bool first = true;
+                    for (int k = g * GROUP; k < k_end; ++k)
+                        for (int ch = 0; ch < KCH; ++ch) {
+                            mbar_wait(&bar_full[stage], phase);
+                            tc_fence_after();
+                            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                            const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
+                            const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                                const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
+                                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
+                                first = false;
+                                umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                            }
+                            umma_commit(&bar_empty[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    umma_commit(&bar_tfull[acc]);
+                    if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== gather producers: one thread per tile row =====================
+        const int r = (warp - 4) * 32 + lane;
+        const uint32_t row_off = (uint32_t)r * 128u;      // 128 B per row in the K-major tile
+        const uint32_t sw = (uint32_t)(r & 7);             // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int row = tile * BLOCK_M + r;
+            const int *nb = p.nbr + (size_t)row * K;
+            for (int k = 0; k < K; ++k) {
+                int src = (row < n_out) ? __ldg(&nb[k]) : -1;
+                const uint32_t nbytes = src >= 0 ? 16u : 0u;   // src-size 0 -> 16 bytes of zeros
+                const size_t base = (size_t)(src >= 0 ? src : 0) * CIN;
+                for (int ch = 0; ch < KCH; ++ch) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES) + row_off;
+                    const float *gh = p.in_hi + base + ch * BLOCK_K;
+                    const float *gl = p.in_lo + base + ch * BLOCK_K;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t dst = sa + (((uint32_t)j ^ sw) << 4);
+                        cp_async16(dst, gh + j * 4, nbytes);
+                        cp_async16(dst + A_TILE_BYTES, gl + j * 4, nbytes);
+                    }
+                    cp_async_mbar_arrive_noinc(&bar_full[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp >= 8) {
+        // ===================== epilogue =====================
+        const int ew = warp - 8;                 // == warp % 4: TMEM lane quarter
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int row = tile * BLOCK_M + ew * 32 + lane;
+            float sum[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) sum[j] = 0.f;
+            for (int g = 0; g < num_groups; ++g) {
+                mbar_wait(&bar_tfull[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+#pragma unroll
+                for (int c0 = 0; c0 < N; c0 += 16) {
+                    uint32_t rr[16];
+                    tmem_ld16(taddr + c0, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+                if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < n_out) {
+                float *oh = p.out_hi + (size_t)row * N;
+                float *ol = p.out_lo ? p.out_lo + (size_t)row * N : nullptr;
+#pragma unroll
+                for (int c0 = 0; c0 < N; c0 += 4) {
+                    float v[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float x = fmaf(sum[c0 + j], s_scale[c0 + j], s_shift[c0 + j]);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (ol) { float hi = to_tf32_rn(x); lo[j] = to_tf32_rn(x - hi); x = hi; }
+                        v[j] = x;
+                    }
+                    *reinterpret_cast<float4 *>(oh + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (ol) *reinterpret_cast<float4 *>(ol + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+    }
+}
+
+template <int CIN, int COUT, int STAGES>
+int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
+{
+    constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * 4;
+    size_t smem = stage * STAGES + 1024;
+    static bool attr = false;
+    if (!attr) {
+        B2S_CUDA_OK(cudaFuncSetAttribute(k_sparse_conv_tc<CIN, COUT, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
+    int grid = tiles_cap < num_sms ? tiles_cap : num_sms;
+    k_sparse_conv_tc<CIN, COUT, STAGES><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
+    B2S_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int cin, const float *w_hi,
+                                  const float *w_lo, const int *nbr, int K, const int *num_out_dev, int cap_out,
+                                  const float *scale, const float *shift, int relu, float *out_hi, float *out_lo,
+                                  int cout, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE((cin == 32 || cin == 64) && (cout == 32 || cout == 64),
+                "b2s_sparse_conv_tc: built for Cin, Cout in {32, 64} (thin layers use b2s_sparse_conv)");
+    B2S_REQUIRE(K >= 1 && cap_out >= 0, "b2s_sparse_conv_tc: bad sizes");
+    if (cap_out == 0) return 0;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        B2S_CUDA_OK(cudaGetDevice(&dev));
+        B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // weights [K][Cout][Cin] (K-major B operand), hi and lo planes
+    CUtensorMap m_hi, m_lo;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)K};
+    cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout * cin * 4};
+    cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
+    if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
+    SpParams p;
+    p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
+    p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
+    if (cin == 64 && cout == 64) return launch<64, 64, 4>(m_hi, m_lo, p, num_sms, stream);
+    if (cin == 32 && cout == 64) return launch<32, 64, 4>(m_hi, m_lo, p, num_sms, stream);
+    if (cin == 32 && cout == 32) return launch<32, 32, 4>(m_hi, m_lo, p, num_sms, stream);
+    return launch<64, 32, 4>(m_hi, m_lo, p, num_sms, stream);
+}

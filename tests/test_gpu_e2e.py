@@ -61,8 +61,8 @@ def test_module_path_matches_golden(product, name, seed, n, path):
 
 @pytest.mark.parametrize("name,seed,n,path", CASES, ids=IDS)
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
-@pytest.mark.parametrize("rpn_impl", ["cudnn", "tc"])
-def test_engine_matches_golden(product, name, seed, n, path, graph, rpn_impl):
+@pytest.mark.parametrize("rpn_impl,sparse_impl", [("cudnn", "fma"), ("tc", "fma"), ("tc", "tc")])
+def test_engine_matches_golden(product, name, seed, n, path, graph, rpn_impl, sparse_impl):
     from b2second import tc
     from b2second.engine import InferenceEngine
     fix = np.load(path)
@@ -70,7 +70,8 @@ def test_engine_matches_golden(product, name, seed, n, path, graph, rpn_impl):
     net = build(name, product, "cuda")
     if rpn_impl == "tc" and not tc.supported(net.rpn):
         pytest.skip("multi-stage RPN stays on cuDNN this round")
-    eng = InferenceEngine(net, batch_size=1, max_points=max(n, 1000), use_cuda_graph=graph, rpn_impl=rpn_impl)
+    eng = InferenceEngine(net, batch_size=1, max_points=max(n, 1000), use_cuda_graph=graph, rpn_impl=rpn_impl,
+                          sparse_impl=sparse_impl)
     eng.infer([torch.from_numpy(pts).cuda()])
     if graph:   # replay twice: the graph must be re-entrant over its static buffers
         eng.infer([torch.from_numpy(pts).cuda()])
@@ -88,7 +89,7 @@ def test_engine_batched_frames_match_single_frames(product):
     name = "car.fhd"
     net = build(name, product, "cuda")
     clouds = [gu.make_cloud(name, s, n) for s, n in ((0, 20000), (3, 15000), (1, 29000))]
-    single = InferenceEngine(net, batch_size=1, max_points=30000, use_cuda_graph=False, rpn_impl="cudnn")
+    single = InferenceEngine(net, batch_size=1, max_points=30000, use_cuda_graph=False, rpn_impl="cudnn", sparse_impl="fma")
     ref = []
     for c in clouds:
         single.infer([torch.from_numpy(c).cuda()])
@@ -96,7 +97,7 @@ def test_engine_batched_frames_match_single_frames(product):
         ref.append({"det": single.detections()[0], "nvox": int(single.num_voxels[0].item()),
                     "ncand": int(single.cand_count[0].item()), "bev": single.bev[0].clone(),
                     "box": single._keep[1][0].clone(), "cls": single._keep[2][0].clone()})
-    eng = InferenceEngine(net, batch_size=3, max_points=30000, use_cuda_graph=False, rpn_impl="cudnn")
+    eng = InferenceEngine(net, batch_size=3, max_points=30000, use_cuda_graph=False, rpn_impl="cudnn", sparse_impl="fma")
     eng.infer([torch.from_numpy(c).cuda() for c in clouds])
     got = eng.detections()
     nv = eng.num_voxels.cpu().tolist()
