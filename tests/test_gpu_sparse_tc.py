@@ -50,8 +50,9 @@ def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
     f_hi, f_lo = tc.split_tf32(feats.cuda())
     o_hi = torch.zeros(rb.num_out, cout, device="cuda")
     o_lo = torch.zeros_like(o_hi)
-    L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(rb.nbr.contiguous()),
-                                   27, L.ptr(rb.num_out_dev), rb.num_out, L.ptr(scale.cuda()), L.ptr(shift.cuda()), 1,
+    scale_d, shift_d, nbr = scale.cuda(), shift.cuda(), rb.nbr.contiguous()   # keep alive across the async launch
+    L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr),
+                                   27, L.ptr(rb.num_out_dev), rb.num_out, L.ptr(scale_d), L.ptr(shift_d), 1,
                                    L.ptr(o_hi), L.ptr(o_lo), cout, L.stream()), "b2s_sparse_conv_tc")
     torch.cuda.synchronize()
     got = (o_hi + o_lo).cpu()
@@ -65,4 +66,8 @@ def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
     L.check(lib.b2s_split_tf32(L.ptr(m), L.ptr(h2), L.ptr(l2), L.ptr(rb.num_out_dev), rb.num_out, cout, L.stream()),
             "b2s_split_tf32")
     torch.cuda.synchronize()
-    assert torch.equal(m, o_hi + o_lo) and torch.equal(h2, o_hi) and torch.equal(l2, o_lo)
+    # merge is exact; re-splitting may pick the neighbouring tf32 value for hi at rounding ties, but the pair
+    # still sums to the same fp32 value within the dropped 2^-23 tail
+    assert torch.equal(m, o_hi + o_lo)
+    assert float((h2 + l2 - m).abs().max()) <= 2e-7 * float(m.abs().max())
+    assert int((h2.view(torch.int32) & 0x1FFF).abs().sum()) == 0 and int((l2.view(torch.int32) & 0x1FFF).abs().sum()) == 0
