@@ -256,6 +256,16 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    if os.environ.get("B2S_PROFILE"):      # `ncu --profile-from-start off`: capture steady-state steps only
+        for i in range(warm):
+            step_resident(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for i in range(int(os.environ["B2S_PROFILE"])):
+            step_resident(i)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     ms_res = timed(step_resident, args.steps, warm)
     ms_e2e = timed(step_e2e, args.steps, warm)
     clocks = sampler.stop() if rank == 0 else None
