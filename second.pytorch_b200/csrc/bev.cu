@@ -6,26 +6,36 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxBlocks = 148 * 8;   // bounded grids + grid-stride loops: cost follows the live row count
+
+inline int bounded_grid(long long items)
+{
+    long long b = (items + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    return (int)(b < kMaxBlocks ? b : kMaxBlocks);
+}
 
 __global__ void k_to_bev(const float *__restrict__ feat, const int *__restrict__ coors,
                          const int *__restrict__ n_dev, int cap_rows, int C, int batch, int D, int H, int W,
                          float *__restrict__ out, int layout)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_dev, cap_rows);
-    if (gid >= (long long)n * C) return;
-    int row = (int)(gid / C), c = (int)(gid % C);
-    int4 q = __ldg(reinterpret_cast<const int4 *>(coors + (size_t)row * 4));  // b,z,y,x
-    if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
-        (unsigned)q.w >= (unsigned)W)
-        return;
-    float v = __ldg(&feat[gid]);
-    size_t CD = (size_t)C * D;
-    size_t ch = (size_t)c * D + q.y;
-    size_t idx;
-    if (layout == B2S_LAYOUT_NCHW) idx = (((size_t)q.x * CD + ch) * H + q.z) * W + q.w;
-    else idx = (((size_t)q.x * H + q.z) * W + q.w) * CD + ch;
-    out[idx] = v;
+    const int n = min(*n_dev, cap_rows);
+    const long long total = (long long)n * C;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / C), c = (int)(gid % C);
+        int4 q = __ldg(reinterpret_cast<const int4 *>(coors + (size_t)row * 4));  // b,z,y,x
+        if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
+            (unsigned)q.w >= (unsigned)W)
+            continue;
+        float v = __ldg(&feat[gid]);
+        size_t CD = (size_t)C * D;
+        size_t ch = (size_t)c * D + q.y;
+        size_t idx;
+        if (layout == B2S_LAYOUT_NCHW) idx = (((size_t)q.x * CD + ch) * H + q.z) * W + q.w;
+        else idx = (((size_t)q.x * H + q.z) * W + q.w) * CD + ch;
+        out[idx] = v;
+    }
 }
 
 // tensor-core RPN input: NHWC + one-pixel zero halo, hi/lo (3xTF32) planes
@@ -33,24 +43,26 @@ __global__ void k_to_bev_tc(const float *__restrict__ feat, const int *__restric
                             const int *__restrict__ n_dev, int cap_rows, int C, int batch, int D, int H, int W,
                             float *__restrict__ out_hi, float *__restrict__ out_lo)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_dev, cap_rows);
-    if (gid >= (long long)n * C) return;
-    int row = (int)(gid / C), c = (int)(gid % C);
-    int4 q = __ldg(reinterpret_cast<const int4 *>(coors + (size_t)row * 4));  // b,z,y,x
-    if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
-        (unsigned)q.w >= (unsigned)W)
-        return;
-    float v = __ldg(&feat[gid]);
-    unsigned u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    float hi = __uint_as_float(u);
-    size_t CD = (size_t)C * D;
-    size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
-    out_hi[idx] = hi;
-    unsigned ul;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
-    out_lo[idx] = __uint_as_float(ul);
+    const int n = min(*n_dev, cap_rows);
+    const long long total = (long long)n * C;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / C), c = (int)(gid % C);
+        int4 q = __ldg(reinterpret_cast<const int4 *>(coors + (size_t)row * 4));  // b,z,y,x
+        if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
+            (unsigned)q.w >= (unsigned)W)
+            continue;
+        float v = __ldg(&feat[gid]);
+        unsigned u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+        float hi = __uint_as_float(u);
+        size_t CD = (size_t)C * D;
+        size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
+        out_hi[idx] = hi;
+        unsigned ul;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
+        out_lo[idx] = __uint_as_float(ul);
+    }
 }
 
 // PointPillars PFN (single layer): one warp per pillar; lane l owns output channels l, l+32, ...
@@ -134,7 +146,7 @@ extern "C" int b2s_to_bev(const float *feat, const int *coors, const int *num_ro
     size_t total = (size_t)batch * C * D * H * W;
     B2S_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * total, stream));
     if (cap_rows > 0) {
-        k_to_bev<<<b2s_cdiv((long long)cap_rows * C, kThreads), kThreads, 0, stream>>>(
+        k_to_bev<<<bounded_grid((long long)cap_rows * C), kThreads, 0, stream>>>(
             feat, coors, num_rows_dev, cap_rows, C, batch, D, H, W, out, layout);
         B2S_LAUNCH_OK();
     }
@@ -150,7 +162,7 @@ extern "C" int b2s_to_bev_tc(const float *feat, const int *coors, const int *num
     B2S_CUDA_OK(cudaMemsetAsync(out_hi, 0, sizeof(float) * total, stream));
     B2S_CUDA_OK(cudaMemsetAsync(out_lo, 0, sizeof(float) * total, stream));
     if (cap_rows > 0) {
-        k_to_bev_tc<<<b2s_cdiv((long long)cap_rows * C, kThreads), kThreads, 0, stream>>>(
+        k_to_bev_tc<<<bounded_grid((long long)cap_rows * C), kThreads, 0, stream>>>(
             feat, coors, num_rows_dev, cap_rows, C, batch, D, H, W, out_hi, out_lo);
         B2S_LAUNCH_OK();
     }

@@ -418,37 +418,51 @@ k_reduce_epilogue(const unsigned long long *__restrict__ mask, const int *__rest
     }
     __syncthreads();
     const int nk = s_nkeep;
-    // epilogue (serial over <= post_max boxes to keep the output order): thread 0
+    // epilogue, one thread per kept box (loads in parallel; a serial loop of dependent global loads cost ~200 us):
+    // pass 1 = range test -> s_keep[q] becomes the compacted output position (or -1); pass 2 = write.
+    __shared__ int s_pos[1024];
+    const int stride = code + 2;
+    for (int q = tid; q < nk; q += 256) {
+        int slot = sorted_slot[(size_t)b * pre_max + s_keep[q]];
+        const float *bx = cand_box + ((size_t)b * cand_cap + slot) * code;
+        bool ok = true;
+        if (has_range) {
+            float x = bx[0], y = bx[1], z = bx[2];
+            ok = x >= r0 && y >= r1 && z >= r2 && x <= r3 && y <= r4 && z <= r5;
+        }
+        s_pos[q] = ok ? 1 : 0;
+    }
+    __syncthreads();
     if (tid == 0) {
         int out = 0;
-        const int stride = code + 2;
-        const float PI = 3.14159265358979323846f;
         for (int q = 0; q < nk; ++q) {
-            int slot = sorted_slot[(size_t)b * pre_max + s_keep[q]];
-            size_t cs = (size_t)b * cand_cap + slot;
-            const float *bx = cand_box + cs * code;
-            float v[kMaxCode];
-            for (int c = 0; c < code; ++c) v[c] = bx[c];
-            if (use_dir) {
-                // voxelnet.py:598-607: period = 2*pi/bins; r = limit_period(r - off, lim, period) + off + period*label
-                float period = (float)(2.0 * 3.14159265358979323846 / (double)num_dir_bins);
-                float val = __fsub_rn(v[6], dir_offset);
-                float fl = floorf(__fadd_rn(__fdiv_rn(val, period), dir_limit_offset));
-                float dir_rot = __fsub_rn(val, __fmul_rn(fl, period));
-                v[6] = __fadd_rn(__fadd_rn(dir_rot, dir_offset), __fmul_rn(period, (float)cand_dir[cs]));
-            }
-            (void)PI;
-            bool ok = true;
-            if (has_range)
-                ok = v[0] >= r0 && v[1] >= r1 && v[2] >= r2 && v[0] <= r3 && v[1] <= r4 && v[2] <= r5;
-            if (!ok) continue;
-            float *d = det + ((size_t)b * post_max + out) * stride;
-            for (int c = 0; c < code; ++c) d[c] = v[c];
-            d[code] = cand_score[cs];
-            d[code + 1] = (float)cand_label[cs];
-            ++out;
+            int f = s_pos[q];
+            s_pos[q] = f ? out : -1;
+            out += f;
         }
         det_count[b] = out;
+    }
+    __syncthreads();
+    for (int q = tid; q < nk; q += 256) {
+        const int pos = s_pos[q];
+        if (pos < 0) continue;
+        int slot = sorted_slot[(size_t)b * pre_max + s_keep[q]];
+        size_t cs = (size_t)b * cand_cap + slot;
+        const float *bx = cand_box + cs * code;
+        float v[kMaxCode];
+        for (int c = 0; c < code; ++c) v[c] = bx[c];
+        if (use_dir) {
+            // voxelnet.py:598-607: period = 2*pi/bins; r = limit_period(r - off, lim, period) + off + period*label
+            float period = (float)(2.0 * 3.14159265358979323846 / (double)num_dir_bins);
+            float val = __fsub_rn(v[6], dir_offset);
+            float fl = floorf(__fadd_rn(__fdiv_rn(val, period), dir_limit_offset));
+            float dir_rot = __fsub_rn(val, __fmul_rn(fl, period));
+            v[6] = __fadd_rn(__fadd_rn(dir_rot, dir_offset), __fmul_rn(period, (float)cand_dir[cs]));
+        }
+        float *d = det + ((size_t)b * post_max + pos) * stride;
+        for (int c = 0; c < code; ++c) d[c] = v[c];
+        d[code] = cand_score[cs];
+        d[code + 1] = (float)cand_label[cs];
     }
 }
 

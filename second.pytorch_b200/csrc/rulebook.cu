@@ -10,12 +10,24 @@
 // (b,z,y,x) key (the order upstream's GPU path produces with thrust sort+unique).  Here dedup + sort
 // are one step: an occupancy bitmap over the output grid plus a popcount prefix scan gives every
 // active output cell its sorted rank directly.
+//
+// All row counts are read from device memory; grids are bounded (a few CTAs per SM) with grid-stride loops,
+// so the cost follows the live row count, not the buffer capacity (capacity-sized grids cost ~40 us per
+// launch of mostly-idle threads in the first profile).
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kScanThreads = 1024;
+constexpr int kMaxBlocks = 148 * 8;
+
+inline int bounded_grid(long long work_items, int threads)
+{
+    long long b = (work_items + threads - 1) / threads;
+    if (b < 1) b = 1;
+    return (int)(b < kMaxBlocks ? b : kMaxBlocks);
+}
 
 struct ConvGeom {
     int in_shape[3], out_shape[3], k[3], s[3], p[3], d[3];
@@ -26,61 +38,78 @@ __global__ void k_hash_build(const int *__restrict__ coors, const int *__restric
                              int D, int H, int W, unsigned long long *keys, int *vals, int mask,
                              unsigned *status)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_dev, cap_rows);
-    if (i >= n) return;
-    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)i * 4);
-    unsigned long long key = b2s_flat_key(c.x, c.y, c.z, c.w, D, H, W);
-    int h = b2s_hash_insert(keys, mask, key);
-    if (h < 0) { atomicOr(status, B2S_STATUS_HASH_FULL); return; }
-    vals[h] = i;
+    const int n = min(*n_dev, cap_rows);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)i * 4);
+        unsigned long long key = b2s_flat_key(c.x, c.y, c.z, c.w, D, H, W);
+        int h = b2s_hash_insert(keys, mask, key);
+        if (h < 0) { atomicOr(status, B2S_STATUS_HASH_FULL); continue; }
+        vals[h] = i;
+    }
 }
 
-// one thread per (row, k)
+// SubM neighbour table.  The relation is symmetric (j = i + delta  <=>  i = j - delta, mirrored offset index
+// K-1-k), so only the first half of the offsets is looked up and both entries are written; nbr is pre-filled
+// with -1 by the caller.  One thread per (row, k < K/2).
 __global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
                            ConvGeom g, const unsigned long long *__restrict__ keys,
                            const int *__restrict__ vals, int mask, int *nbr)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_dev, cap_rows);
-    if (gid >= (long long)n * g.K) return;
-    int row = (int)(gid / g.K), k = (int)(gid % g.K);
-    int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
-    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
-    int z = c.y + (kz - g.k[0] / 2) * g.d[0];
-    int y = c.z + (ky - g.k[1] / 2) * g.d[1];
-    int x = c.w + (kx - g.k[2] / 2) * g.d[2];
-    int r = -1;
-    if (z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1] && x >= 0 && x < g.in_shape[2]) {
-        if (kz == g.k[0] / 2 && ky == g.k[1] / 2 && kx == g.k[2] / 2) r = row;
-        else r = b2s_hash_find(keys, vals, mask,
-                               b2s_flat_key(c.x, z, y, x, g.in_shape[0], g.in_shape[1], g.in_shape[2]));
+    const int n = min(*n_dev, cap_rows);
+    const int half = g.K / 2;            // offsets 0..half-1 are looked up, `half` is the centre
+    const long long total = (long long)n * (half + 1);
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / (half + 1)), k = (int)(gid % (half + 1));
+        if (k == half) { nbr[(size_t)row * g.K + half] = row; continue; }
+        int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
+        int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
+        int z = c.y + (kz - g.k[0] / 2) * g.d[0];
+        int y = c.z + (ky - g.k[1] / 2) * g.d[1];
+        int x = c.w + (kx - g.k[2] / 2) * g.d[2];
+        if (z < 0 || z >= g.in_shape[0] || y < 0 || y >= g.in_shape[1] || x < 0 || x >= g.in_shape[2]) continue;
+        int j = b2s_hash_find(keys, vals, mask,
+                              b2s_flat_key(c.x, z, y, x, g.in_shape[0], g.in_shape[1], g.in_shape[2]));
+        if (j >= 0 && j < n) {
+            nbr[(size_t)row * g.K + k] = j;
+            nbr[(size_t)j * g.K + (g.K - 1 - k)] = row;
+        }
     }
-    nbr[gid] = r;
 }
 
-// one thread per (input row, k): mark candidate output cells
+// one thread per input row: mark every output cell the row contributes to
 __global__ void k_conv_mark(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
                             ConvGeom g, unsigned *bitmap)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_dev, cap_rows);
-    if (gid >= (long long)n * g.K) return;
-    int row = (int)(gid / g.K), k = (int)(gid % g.K);
-    int kk[3] = {k / (g.k[2] * g.k[1]), (k / g.k[2]) % g.k[1], k % g.k[2]};
-    int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
-    int ic[3] = {c.y, c.z, c.w};
-    int o[3];
+    const int n = min(*n_dev, cap_rows);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
+        const int ic[3] = {c.y, c.z, c.w};
+        // per dimension: the (<= ceil(k/s)) valid output coordinates
+        int oc[3][4], cnt[3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        int num = ic[j] + g.p[j] - kk[j] * g.d[j];
-        if (num < 0) return;
-        if (num % g.s[j] != 0) return;
-        o[j] = num / g.s[j];
-        if (o[j] >= g.out_shape[j]) return;
+        for (int j = 0; j < 3; ++j) {
+            cnt[j] = 0;
+            for (int kk = 0; kk < g.k[j]; ++kk) {
+                int num = ic[j] + g.p[j] - kk * g.d[j];
+                if (num < 0 || num % g.s[j] != 0) continue;
+                int o = num / g.s[j];
+                if (o >= g.out_shape[j]) continue;
+                bool dup = false;
+                for (int q = 0; q < cnt[j]; ++q) dup |= (oc[j][q] == o);
+                if (!dup && cnt[j] < 4) oc[j][cnt[j]++] = o;
+            }
+        }
+        for (int a = 0; a < cnt[0]; ++a)
+            for (int b = 0; b < cnt[1]; ++b)
+                for (int e = 0; e < cnt[2]; ++e) {
+                    unsigned long long key = b2s_flat_key(c.x, oc[0][a], oc[1][b], oc[2][e], g.out_shape[0],
+                                                          g.out_shape[1], g.out_shape[2]);
+                    unsigned bit = 1u << (key & 31);
+                    unsigned *w = &bitmap[key >> 5];
+                    if (!(*(volatile unsigned *)w & bit)) atomicOr(w, bit);
+                }
     }
-    unsigned long long key = b2s_flat_key(c.x, o[0], o[1], o[2], g.out_shape[0], g.out_shape[1], g.out_shape[2]);
-    atomicOr(&bitmap[key >> 5], 1u << (key & 31));
 }
 
 __global__ void k_popc_scan(const unsigned *__restrict__ bitmap, long long nwords, int *word_prefix,
@@ -117,35 +146,43 @@ __global__ void k_scan_sums(int *block_sums, int nblk, int *num_out_dev, int cap
     }
 }
 
-// one thread per bitmap word: emit sorted output coordinates + out hash
+// warp per 32 bitmap words; the bits of each non-empty word are expanded by the 32 lanes in parallel
 __global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nwords,
                             const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
                             ConvGeom g, int cap_out, int *coors_out, unsigned long long *keys_out,
                             int *vals_out, int mask_out, unsigned *status)
 {
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwords) return;
-    unsigned bits = bitmap[i];
-    if (bits == 0) return;
-    int row = block_prefix[i / kScanThreads] + word_prefix[i];
-    const unsigned long long W = g.out_shape[2], H = g.out_shape[1], D = g.out_shape[0];
-    while (bits) {
-        int bit = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (row < cap_out) {
-            unsigned long long key = ((unsigned long long)i << 5) + bit;
-            int x = (int)(key % W);
-            unsigned long long r = key / W;
-            int y = (int)(r % H);
-            r /= H;
-            int z = (int)(r % D);
-            int b = (int)(r / D);
-            *reinterpret_cast<int4 *>(coors_out + (size_t)row * 4) = make_int4(b, z, y, x);
-            int h = b2s_hash_insert(keys_out, mask_out, key);
-            if (h < 0) atomicOr(status, B2S_STATUS_HASH_FULL);
-            else vals_out[h] = row;
+    const int lane = threadIdx.x & 31;
+    const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned W = g.out_shape[2], H = g.out_shape[1], D = g.out_shape[0];
+    for (long long base = warp0 * 32; base < nwords; base += warps_total * 32) {
+        long long i = base + lane;
+        unsigned bits = i < nwords ? bitmap[i] : 0u;
+        unsigned nonempty = __ballot_sync(0xffffffffu, bits != 0u);
+        int my_row0 = bits ? block_prefix[i / kScanThreads] + word_prefix[i] : 0;
+        while (nonempty) {
+            int src = __ffs(nonempty) - 1;
+            nonempty &= nonempty - 1;
+            unsigned wbits = __shfl_sync(0xffffffffu, bits, src);
+            int row0 = __shfl_sync(0xffffffffu, my_row0, src);
+            if (wbits & (1u << lane)) {
+                int row = row0 + __popc(wbits & ((1u << lane) - 1u));
+                if (row < cap_out) {
+                    unsigned long long key = (((unsigned long long)(base + src)) << 5) + lane;
+                    unsigned long long r = key / W;
+                    int x = (int)(key - r * W);
+                    unsigned long long r2 = r / H;
+                    int y = (int)(r - r2 * H);
+                    int b = (int)(r2 / D);
+                    int z = (int)(r2 - (unsigned long long)b * D);
+                    *reinterpret_cast<int4 *>(coors_out + (size_t)row * 4) = make_int4(b, z, y, x);
+                    int h = b2s_hash_insert(keys_out, mask_out, key);
+                    if (h < 0) atomicOr(status, B2S_STATUS_HASH_FULL);
+                    else vals_out[h] = row;
+                }
+            }
         }
-        ++row;
     }
 }
 
@@ -154,40 +191,44 @@ __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restr
                            ConvGeom g, const unsigned long long *__restrict__ keys_in,
                            const int *__restrict__ vals_in, int mask_in, int *nbr)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_out_dev, cap_out);
-    if (gid >= (long long)n * g.K) return;
-    int row = (int)(gid / g.K), k = (int)(gid % g.K);
-    int kk[3] = {k / (g.k[2] * g.k[1]), (k / g.k[2]) % g.k[1], k % g.k[2]};
-    int4 c = *reinterpret_cast<const int4 *>(coors_out + (size_t)row * 4);
-    int oc[3] = {c.y, c.z, c.w};
-    int ic[3];
-    bool ok = true;
+    const int n = min(*n_out_dev, cap_out);
+    const long long total = (long long)n * g.K;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / g.K), k = (int)(gid % g.K);
+        int kk[3] = {k / (g.k[2] * g.k[1]), (k / g.k[2]) % g.k[1], k % g.k[2]};
+        int4 c = *reinterpret_cast<const int4 *>(coors_out + (size_t)row * 4);
+        int oc[3] = {c.y, c.z, c.w};
+        int ic[3];
+        bool ok = true;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        ic[j] = oc[j] * g.s[j] - g.p[j] + kk[j] * g.d[j];
-        if (ic[j] < 0 || ic[j] >= g.in_shape[j]) ok = false;
+        for (int j = 0; j < 3; ++j) {
+            ic[j] = oc[j] * g.s[j] - g.p[j] + kk[j] * g.d[j];
+            if (ic[j] < 0 || ic[j] >= g.in_shape[j]) ok = false;
+        }
+        int r = -1;
+        if (ok)
+            r = b2s_hash_find(keys_in, vals_in, mask_in,
+                              b2s_flat_key(c.x, ic[0], ic[1], ic[2], g.in_shape[0], g.in_shape[1], g.in_shape[2]));
+        nbr[gid] = r;
     }
-    int r = -1;
-    if (ok)
-        r = b2s_hash_find(keys_in, vals_in, mask_in,
-                          b2s_flat_key(c.x, ic[0], ic[1], ic[2], g.in_shape[0], g.in_shape[1], g.in_shape[2]));
-    nbr[gid] = r;
 }
 
 __global__ void k_pairs(const int *__restrict__ nbr, const int *__restrict__ n_out_dev, int cap_out, int K,
                         int L, int *pairs, int *pair_num)
 {
-    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int n = min(*n_out_dev, cap_out);
-    if (gid >= (long long)n * K) return;
-    int row = (int)(gid / K), k = (int)(gid % K);
-    int r = nbr[gid];
-    if (r < 0) return;
-    int pos = atomicAdd(&pair_num[k], 1);
-    if (pos < L) {
-        pairs[((size_t)k * 2 + 0) * L + pos] = r;
-        pairs[((size_t)k * 2 + 1) * L + pos] = row;
+    const int n = min(*n_out_dev, cap_out);
+    const long long total = (long long)n * K;
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / K), k = (int)(gid % K);
+        int r = nbr[gid];
+        if (r < 0) continue;
+        int pos = atomicAdd(&pair_num[k], 1);
+        if (pos < L) {
+            pairs[((size_t)k * 2 + 0) * L + pos] = r;
+            pairs[((size_t)k * 2 + 1) * L + pos] = row;
+        }
     }
 }
 
@@ -241,7 +282,7 @@ extern "C" int b2s_hash_build(const int *coors, const int *num_rows_dev, int cap
     B2S_CUDA_OK(cudaMemsetAsync(hash_keys, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap, stream));
     B2S_CUDA_OK(cudaMemsetAsync(hash_vals, 0xFF, sizeof(int) * (size_t)hash_cap, stream));
     if (cap_rows > 0) {
-        k_hash_build<<<b2s_cdiv(cap_rows, kThreads), kThreads, 0, stream>>>(
+        k_hash_build<<<bounded_grid(cap_rows, kThreads), kThreads, 0, stream>>>(
             coors, num_rows_dev, cap_rows, shape[0], shape[1], shape[2], hash_keys, hash_vals, hash_cap - 1,
             status_dev);
         B2S_LAUNCH_OK();
@@ -259,7 +300,8 @@ extern "C" int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int 
                 "b2s_rulebook_subm: bad geometry");
     B2S_REQUIRE((g.k[0] & 1) && (g.k[1] & 1) && (g.k[2] & 1), "b2s_rulebook_subm: kernel sizes must be odd");
     if (cap_rows > 0) {
-        k_subm_nbr<<<b2s_cdiv((long long)cap_rows * g.K, kThreads), kThreads, 0, stream>>>(
+        B2S_CUDA_OK(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)cap_rows * g.K, stream));
+        k_subm_nbr<<<bounded_grid((long long)cap_rows * (g.K / 2 + 1), kThreads), kThreads, 0, stream>>>(
             coors, num_rows_dev, cap_rows, g, hash_keys, hash_vals, hash_cap - 1, nbr);
         B2S_LAUNCH_OK();
     }
@@ -287,6 +329,7 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
         int expect = (g.in_shape[j] + 2 * g.p[j] - g.d[j] * (g.k[j] - 1) - 1) / g.s[j] + 1;
         B2S_REQUIRE(expect == g.out_shape[j], "b2s_rulebook_conv: out_shape[%d]=%d, expected %d", j,
                     g.out_shape[j], expect);
+        B2S_REQUIRE((g.k[j] + g.s[j] - 1) / g.s[j] <= 4, "b2s_rulebook_conv: kernel/stride ratio > 4 in dim %d", j);
     }
     B2S_REQUIRE((hash_cap_out & (hash_cap_out - 1)) == 0 && hash_cap_out >= 2 * cap_out && hash_cap_out >= 2,
                 "b2s_rulebook_conv: hash_cap_out must be a power of two >= 2*cap_out");
@@ -297,20 +340,19 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
     B2S_CUDA_OK(cudaMemsetAsync(hash_keys_out, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap_out, stream));
     B2S_CUDA_OK(cudaMemsetAsync(hash_vals_out, 0xFF, sizeof(int) * (size_t)hash_cap_out, stream));
     if (cap_in > 0) {
-        k_conv_mark<<<b2s_cdiv((long long)cap_in * g.K, kThreads), kThreads, 0, stream>>>(
-            coors_in, num_in_dev, cap_in, g, w.bitmap);
+        k_conv_mark<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(coors_in, num_in_dev, cap_in, g, w.bitmap);
         B2S_LAUNCH_OK();
     }
     k_popc_scan<<<w.nblk, kScanThreads, 0, stream>>>(w.bitmap, w.nwords, w.word_prefix, w.block_sums);
     B2S_LAUNCH_OK();
     k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblk, num_out_dev, cap_out, status_dev);
     B2S_LAUNCH_OK();
-    k_conv_emit<<<w.nblk, kScanThreads, 0, stream>>>(w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out,
-                                                    coors_out, hash_keys_out, hash_vals_out, hash_cap_out - 1,
-                                                    status_dev);
+    k_conv_emit<<<bounded_grid(w.nwords, kThreads), kThreads, 0, stream>>>(
+        w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out, coors_out, hash_keys_out, hash_vals_out,
+        hash_cap_out - 1, status_dev);
     B2S_LAUNCH_OK();
     if (cap_out > 0) {
-        k_conv_nbr<<<b2s_cdiv((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
+        k_conv_nbr<<<bounded_grid((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
             coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
         B2S_LAUNCH_OK();
     }
@@ -322,8 +364,8 @@ extern "C" int b2s_rulebook_pairs(const int *nbr, const int *num_out_dev, int ca
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (cap_out > 0 && K > 0) {
-        k_pairs<<<b2s_cdiv((long long)cap_out * K, kThreads), kThreads, 0, stream>>>(nbr, num_out_dev, cap_out, K,
-                                                                                 L, indice_pairs, indice_pair_num);
+        k_pairs<<<bounded_grid((long long)cap_out * K, kThreads), kThreads, 0, stream>>>(nbr, num_out_dev, cap_out, K,
+                                                                                     L, indice_pairs, indice_pair_num);
         B2S_LAUNCH_OK();
     }
     return 0;

@@ -109,22 +109,26 @@ __global__ void k_scan_sums_and_frames(int *block_sums, int nblk, const int *__r
     __syncthreads();
     const int total_cells = carry;
     // global first-come rank at each frame start = number of first-points with index < offsets[f]
-    for (int f = threadIdx.x; f <= batch; f += blockDim.x) {
+    __shared__ int s_min;
+    for (int f = 0; f <= batch; ++f) {          // block-cooperative: thread t looks at point blk*1024 + t
         int off = (offsets == nullptr) ? (f == 0 ? 0 : P) : offsets[f];
-        int r;
-        if (off >= P) r = total_cells;
-        else {
-            // rank of the first "first-point" at or after `off`: scan forward inside its block
-            int blk = off / kScanThreads;
-            int end = min(P, (blk + 1) * kScanThreads);
-            r = -1;
-            for (int j = off; j < end; ++j) {
-                int rl = rank_local[j];
-                if (rl >= 0) { r = block_sums[blk] + rl; break; }
-            }
-            if (r < 0) r = block_sums[blk + 1];
+        if (off >= P) {
+            if (threadIdx.x == 0) frame_rank_start[f] = total_cells;
+            continue;                            // `off` is block-uniform
         }
-        frame_rank_start[f] = r;
+        // rank of the first "first-point" at or after `off` = smallest local rank among them in its scan block
+        int blk = off / kScanThreads;
+        if (threadIdx.x == 0) s_min = 0x7FFFFFFF;
+        __syncthreads();
+        int j = blk * kScanThreads + threadIdx.x;
+        if (j >= off && j < P) {
+            int rl = rank_local[j];
+            if (rl >= 0) atomicMin(&s_min, rl);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            frame_rank_start[f] = (s_min != 0x7FFFFFFF) ? block_sums[blk] + s_min : block_sums[blk + 1];
+        __syncthreads();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
