@@ -131,7 +131,9 @@ int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const in
 /* same contraction on the tensor pipe (tcgen05, 3xTF32 hi/lo split, fp32-grade): Cin, Cout in {32, 64}.
  *   feat_hi/lo [rows_in, Cin] hi/lo planes; w_hi/lo [K, Cout, Cin] (the reference weight [K,Cin,Cout] transposed);
  *   out_hi/out_lo [cap_out, Cout] (out_lo NULL -> out_hi holds the full fp32 value). */
-int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int cin, const float *w_hi, const float *w_lo,
+int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in /*row capacity of the feature planes
+                       (the TMA gather's tensor extent; rows >= rows_in read as zeros)*/,
+                       int cin, const float *w_hi, const float *w_lo,
                        const int *nbr, int K, const int *num_out_dev, int cap_out, const float *scale,
                        const float *shift, int relu, float *out_hi, float *out_lo, int cout, void *stream);
 

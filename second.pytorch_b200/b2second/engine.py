@@ -317,7 +317,7 @@ class InferenceEngine:
                         L.check(lib.b2s_split_tf32(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
                                                    lyr["cin"], st), "b2s_split_tf32")
                         feats, feats_lo = hi, lo
-                    L.check(lib.b2s_sparse_conv_tc(L.ptr(feats), L.ptr(feats_lo), lyr["cin"], L.ptr(lyr["w_hi"]),
+                    L.check(lib.b2s_sparse_conv_tc(L.ptr(feats), L.ptr(feats_lo), lin.cap, lyr["cin"], L.ptr(lyr["w_hi"]),
                                                    L.ptr(lyr["w_lo"]), L.ptr(lyr["rb"]["nbr"]), lyr["K"],
                                                    L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
                                                    L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),

@@ -5,14 +5,19 @@
 //     D[128 rows, Cout] += A[128 gathered rows, 32 channels] * W[k][Cout, 32 channels]^T
 // is a tcgen05.mma (kind::tf32) on the 3xTF32 hi/lo split (see conv_tc.cu), accumulating in TMEM.
 //
-// Warp roles (12 warps):
-//   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
+// The gather is done by the TMA unit: cp.async.bulk.tensor.2d ... tile::gather4 fetches FOUR arbitrary rows of
+// the [rows, Cin] feature matrix (32 channels = 128 B each) straight into the K-major SWIZZLE_128B A tile; a
+// missing neighbour is an out-of-range row index, which TMA zero-fills without touching memory.  (Probe:
+// tests/cuda/gather4_probe.cu -- box {32,1}, rows land 128 B apart with the standard address swizzle.)
+// One warp issues, per K block, 32 hi + 32 lo gather4 ops (lane l = tile rows 4l..4l+3) plus the two weight
+// tiles, all completing on the stage's mbarrier -- no LSU instructions, no shared-memory bank conflicts
+// (the first version gathered with per-thread 16-byte cp.async: 25-30 % tensor-pipe activity).
+//
+// Warp roles (8 warps):
+//   warp 0      TMA producer (gather4 of A hi/lo + bulk tensor load of W[k] hi/lo)
 //   warp 1      MMA issuer (one elected lane)
 //   warp 2      TMEM allocator
-//   warps 4-7   gather producers: thread r copies row nbr[tile*128+r][k] (hi and lo planes) with 16-byte
-//               cp.async into the K-major SWIZZLE_128B A tile (zero-fill for missing neighbours) and signals the
-//               stage's mbarrier with cp.async.mbarrier.arrive.noinc
-//   warps 8-11  epilogue: drain per-group partial sums from TMEM (round-to-nearest adds in registers, the
+//   warps 4-7   epilogue: drain per-group partial sums from TMEM (round-to-nearest adds in registers; the
 //               tensor core's own accumulate is not RN -- see conv_tc.cu), BN scale/shift + ReLU, hi/lo split,
 //               one contiguous row store per thread
 // K block = (kernel offset, 32-channel chunk); accumulation group = GROUP offsets (short chains).
@@ -21,21 +26,21 @@
 namespace {
 
 using namespace b2s_tc;
-constexpr int kThreads = 384;
+constexpr int kThreads = 256;
 constexpr int GROUP = 3;        // kernel offsets per accumulation chain
 constexpr int ACC_SLOTS = 4;
+constexpr int kOobRow = 0x3FFFFFFF;   // row coordinate beyond any tensor: TMA zero-fills
 
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
+__device__ __forceinline__ void tma_gather4(uint32_t smem_dst, const CUtensorMap *map, uint64_t *bar, int col, int r0,
+                                            int r1, int r2, int r3)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+        "%6, %7}], [%2];"
+        ::"r"(smem_dst), "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
 struct SpParams {
-    const float *in_hi, *in_lo;
     const int *nbr;
     const int *n_out_dev;
     int cap_out, K, relu;
@@ -46,7 +51,8 @@ struct SpParams {
 // CIN in {32, 64}; COUT (= UMMA N) in {32, 64}
 template <int CIN, int COUT, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SpParams p)
 {
     constexpr int N = COUT;
@@ -61,6 +67,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[ACC_SLOTS], bar_tempty[ACC_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
+    __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
@@ -73,7 +80,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 128 + 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -88,20 +95,42 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     const uint32_t tmem_base = s_tmem_base;
 
     if (warp == 0) {
-        // ===================== weight TMA producer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int k = 0; k < K; ++k)
-                    for (int ch = 0; ch < KCH; ++ch) {
+        // ===================== TMA producer: gather4 of A (hi, lo) + weight tiles =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            // stage the tile's neighbour table (128 x K ints, contiguous in global memory)
+            __syncwarp();
+            {
+                const int row0 = tile * BLOCK_M;
+                const int valid = min(BLOCK_M, n_out - row0) * K;
+                const int *src = p.nbr + (size_t)row0 * K;
+                for (int i = lane; i < BLOCK_M * K; i += 32) {
+                    int v = i < valid ? __ldg(&src[i]) : -1;
+                    s_nbr[i] = v >= 0 ? v : kOobRow;
+                }
+            }
+            __syncwarp();
+            for (int k = 0; k < K; ++k) {
+                const int r0 = s_nbr[(lane * 4 + 0) * K + k], r1 = s_nbr[(lane * 4 + 1) * K + k];
+                const int r2 = s_nbr[(lane * 4 + 2) * K + k], r3 = s_nbr[(lane * 4 + 3) * K + k];
+                for (int ch = 0; ch < KCH; ++ch) {
+                    if (lane == 0) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
-                        uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
-                        mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
+                        mbar_arrive_expect_tx(&bar_full[stage], STAGE_BYTES);
+                    }
+                    __syncwarp();
+                    uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                    const uint32_t dst = smem_u32(st) + (uint32_t)lane * 512u;     // 4 rows x 128 B per lane
+                    tma_gather4(dst, &map_a_hi, &bar_full[stage], ch * BLOCK_K, r0, r1, r2, r3);
+                    tma_gather4(dst + A_TILE_BYTES, &map_a_lo, &bar_full[stage], ch * BLOCK_K, r0, r1, r2, r3);
+                    if (lane == 0) {
                         tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], ch * BLOCK_K, 0, k);
                         tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], ch * BLOCK_K, 0, k);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -142,47 +171,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== gather producers: one thread per tile row =====================
-        const int r = (warp - 4) * 32 + lane;
-        const uint32_t row_off = (uint32_t)r * 128u;      // 128 B per row in the K-major tile
-        const uint32_t sw = (uint32_t)(r & 7);             // SWIZZLE_128B: 16-byte chunk index ^= row % 8
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int row = tile * BLOCK_M + r;
-            const int *nb = p.nbr + (size_t)row * K;
-            // prefetch this row's whole neighbour list (27 independent loads) so the per-offset loop below is
-            // not a chain of dependent L2 round trips (measured: 25 % tensor-pipe activity without this)
-            int nbv[27];
-#pragma unroll
-            for (int k = 0; k < 27; ++k) nbv[k] = (k < K && row < n_out) ? __ldg(&nb[k]) : -1;
-#pragma unroll
-            for (int k = 0; k < 27; ++k) {
-                if (k >= K) break;
-                const int src = nbv[k];
-                const uint32_t nbytes = src >= 0 ? 16u : 0u;   // src-size 0 -> 16 bytes of zeros
-                const size_t base = (size_t)(src >= 0 ? src : 0) * CIN;
-                for (int ch = 0; ch < KCH; ++ch) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES) + row_off;
-                    const float *gh = p.in_hi + base + ch * BLOCK_K;
-                    const float *gl = p.in_lo + base + ch * BLOCK_K;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint32_t dst = sa + (((uint32_t)j ^ sw) << 4);
-                        cp_async16(dst, gh + j * 4, nbytes);
-                        cp_async16(dst + A_TILE_BYTES, gl + j * 4, nbytes);
-                    }
-                    cp_async_mbar_arrive_noinc(&bar_full[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
-            }
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp >= 8) {
+    } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 8;                 // == warp % 4: TMEM lane quarter
+        const int ew = warp - 4;                 // == warp % 4: TMEM lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -235,7 +226,8 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
 }
 
 template <int CIN, int COUT, int STAGES>
-int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
+int launch(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &w_hi, const CUtensorMap &w_lo,
+           const SpParams &p, int num_sms, cudaStream_t stream)
 {
     constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * 4;
     size_t smem = stage * STAGES + 1024;
@@ -247,14 +239,20 @@ int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, 
     }
     int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles_cap < num_sms ? tiles_cap : num_sms;
-    k_sparse_conv_tc<CIN, COUT, STAGES><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
+    k_sparse_conv_tc<CIN, COUT, STAGES><<<grid, kThreads, smem, stream>>>(a_hi, a_lo, w_hi, w_lo, p);
     B2S_LAUNCH_OK();
     return 0;
 }
 
+int make_map_sw(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims, const cuuint64_t *str,
+                const cuuint32_t *box)
+{
+    return make_map(m, base, rank, dims, str, box);
+}
+
 }  // namespace
 
-extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int cin, const float *w_hi,
+extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in, int cin, const float *w_hi,
                                   const float *w_lo, const int *nbr, int K, const int *num_out_dev, int cap_out,
                                   const float *scale, const float *shift, int relu, float *out_hi, float *out_lo,
                                   int cout, void *stream_)
@@ -262,7 +260,7 @@ extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, in
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE((cin == 32 || cin == 64) && (cout == 32 || cout == 64),
                 "b2s_sparse_conv_tc: built for Cin, Cout in {32, 64} (thin layers use b2s_sparse_conv)");
-    B2S_REQUIRE(K >= 1 && K <= 27 && cap_out >= 0, "b2s_sparse_conv_tc: K must be 1..27");
+    B2S_REQUIRE(K >= 1 && K <= 27 && cap_out >= 0 && rows_in >= 1, "b2s_sparse_conv_tc: K must be 1..27, rows_in >= 1");
     if (cap_out == 0) return 0;
     static int num_sms = 0;
     if (!num_sms) {
@@ -270,17 +268,26 @@ extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, in
         B2S_CUDA_OK(cudaGetDevice(&dev));
         B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // weights [K][Cout][Cin] (K-major B operand), hi and lo planes
-    CUtensorMap m_hi, m_lo;
-    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)K};
-    cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout * cin * 4};
-    cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
-    if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
+    // A: feature planes [rows_in, Cin], gathered 4 rows x 32 channels at a time (box {32, 1})
+    CUtensorMap a_hi, a_lo, m_hi, m_lo;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)rows_in};
+        cuuint64_t str[1] = {(cuuint64_t)cin * 4};
+        cuuint32_t box[2] = {BLOCK_K, 1};
+        if (make_map_sw(&a_hi, feat_hi, 2, dims, str, box) || make_map_sw(&a_lo, feat_lo, 2, dims, str, box)) return -1;
+    }
+    {
+        // weights [K][Cout][Cin] (K-major B operand), hi and lo planes
+        cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)K};
+        cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout * cin * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
+        if (make_map_sw(&m_hi, w_hi, 3, dims, str, box) || make_map_sw(&m_lo, w_lo, 3, dims, str, box)) return -1;
+    }
     SpParams p;
-    p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
+    p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
     p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
-    if (cin == 64 && cout == 64) return launch<64, 64, 4>(m_hi, m_lo, p, num_sms, stream);
-    if (cin == 32 && cout == 64) return launch<32, 64, 4>(m_hi, m_lo, p, num_sms, stream);
-    if (cin == 32 && cout == 32) return launch<32, 32, 4>(m_hi, m_lo, p, num_sms, stream);
-    return launch<64, 32, 4>(m_hi, m_lo, p, num_sms, stream);
+    if (cin == 64 && cout == 64) return launch<64, 64, 4>(a_hi, a_lo, m_hi, m_lo, p, num_sms, stream);
+    if (cin == 32 && cout == 64) return launch<32, 64, 4>(a_hi, a_lo, m_hi, m_lo, p, num_sms, stream);
+    if (cin == 32 && cout == 32) return launch<32, 32, 4>(a_hi, a_lo, m_hi, m_lo, p, num_sms, stream);
+    return launch<64, 32, 4>(a_hi, a_lo, m_hi, m_lo, p, num_sms, stream);
 }

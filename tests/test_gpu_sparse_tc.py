@@ -51,7 +51,7 @@ def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
     o_hi = torch.zeros(rb.num_out, cout, device="cuda")
     o_lo = torch.zeros_like(o_hi)
     scale_d, shift_d, nbr = scale.cuda(), shift.cuda(), rb.nbr.contiguous()   # keep alive across the async launch
-    L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr),
+    L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), f_hi.shape[0], cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr),
                                    27, L.ptr(rb.num_out_dev), rb.num_out, L.ptr(scale_d), L.ptr(shift_d), 1,
                                    L.ptr(o_hi), L.ptr(o_lo), cout, L.stream()), "b2s_sparse_conv_tc")
     torch.cuda.synchronize()
