@@ -235,6 +235,11 @@ int launch(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &
 
 }  // namespace
 
+// conv3x3_tc.cu
+int b2s_conv3x3_tc_halo(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
+                        const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
+                        float *out_lo, int out_stride, int num_sms, cudaStream_t stream);
+
 extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
                              const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
                              int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream_)
@@ -251,6 +256,15 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
         B2S_CUDA_OK(cudaGetDevice(&dev));
         B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
+    // 3x3, Cout 128, hi/lo halo-padded output: the halo-tile kernel (conv3x3_tc.cu) moves ~42 % fewer bytes
+    static int use_halo = -1;
+    if (use_halo < 0) {
+        const char *e = getenv("B2S_CONV_HALO");
+        use_halo = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_halo && taps == 9 && n_pad == 128 && out_lo != nullptr && out_padded)
+        return b2s_conv3x3_tc_halo(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
+                                   out_stride, num_sms, stream);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
