@@ -40,6 +40,7 @@ struct ConvParams {
     int out_stride;          // channels per output pixel row (>= Cout; lets heads write a packed record)
     const float *scale, *shift;
     float *out_hi, *out_lo;
+    int dbg;                 // B2S_CONV_DBG diagnostics (results wrong!): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no drain
 };
 
 template <int N, int STAGES>
@@ -65,6 +66,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[ACC_SLOTS], bar_tempty[ACC_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
+    __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 px x 32 ch transpose tile (padded rows)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BLOCK_K;
@@ -105,6 +107,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                     int dy = (p.taps == 9) ? tap / 3 : 1, dx = (p.taps == 9) ? tap % 3 : 1;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                    if (p.dbg & 1) {
+                        mbar_arrive_expect_tx(&bar_full[stage], A_TILE_BYTES + B_TILE_BYTES);
+                        tma_load_4d(st, &map_a_hi, &bar_full[stage], chunk * BLOCK_K, w0 + dx, h0 + dy, b);
+                        tma_load_3d(st + 2 * A_TILE_BYTES, &map_b_hi, &bar_full[stage], chunk * BLOCK_K, 0, tap);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&bar_full[stage], STAGE_BYTES);
                     tma_load_4d(st, &map_a_hi, &bar_full[stage], chunk * BLOCK_K, w0 + dx, h0 + dy, b);
                     tma_load_4d(st + A_TILE_BYTES, &map_a_lo, &bar_full[stage], chunk * BLOCK_K, w0 + dx, h0 + dy, b);
@@ -138,6 +147,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                            if (p.dbg & 2) {
+                                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (chunk | k) != 0);
+                                continue;
+                            }
                             umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (chunk | k) != 0);
                             umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
                             umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
@@ -175,37 +188,71 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+                if (!(p.dbg & 4)) {
 #pragma unroll
-                for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c0, r);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < N; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + c0, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                        for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);
                 if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
             }
-            if (valid) {
+            // Coalesced stores.  In TMEM layout every lane owns one pixel (128 channels = 512 B), so a direct store is
+            // 32 lanes x 16 B at a 512-B stride: half-filled sectors, 32 L2 transactions per instruction -- measured as
+            // the dominant fixed cost of this kernel (B2S_CONV_DBG sweep, round 1).  Each warp therefore transposes
+            // 32 pixels x 32 channels through a 4.5 KB shared staging tile and writes whole 128-byte lines:
+            // instruction `it` covers pixels it*4 + lane/8, 16-byte chunk lane%8.
+            float *stg = s_stage[ew];
+            const int sp = lane >> 3, sq = lane & 7;
+            size_t gpix[8];
+            bool gok[8];
 #pragma unroll
-                for (int c0 = 0; c0 < N; c0 += 4) {
-                    if (c0 < p.Cout) {
-                        float v[4], lo[4];
+            for (int it = 0; it < 8; ++it) {
+                const int mm = ew * 32 + it * 4 + sp;
+                const int hh = th * TILE_H + mm / TILE_W, ww = tw * TILE_W + mm % TILE_W;
+                gok[it] = (hh < p.H) && (ww < p.W);
+                gpix[it] = p.out_padded ? ((size_t)b * (p.H + 2) + (hh + 1)) * (p.W + 2) + (ww + 1)
+                                        : ((size_t)b * p.H + hh) * p.W + ww;
+            }
+#pragma unroll
+            const int planes = p.out_lo ? 2 : 1;
+            for (int pl_i = 0; pl_i < planes; ++pl_i) {
+                float *outp = pl_i ? p.out_lo : p.out_hi;
+#pragma unroll
+                for (int cc = 0; cc < N; cc += 32) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c0 = 0; c0 < 32; c0 += 4) {
+                        float v[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float x = fmaf(sum[c0 + j], s_scale[c0 + j], s_shift[c0 + j]);
+                            float x = fmaf(sum[cc + c0 + j], s_scale[cc + c0 + j], s_shift[cc + c0 + j]);
                             if (p.relu) x = fmaxf(x, 0.f);
                             // both planes exactly tf32-representable (round-to-nearest)
-                            if (ol) { float hi = to_tf32_rn(x); lo[j] = to_tf32_rn(x - hi); x = hi; }
+                            if (p.out_lo) { float hi = to_tf32_rn(x); x = pl_i ? to_tf32_rn(x - hi) : hi; }
                             v[j] = x;
                         }
-                        *reinterpret_cast<float4 *>(oh + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                        if (ol) *reinterpret_cast<float4 *>(ol + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<float4 *>(stg + lane * 36 + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    __syncwarp();
+                    if (cc + sq * 4 < p.Cout) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            if (!gok[it]) continue;
+                            const size_t off = gpix[it] * p.out_stride + cc + sq * 4;
+                            *reinterpret_cast<float4 *>(outp + off) =
+                                *reinterpret_cast<const float4 *>(stg + (it * 4 + sp) * 36 + sq * 4);
+                        }
                     }
                 }
             }
+            (void)valid; (void)oh; (void)ol;
         }
     }
     tc_fence_before();
@@ -260,7 +307,7 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
     static int use_halo = -1;
     if (use_halo < 0) {
         const char *e = getenv("B2S_CONV_HALO");
-        use_halo = (e && e[0] == '0') ? 0 : 1;
+        use_halo = (e && e[0] == '1') ? 1 : 0;   // EXPERIMENT, off by default: results are wrong so far
     }
     if (use_halo && taps == 9 && n_pad == 128 && out_lo != nullptr && out_padded)
         return b2s_conv3x3_tc_halo(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
@@ -285,6 +332,11 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
     p.tiles_w = (W + TILE_W - 1) / TILE_W;
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.out_padded = out_padded; p.out_stride = out_stride;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("B2S_CONV_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
+    }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     switch (n_pad) {
         case 128: return launch<128, 3>(a_hi, a_lo, b_hi, b_lo, p, num_sms, stream);

@@ -64,6 +64,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
     __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
+    __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 rows x 32 ch transpose tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
@@ -150,12 +151,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         // Lane mapping: one warp instruction covers 4 rows x 8 sixteen-byte chunks, so the 32 lanes write 4 whole
         // 128-byte smem rows (bank-conflict free under the 128B swizzle) and read 4 x 128 contiguous global bytes.
         // (One lane per row -- the first version -- was a 4-way bank conflict on every cp.async.)
-        // Zero rows (missing neighbours, ~70 % of all rows) are written only when the smem row does not already
-        // hold zeros from this thread's previous use of the stage: zmask bit (stage, i) remembers that.
         const int gw = warp - 4;                               // rows 32*gw .. 32*gw+31 of the tile
         const int sub = lane >> 3;                             // row within a group of 4
         const uint32_t chunk = (uint32_t)(lane & 7);           // 16-byte chunk of the 128-byte row
-        uint32_t zmask = 0;
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -179,18 +177,13 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     for (int i = 0; i < 8; ++i) {
                         const int rl = gw * 32 + i * 4 + sub;                  // row inside the tile
                         const int src = srcs[i];
-                        const uint32_t bit = 1u << (stage * 8 + i);
+                        const uint32_t nbytes = src >= 0 ? 16u : 0u;           // src-size 0 -> 16 bytes of zeros
+                        const size_t off = (size_t)(src >= 0 ? src : 0) * CIN + ch * BLOCK_K + chunk * 4;
                         const uint32_t dst = sa + (uint32_t)rl * 128u + ((chunk ^ (uint32_t)(rl & 7)) << 4);
-                        if (src >= 0) {
-                            const size_t off = (size_t)src * CIN + ch * BLOCK_K + chunk * 4;
-                            cp_async16(dst, p.in_hi + off, 16u);
-                            cp_async16(dst + A_TILE_BYTES, p.in_lo + off, 16u);
-                            zmask &= ~bit;
-                        } else if (!(zmask & bit)) {
-                            cp_async16(dst, p.in_hi, 0u);                       // src-size 0 -> 16 bytes of zeros
-                            cp_async16(dst + A_TILE_BYTES, p.in_lo, 0u);
-                            zmask |= bit;
-                        }
+                        // uniform issue (no per-lane branch): skipping already-zero rows was tried and was SLOWER
+                        // (divergent cp.async issue), measured round 1
+                        cp_async16(dst, p.in_hi + off, nbytes);
+                        cp_async16(dst + A_TILE_BYTES, p.in_lo + off, nbytes);
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -225,23 +218,40 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);
                 if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
             }
-            if (row < n_out) {
-                float *oh = p.out_hi + (size_t)row * N;
-                float *ol = p.out_lo ? p.out_lo + (size_t)row * N : nullptr;
+            // coalesced stores: transpose 32 rows x 32 channels through a padded shared tile so every store
+            // instruction writes four whole 128-byte lines (a lane-per-row store is 16 B at a 256-B stride)
+            float *stg = s_stage[ew];
+            const int sp = lane >> 3, sq = lane & 7;
+            const int row_w0 = tile * BLOCK_M + ew * 32;       // first row of this warp
+            const int planes = p.out_lo ? 2 : 1;
+            for (int pl_i = 0; pl_i < planes; ++pl_i) {
+                float *outp = pl_i ? p.out_lo : p.out_hi;
 #pragma unroll
-                for (int c0 = 0; c0 < N; c0 += 4) {
-                    float v[4], lo[4];
+                for (int cc = 0; cc < N; cc += 32) {
+                    __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float x = fmaf(sum[c0 + j], s_scale[c0 + j], s_shift[c0 + j]);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (ol) { float hi = to_tf32_rn(x); lo[j] = to_tf32_rn(x - hi); x = hi; }
-                        v[j] = x;
+                    for (int c0 = 0; c0 < 32; c0 += 4) {
+                        float v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x = fmaf(sum[cc + c0 + j], s_scale[cc + c0 + j], s_shift[cc + c0 + j]);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            if (p.out_lo) { float hi = to_tf32_rn(x); x = pl_i ? to_tf32_rn(x - hi) : hi; }
+                            v[j] = x;
+                        }
+                        *reinterpret_cast<float4 *>(stg + lane * 36 + c0) = make_float4(v[0], v[1], v[2], v[3]);
                     }
-                    *reinterpret_cast<float4 *>(oh + c0) = make_float4(v[0], v[1], v[2], v[3]);
-                    if (ol) *reinterpret_cast<float4 *>(ol + c0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rr = row_w0 + it * 4 + sp;
+                        if (rr < n_out)
+                            *reinterpret_cast<float4 *>(outp + (size_t)rr * N + cc + sq * 4) =
+                                *reinterpret_cast<const float4 *>(stg + (it * 4 + sp) * 36 + sq * 4);
+                    }
                 }
             }
+            (void)row;
         }
     }
     tc_fence_before();

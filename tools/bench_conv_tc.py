@@ -1,0 +1,34 @@
+"""micro-benchmark of b2s_conv2d_tc alone (RPN 3x3 128->128 at car.fhd size), CUDA-event timed.
+B2S_CONV_DBG (diagnostic, wrong results): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no TMEM drain."""
+import os
+import sys
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(REPO, "second.pytorch_b200"))
+import torch
+from b2second import loader, tc
+sp = loader.product_spconv()
+L = sp._lib
+lib = L.load()
+B, H, W, C = 8, 200, 176, 128
+x = torch.randn(B, H + 2, W + 2, C, device="cuda")
+hi, lo = tc.split_tf32(x)
+w = torch.randn(9, C, C, device="cuda") * 0.03
+w_hi, w_lo = tc.split_tf32(w)
+scale = torch.ones(C, device="cuda"); shift = torch.zeros(C, device="cuda")
+o_hi = torch.zeros_like(hi); o_lo = torch.zeros_like(hi)
+flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
+def run():
+    L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, C, L.ptr(w_hi), L.ptr(w_lo), 9, C, 128, L.ptr(scale),
+                              L.ptr(shift), 1, L.ptr(o_hi), L.ptr(o_lo), 1, C, L.stream()), "conv")
+for _ in range(3): run()
+torch.cuda.synchronize()
+ts = []
+for i in range(10):
+    flush.fill_(i)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(); b.record(); torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b))
+ms = sorted(ts)[len(ts) // 2]
+flops = 2.0 * B * H * W * C * C * 9
+print("B2S_CONV_DBG=%s B2S_CONV_HALO=%s  median %.3f ms  algorithmic %.1f TFLOP/s (x3 tf32 issued: %.1f)" % (
+    os.environ.get("B2S_CONV_DBG", "0"), os.environ.get("B2S_CONV_HALO", "0"), ms, flops / ms / 1e9, 3 * flops / ms / 1e9))
