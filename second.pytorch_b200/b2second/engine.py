@@ -471,6 +471,23 @@ class InferenceEngine:
                         "flops": 2 * pairs * cin * cout})
         return out
 
+    def rpn_layer_stats(self):
+        """per tcgen05 RPN layer: algorithmic fp32 flops (2*pixels*taps*cin*cout; the 3xTF32 split issues 3x that on
+        the tensor pipe) and algorithmic bytes (hi/lo planes in and out + weights)."""
+        if self.rpn_impl != "tc":
+            return []
+        _, H, W = self.final_level.shape
+        px = self.B * H * W
+        out = []
+        for i, lyr in enumerate(self.tc_plan):
+            last = i == len(self.tc_plan) - 1
+            cin, cout, taps = lyr["cin"], lyr["cout"], lyr["taps"]
+            planes_out = 1 if last else 2
+            out.append({"index": i, "cin": cin, "cout": cout, "taps": taps, "pixels": px,
+                        "flops": 2 * px * taps * cin * cout,
+                        "bytes": 4 * (2 * px * cin + planes_out * px * cout + 2 * taps * cin * lyr["n_pad"])})
+        return out
+
     # ---------------------------------------------------------------- public API
     def load_points(self, frames):
         """frames: list of B CUDA (or pinned/CPU) float32 [P_i, F] tensors -> static input buffers."""

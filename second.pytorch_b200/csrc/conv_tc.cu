@@ -41,6 +41,7 @@ struct ConvParams {
     const float *scale, *shift;
     float *out_hi, *out_lo;
     int dbg;                 // B2S_CONV_DBG diagnostics (results wrong!): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no drain
+    int chain;               // filter taps per TMEM accumulation chain (1 = per-tap drain; B2S_CONV_CHAIN experiment)
 };
 
 template <int N, int STAGES>
@@ -147,11 +148,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int tap = 0; tap < p.taps; ++tap) {
+                for (int tap0 = 0; tap0 < p.taps; tap0 += p.chain) {
                     mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
-                    for (int chunk = 0; chunk < kchunks; ++chunk) {
+                    const int kb_chain = (min(p.taps, tap0 + p.chain) - tap0) * kchunks;
+                    for (int chunk = 0; chunk < kb_chain; ++chunk) {
                         mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
                         tc_fence_after();
                         const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
@@ -198,7 +200,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;
-            for (int tap = 0; tap < p.taps; ++tap) {
+            for (int tap0 = 0; tap0 < p.taps; tap0 += p.chain) {
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
@@ -296,10 +298,10 @@ int launch(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &
 
 }  // namespace
 
-// conv3x3_tc.cu
-int b2s_conv3x3_tc_halo(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
-                        const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
-                        float *out_lo, int out_stride, int num_sms, cudaStream_t stream);
+// conv_tc2.cu
+int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
+                    const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
+                    float *out_lo, int out_stride, int num_sms, cudaStream_t stream);
 
 extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
                              const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
@@ -317,15 +319,16 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
         B2S_CUDA_OK(cudaGetDevice(&dev));
         B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // 3x3, Cout 128, hi/lo halo-padded output: the halo-tile kernel (conv3x3_tc.cu) moves ~42 % fewer bytes
-    static int use_halo = -1;
-    if (use_halo < 0) {
-        const char *e = getenv("B2S_CONV_HALO");
-        use_halo = (e && e[0] == '1') ? 1 : 0;   // EXPERIMENT, off by default: results are wrong so far
+    // 3x3, n_pad 128, hi/lo halo-padded output: the weights-stationary N=256 kernel (conv_tc2.cu).
+    // B2S_CONV_V2=0 falls back to k_conv_tc below (kept for 1x1 layers, heads and other widths).
+    static int use_v2 = -1;
+    if (use_v2 < 0) {
+        const char *e = getenv("B2S_CONV_V2");
+        use_v2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use_halo && taps == 9 && n_pad == 128 && out_lo != nullptr && out_padded)
-        return b2s_conv3x3_tc_halo(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
-                                   out_stride, num_sms, stream);
+    if (use_v2 && taps == 9 && n_pad == 128 && out_lo != nullptr && out_padded)
+        return b2s_conv3x3_tc2(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
+                               out_stride, num_sms, stream);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
@@ -350,6 +353,9 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("B2S_CONV_DBG"); dbg = e ? atoi(e) : 0; }
         p.dbg = dbg;
+        static int chain = -1;
+        if (chain < 0) { const char *e = getenv("B2S_CONV_CHAIN"); chain = e ? atoi(e) : 1; if (chain < 1) chain = 1; }
+        p.chain = chain;
     }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     switch (n_pad) {

@@ -1,0 +1,259 @@
+// conv_tc2.cu -- 3x3 RPN convolution, second-generation tcgen05 kernel (weights-stationary orientation).
+//
+// Why a second kernel: k_conv_tc (conv_tc.cu) computes D[128 pixels, Cout] with both operands in shared memory.
+// A 128x128x8 tf32 MMA reads 4 KB of A and 4 KB of B from shared memory in its 64 tensor cycles -- exactly the
+// 128 B/clk the shared-memory data pipe can deliver -- so every TMA write into the ring (64 KB per K block) is
+// time the tensor pipe waits.  ncu (profiles/r1_tc_kernels_ncu_full.csv): tensor pipe 59.5 % active,
+// l1tex__data_pipe_tc_wavefronts_mem_shared 57.9 % + TMA writes + epilogue staging = the pipe is full.
+//
+// This kernel removes shared-memory traffic per tensor cycle two ways:
+//   1. orientation swap, N = 256:  D^T[Cout = 128 (M, TMEM lanes), 256 pixels (N, TMEM columns)]
+//          += W[tap][Cout, 32 ch] (A)  *  X[256 pixels, 32 ch]^T (B)
+//      a 128x256x8 MMA reads 4 + 8 KB in 128 tensor cycles = 96 B/clk;
+//   2. vertical reuse: the activation stage is an 18-row x 16-col pixel tile (one 32-channel chunk, one
+//      horizontal tap offset dx).  The three vertical taps dy = 0,1,2 are the SAME stage viewed 16 pixel rows
+//      (= 2048 B = two whole 1024-byte swizzle atoms) further down, so the UMMA descriptor just starts 2048*dy
+//      bytes later -- no swizzle-phase tricks.  Activation bytes written to shared memory drop 2.7x.
+// Per (dx, chunk) group: 72 KB activations + 3 x 32 KB weights written, 36 MMAs (4608 tensor cycles).
+//
+// Accumulation chains stay short (the tensor core's fp32 accumulate truncates: measured rms error grows linearly
+// with chain length, tools/bench_conv_tc.py): one chain = one (dx, chunk) group = 36 MMAs, drained by the
+// epilogue warps into fp32 registers with round-to-nearest adds; two 256-column TMEM accumulators ping-pong.
+//
+// Epilogue without staging: a TMEM lane is an output CHANNEL here, so lane l of a warp holds channel 32q+l of
+// one pixel -- a plain 4-byte store per lane writes 128 contiguous bytes of the NHWC row.
+//
+// Warp roles (12 warps): 0 activation TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 weight TMA producer,
+// 4-11 epilogue (lane quarter = warp % 4, pixel half = (warp - 4) / 4).
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace b2s_tc;
+constexpr int T2_H = 16, T2_W = 16;                 // 256 output pixels per tile
+constexpr int HALO_H = T2_H + 2;                    // rows of the activation stage
+constexpr int N_PIX = T2_H * T2_W;                  // UMMA N
+constexpr int kThreads2 = 384;
+constexpr uint32_t X_PLANE_BYTES = HALO_H * T2_W * BLOCK_K * 4;   // 36 KB (hi or lo)
+constexpr uint32_t X_STAGE_BYTES = 2 * X_PLANE_BYTES;             // 72 KB
+constexpr uint32_t W_PLANE_BYTES = 128 * BLOCK_K * 4;             // 16 KB
+constexpr uint32_t W_STAGE_BYTES = 2 * W_PLANE_BYTES;             // 32 KB
+constexpr int X_STAGES = 2, W_STAGES = 2, ACC2 = 2;
+constexpr uint32_t DY_BYTES = T2_W * BLOCK_K * 4;                 // one pixel row of the tile = 2048 B
+
+struct Conv2Params {
+    int B, H, W, Cin, Cout, relu;
+    int tiles_h, tiles_w, num_tiles;
+    int out_stride;
+    const float *scale, *shift;
+    float *out_hi, *out_lo;          // [B, H+2, W+2, out_stride] halo-padded planes (interior written)
+};
+
+__global__ void __launch_bounds__(kThreads2, 1)
+k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
+              const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+              const Conv2Params p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_x = smem;                                   // X_STAGES x 72 KB
+    uint8_t *smem_w = smem + X_STAGES * X_STAGE_BYTES;        // W_STAGES x 32 KB
+    __shared__ __align__(8) uint64_t bar_xfull[X_STAGES], bar_xempty[X_STAGES], bar_wfull[W_STAGES],
+        bar_wempty[W_STAGES], bar_tfull[ACC2], bar_tempty[ACC2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kchunks = p.Cin / BLOCK_K;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < X_STAGES; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
+        for (int i = 0; i < W_STAGES; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
+        for (int i = 0; i < ACC2; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== activation producer: one 18x16-pixel x 32-channel stage per (dx, chunk) ==========
+        if (lane == 0) {
+            int xs = 0;
+            uint32_t xph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+                const int h0 = th * T2_H, w0 = tw * T2_W;
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int chunk = 0; chunk < kchunks; ++chunk) {
+                        mbar_wait(&bar_xempty[xs], xph ^ 1);
+                        uint8_t *st = smem_x + (size_t)xs * X_STAGE_BYTES;
+                        mbar_arrive_expect_tx(&bar_xfull[xs], X_STAGE_BYTES);
+                        // padded coordinates: output (h, w) reads padded rows h..h+2 and cols w..w+2
+                        tma_load_4d(st, &map_x_hi, &bar_xfull[xs], chunk * BLOCK_K, w0 + dx, h0, b);
+                        tma_load_4d(st + X_PLANE_BYTES, &map_x_lo, &bar_xfull[xs], chunk * BLOCK_K, w0 + dx, h0, b);
+                        if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer: W[tap = dy*3+dx][128, 32 ch] hi/lo per K block ===================
+        if (lane == 0) {
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int chunk = 0; chunk < kchunks; ++chunk)
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(&bar_wempty[ws], wph ^ 1);
+                            uint8_t *st = smem_w + (size_t)ws * W_STAGE_BYTES;
+                            mbar_arrive_expect_tx(&bar_wfull[ws], W_STAGE_BYTES);
+                            tma_load_3d(st, &map_w_hi, &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
+                            tma_load_3d(st + W_PLANE_BYTES, &map_w_lo, &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
+                            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                        }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(N_PIX);
+            int xs = 0, ws = 0, acc = 0;
+            uint32_t xph = 0, wph = 0, aph = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+                for (int g = 0; g < 3 * kchunks; ++g) {
+                    mbar_wait(&bar_tempty[acc], aph ^ 1);            // epilogue has drained this accumulator
+                    mbar_wait(&bar_xfull[xs], xph);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N_PIX);
+                    const uint32_t sx = smem_u32(smem_x + (size_t)xs * X_STAGE_BYTES);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        mbar_wait(&bar_wfull[ws], wph);
+                        tc_fence_after();
+                        const uint32_t sw = smem_u32(smem_w + (size_t)ws * W_STAGE_BYTES);
+                        const uint64_t w_hi = make_desc_sw128(sw), w_lo = make_desc_sw128(sw + W_PLANE_BYTES);
+                        const uint64_t x_hi = make_desc_sw128(sx + dy * DY_BYTES);
+                        const uint64_t x_lo = make_desc_sw128(sx + X_PLANE_BYTES + dy * DY_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                            umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, (dy | k) != 0);
+                            umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, 1);
+                            umma_tf32(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                        }
+                        umma_commit(&bar_wempty[ws]);
+                        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                    }
+                    umma_commit(&bar_xempty[xs]);
+                    umma_commit(&bar_tfull[acc]);                    // this group's partial sum is complete
+                    if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
+                    if (++acc == ACC2) { acc = 0; aph ^= 1; }
+                }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                     // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;           // pixel half: tile rows 8*half .. 8*half+7
+        const int c = q * 32 + lane;                // output channel of this thread
+        const bool c_ok = c < p.Cout;
+        const float sc = (p.scale && c_ok) ? p.scale[c] : 1.f;
+        const float sh = (p.shift && c_ok) ? p.shift[c] : 0.f;
+        int acc = 0;
+        uint32_t aph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
+            float sum[128];
+#pragma unroll
+            for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+            for (int g = 0; g < 3 * kchunks; ++g) {
+                mbar_wait(&bar_tfull[acc], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_PIX + half * 128);
+#pragma unroll
+                for (int c0 = 0; c0 < 128; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[acc]);
+                if (++acc == ACC2) { acc = 0; aph ^= 1; }
+            }
+            // BN scale/shift + ReLU + hi/lo split; lane = channel, so each store instruction writes one pixel's
+            // 32 consecutive channels = one 128-byte line
+            const int hbase = th * T2_H + half * 8, wbase = tw * T2_W;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int h = hbase + r;
+                if (h >= p.H) break;
+                const size_t rowpix = ((size_t)b * (p.H + 2) + (h + 1)) * (p.W + 2) + (wbase + 1);
+                float *oh = p.out_hi + rowpix * p.out_stride + c;
+                float *ol = p.out_lo + rowpix * p.out_stride + c;
+#pragma unroll
+                for (int cw = 0; cw < T2_W; ++cw) {
+                    float x = fmaf(sum[r * 16 + cw], sc, sh);
+                    if (p.relu) x = fmaxf(x, 0.f);
+                    const float hi = to_tf32_rn(x);
+                    const float lo = to_tf32_rn(x - hi);
+                    if (c_ok && wbase + cw < p.W) {
+                        oh[(size_t)cw * p.out_stride] = hi;
+                        ol[(size_t)cw * p.out_stride] = lo;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    }
+}
+
+}  // namespace
+
+// called by b2s_conv2d_tc (conv_tc.cu) for taps == 9, n_pad == 128, halo-padded hi/lo output
+int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
+                    const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
+                    float *out_lo, int out_stride, int num_sms, cudaStream_t stream)
+{
+    using namespace b2s_tc;
+    CUtensorMap x_hi, x_lo, m_w_hi, m_w_lo;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)(W + 2) * Cin * 4, (cuuint64_t)(H + 2) * (W + 2) * Cin * 4};
+        cuuint32_t box[4] = {BLOCK_K, T2_W, HALO_H, 1};
+        if (make_map(&x_hi, in_hi, 4, dims, str, box) || make_map(&x_lo, in_lo, 4, dims, str, box)) return -1;
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Cin, 128, 9};
+        cuuint64_t str[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)128 * Cin * 4};
+        cuuint32_t box[3] = {BLOCK_K, 128, 1};
+        if (make_map(&m_w_hi, w_hi, 3, dims, str, box) || make_map(&m_w_lo, w_lo, 3, dims, str, box)) return -1;
+    }
+    Conv2Params p;
+    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu;
+    p.tiles_h = (H + T2_H - 1) / T2_H;
+    p.tiles_w = (W + T2_W - 1) / T2_W;
+    p.num_tiles = B * p.tiles_h * p.tiles_w;
+    p.out_stride = out_stride;
+    p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
+    const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_STAGE_BYTES + 1024;
+    static bool attr = false;
+    if (!attr) {
+        B2S_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    k_conv3x3_tc2<<<grid, kThreads2, smem, stream>>>(x_hi, x_lo, m_w_hi, m_w_lo, p);
+    B2S_LAUNCH_OK();
+    return 0;
+}

@@ -32,3 +32,15 @@ ms = sorted(ts)[len(ts) // 2]
 flops = 2.0 * B * H * W * C * C * 9
 print("B2S_CONV_DBG=%s B2S_CONV_HALO=%s  median %.3f ms  algorithmic %.1f TFLOP/s (x3 tf32 issued: %.1f)" % (
     os.environ.get("B2S_CONV_DBG", "0"), os.environ.get("B2S_CONV_HALO", "0"), ms, flops / ms / 1e9, 3 * flops / ms / 1e9))
+# accuracy of the merged hi+lo output against an fp64 cuDNN-free reference (frames 0..1)
+if os.environ.get("B2S_CONV_ACC", "1") == "1":
+    nb = 2
+    xin = (hi[:nb].double() + lo[:nb].double()).permute(0, 3, 1, 2)            # [nb, C, H+2, W+2] (halo = padding)
+    wt = (w_hi.double() + w_lo.double()).reshape(3, 3, C, C).permute(2, 3, 0, 1)  # [Cout, Cin, 3, 3]
+    ref = torch.nn.functional.conv2d(xin, wt).clamp_(min=0).permute(0, 2, 3, 1)  # [nb, H, W, C]
+    got = (o_hi[:nb, 1:-1, 1:-1].double() + o_lo[:nb, 1:-1, 1:-1].double())
+    err = (got - ref).abs()
+    print("B2S_CONV_CHAIN=%s  max|err| %.3e  max|ref| %.3e  max-rel %.3e  rms-rel %.3e  mean signed %.3e" % (
+        os.environ.get("B2S_CONV_CHAIN", "1"), err.max().item(), ref.abs().max().item(),
+        (err.max() / ref.abs().max()).item(), (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item(),
+        ((got - ref).mean() / ref.abs().mean()).item()))
