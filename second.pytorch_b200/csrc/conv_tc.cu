@@ -69,7 +69,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     __shared__ float s_scale[N], s_shift[N];
     __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 px x 32 ch transpose tile (padded rows)
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BLOCK_K;
     const int num_kb = p.taps * kchunks;
 
@@ -141,8 +141,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp walks the loops with warp-uniform values, one elected lane issues (tc_common.cuh)
+        {
             constexpr uint32_t idesc = make_idesc_tf32(N);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem0 = smem_u32(smem);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -151,30 +154,33 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                 for (int tap0 = 0; tap0 < p.taps; tap0 += p.chain) {
                     mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
+                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
                     const int kb_chain = (min(p.taps, tap0 + p.chain) - tap0) * kchunks;
                     for (int chunk = 0; chunk < kb_chain; ++chunk) {
                         mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                        const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
                         const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
                         const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
                         const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                            if (p.dbg & 2) {
-                                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (chunk | k) != 0);
-                                continue;
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                                if (p.dbg & 2) {
+                                    umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, (chunk | k) != 0);
+                                    continue;
+                                }
+                                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (chunk | k) != 0);
+                                umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
+                                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
                             }
-                            umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (chunk | k) != 0);
-                            umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
-                            umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                            umma_commit(&bar_empty[stage]);          // frees the smem stage when the MMAs retire
+                            if (chunk == kb_chain - 1) umma_commit(&bar_tfull[acc]);   // chain's partial sum complete
                         }
-                        umma_commit(&bar_empty[stage]);              // frees the smem stage when the MMAs retire
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(&bar_tfull[acc]);                    // this tap's partial sum is complete
                     if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
                 }
             }

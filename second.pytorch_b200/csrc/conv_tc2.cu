@@ -37,8 +37,11 @@ constexpr int kThreads2 = 384;
 constexpr uint32_t X_PLANE_BYTES = HALO_H * T2_W * BLOCK_K * 4;   // 36 KB (hi or lo)
 constexpr uint32_t X_STAGE_BYTES = 2 * X_PLANE_BYTES;             // 72 KB
 constexpr uint32_t W_PLANE_BYTES = 128 * BLOCK_K * 4;             // 16 KB
-constexpr uint32_t W_STAGE_BYTES = 2 * W_PLANE_BYTES;             // 32 KB
-constexpr int X_STAGES = 2, W_STAGES = 2, ACC2 = 2;
+// Weight ring: 5 slots of ONE plane each (hi and lo alternate).  A K block issues its 8 W_hi MMAs first and frees
+// the hi slot, then its 4 W_lo MMAs -- so a slot is refilled two full K blocks (~3000 tensor cycles) before it is
+// needed.  (First version: 2 slots of hi+lo = one K block of lead -> the MMA issuer waited on weight loads,
+// 0.371 ms/layer; measured round 1.)
+constexpr int X_STAGES = 2, W_STAGES = 5, ACC2 = 2;
 constexpr uint32_t DY_BYTES = T2_W * BLOCK_K * 4;                 // one pixel row of the tile = 2048 B
 
 struct Conv2Params {
@@ -57,12 +60,12 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *smem_x = smem;                                   // X_STAGES x 72 KB
-    uint8_t *smem_w = smem + X_STAGES * X_STAGE_BYTES;        // W_STAGES x 32 KB
+    uint8_t *smem_w = smem + X_STAGES * X_STAGE_BYTES;        // W_STAGES x 16 KB
     __shared__ __align__(8) uint64_t bar_xfull[X_STAGES], bar_xempty[X_STAGES], bar_wfull[W_STAGES],
         bar_wempty[W_STAGES], bar_tfull[ACC2], bar_tempty[ACC2];
     __shared__ uint32_t s_tmem_base;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BLOCK_K;
 
     if (warp == 1 && lane == 0) {
@@ -109,51 +112,69 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
                 for (int dx = 0; dx < 3; ++dx)
                     for (int chunk = 0; chunk < kchunks; ++chunk)
-                        for (int dy = 0; dy < 3; ++dy) {
-                            mbar_wait(&bar_wempty[ws], wph ^ 1);
-                            uint8_t *st = smem_w + (size_t)ws * W_STAGE_BYTES;
-                            mbar_arrive_expect_tx(&bar_wfull[ws], W_STAGE_BYTES);
-                            tma_load_3d(st, &map_w_hi, &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
-                            tma_load_3d(st + W_PLANE_BYTES, &map_w_lo, &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
-                            if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-                        }
+                        for (int dy = 0; dy < 3; ++dy)
+                            for (int pl = 0; pl < 2; ++pl) {           // hi plane, then lo plane
+                                mbar_wait(&bar_wempty[ws], wph ^ 1);
+                                mbar_arrive_expect_tx(&bar_wfull[ws], W_PLANE_BYTES);
+                                tma_load_3d(smem_w + (size_t)ws * W_PLANE_BYTES, pl ? &map_w_lo : &map_w_hi,
+                                            &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
+                                if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(N_PIX);
-            int xs = 0, ws = 0, acc = 0;
-            uint32_t xph = 0, wph = 0, aph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-                for (int g = 0; g < 3 * kchunks; ++g) {
-                    mbar_wait(&bar_tempty[acc], aph ^ 1);            // epilogue has drained this accumulator
-                    mbar_wait(&bar_xfull[xs], xph);
+        // The whole warp walks the loops (all values warp-uniform -> uniform registers); one elected lane issues
+        // the tcgen05 instructions.  See tc_common.cuh: an `if (lane == 0)` issuer costs ~190 cycles per MMA.
+        constexpr uint32_t idesc = make_idesc_tf32(N_PIX);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sx0 = smem_u32(smem_x), sw0 = smem_u32(smem_w);
+        int xs = 0, ws = 0, acc = 0;
+        uint32_t xph = 0, wph = 0, aph = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int g = 0; g < 3 * kchunks; ++g) {
+                mbar_wait(&bar_tempty[acc], aph ^ 1);            // epilogue has drained this accumulator
+                mbar_wait(&bar_xfull[xs], xph);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N_PIX);
+                const uint32_t sx = sx0 + (uint32_t)xs * X_STAGE_BYTES;
+                for (int dy = 0; dy < 3; ++dy) {
+                    const uint64_t x_hi = make_desc_sw128(sx + dy * DY_BYTES);
+                    const uint64_t x_lo = make_desc_sw128(sx + X_PLANE_BYTES + dy * DY_BYTES);
+                    mbar_wait(&bar_wfull[ws], wph);                  // W_hi plane
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N_PIX);
-                    const uint32_t sx = smem_u32(smem_x + (size_t)xs * X_STAGE_BYTES);
-                    for (int dy = 0; dy < 3; ++dy) {
-                        mbar_wait(&bar_wfull[ws], wph);
-                        tc_fence_after();
-                        const uint32_t sw = smem_u32(smem_w + (size_t)ws * W_STAGE_BYTES);
-                        const uint64_t w_hi = make_desc_sw128(sw), w_lo = make_desc_sw128(sw + W_PLANE_BYTES);
-                        const uint64_t x_hi = make_desc_sw128(sx + dy * DY_BYTES);
-                        const uint64_t x_lo = make_desc_sw128(sx + X_PLANE_BYTES + dy * DY_BYTES);
+                    const uint64_t w_hi = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
+                    if (elect_one_sync()) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                            umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, (dy | k) != 0);
-                            umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, 1);
+                            umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
                             umma_tf32(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
                         }
                         umma_commit(&bar_wempty[ws]);
-                        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                     }
-                    umma_commit(&bar_xempty[xs]);
-                    umma_commit(&bar_tfull[acc]);                    // this group's partial sum is complete
-                    if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
-                    if (++acc == ACC2) { acc = 0; aph ^= 1; }
+                    __syncwarp();
+                    if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                    mbar_wait(&bar_wfull[ws], wph);                  // W_lo plane
+                    tc_fence_after();
+                    const uint64_t w_lo = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
+                    if (elect_one_sync()) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                            umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
+                        }
+                        umma_commit(&bar_wempty[ws]);
+                        if (dy == 2) {
+                            umma_commit(&bar_xempty[xs]);
+                            umma_commit(&bar_tfull[acc]);            // this group's partial sum is complete
+                        }
+                    }
+                    __syncwarp();
+                    if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
                 }
-        }
+                if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
+                if (++acc == ACC2) { acc = 0; aph ^= 1; }
+            }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                     // TMEM lane quarter this warp may read
@@ -246,7 +267,7 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.out_stride = out_stride;
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
-    const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_STAGE_BYTES + 1024;
+    const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;
     static bool attr = false;
     if (!attr) {
         B2S_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

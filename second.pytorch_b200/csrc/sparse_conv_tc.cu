@@ -66,7 +66,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
     __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 rows x 32 ch transpose tile
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
     const int num_tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
     const int K = p.K;
@@ -109,39 +109,44 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // whole warp walks the loops with warp-uniform values, one elected lane issues (tc_common.cuh)
+        {
             constexpr uint32_t idesc = make_idesc_tf32(N);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t smem0 = smem_u32(smem);
+            const int n_out_u = __shfl_sync(0xffffffffu, n_out, 0);
+            const int num_tiles_u = (n_out_u + BLOCK_M - 1) / BLOCK_M;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
                 for (int g = 0; g < num_groups; ++g) {
                     mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(acc * N);
-                    const int k_end = min(K, (g + 1) * GROUP);
-                    bool first = true;
-                    for (int k = g * GROUP; k < k_end; ++k)
-                        for (int ch = 0; ch < KCH; ++ch) {
-                            mbar_wait(&bar_full[stage], phase);
-                            tc_fence_after();
-                            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-                            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                            const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
-                            const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
+                    const int kb_end = (min(K, (g + 1) * GROUP) - g * GROUP) * KCH;   // K blocks of this chain
+                    for (int kb = 0; kb < kb_end; ++kb) {
+                        mbar_wait(&bar_full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                        const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
+                        const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                        if (elect_one_sync()) {
 #pragma unroll
                             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                                 const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, first ? 0u : 1u);
-                                first = false;
+                                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | kk) != 0);
                                 umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
                                 umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
                             }
                             umma_commit(&bar_empty[stage]);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            if (kb == kb_end - 1) umma_commit(&bar_tfull[acc]);
                         }
-                    umma_commit(&bar_tfull[acc]);
+                        __syncwarp();
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                     if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
                 }
             }

@@ -13,6 +13,25 @@ constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// Warp-uniform role dispatch.  tcgen05.mma / tcgen05.commit take their operands from UNIFORM registers.  If the
+// issuing code sits in a divergent region (`if (lane == 0) { ... }`), the compiler cannot prove the descriptors
+// warp-uniform and wraps every UTCHMMA in an ELECT / R2UR / BRA.U.ANY "waterfall" loop: ~190 issue cycles per MMA
+// measured with ncu source counters (round 1) -- more than the 64..128 tensor cycles the MMA itself takes, i.e. the
+// issuing thread, not the tensor pipe or shared memory, was the bottleneck of all three tcgen05 kernels.
+// So: the whole warp runs the role's loops with provably uniform values (warp index through a shuffle, the way
+// CUTLASS does it) and one lane is elected only around the asynchronous instructions themselves.
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -44,3 +44,17 @@ if os.environ.get("B2S_CONV_ACC", "1") == "1":
         os.environ.get("B2S_CONV_CHAIN", "1"), err.max().item(), ref.abs().max().item(),
         (err.max() / ref.abs().max()).item(), (err.pow(2).mean().sqrt() / ref.pow(2).mean().sqrt()).item(),
         ((got - ref).mean() / ref.abs().mean()).item()))
+# SM clock / power while the kernel runs back to back (is the tensor pipe power-capped?)
+if os.environ.get("B2S_CONV_CLOCKS", "0") == "1":
+    import subprocess, threading
+    rows = []
+    pr = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap",
+                           "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+    th = threading.Thread(target=lambda: [rows.append(l.strip()) for l in pr.stdout], daemon=True); th.start()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(4000): run()
+    b.record(); torch.cuda.synchronize()
+    pr.terminate()
+    print("back-to-back: %.3f ms/launch; nvidia-smi samples (MHz, W, power-cap): %s" % (a.elapsed_time(b) / 4000, rows[3:-1][::4]))
