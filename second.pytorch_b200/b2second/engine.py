@@ -447,7 +447,7 @@ class InferenceEngine:
             n += 1                               # b2s_pfn
         for lyr in self.layers:
             if lyr["build_rb"]:
-                n += 1 if lyr["conv"].subm else 5   # subm_nbr | mark, popc_scan, scan_sums, emit, conv_nbr
+                n += 1 if lyr["conv"].subm else 6   # subm_nbr | mark, popc_scan, scan_sums, emit, hash_build, conv_nbr
             n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc
             if lyr.get("in_split") is not None:
                 n += 1                           # b2s_split_tf32
