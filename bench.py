@@ -301,20 +301,30 @@ def run_gpu_arm(args):
                    "algorithmic_flops_per_step": conv_flops, "ms_per_step": conv_ms,
                    "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0}
     sparse_roof["frac"] = sparse_roof["achieved"] / hbm_peak
-    rstats = eng.rpn_layer_stats()
-    rpn_ms = stages.get("rpn", 0.0)
-    if rstats and rpn_ms >= conv_ms:
-        # dominant kernel = k_conv_tc (dense RPN, implicit GEMM on tcgen05, 3xTF32 split for fp32-grade results).
-        # `achieved` counts ALGORITHMIC fp32 flops (2*px*taps*cin*cout); the tensor pipe executes 3 tf32 MMAs per
-        # algorithmic MAC, so the ceiling for this arithmetic is bf16_peak/2 (tf32 rate) /3 -- reported alongside.
+    rstats = [s for s in eng.rpn_layer_stats() if s["taps"] == 9]
+    rpn_ms = stages.get("rpn", 0.0)            # the 3x3 stack only (the 1x1 tail is stage "rpn_1x1")
+    if rstats and rpn_ms >= 0.5 * conv_ms:
+        # dominant kernel = k_conv3x3_tc2 (dense RPN 3x3 layers, implicit GEMM on tcgen05, 3xTF32 split for
+        # fp32-grade results).  `achieved` counts ALGORITHMIC fp32 flops per launch (2*px*9*cin*cout) over the
+        # average launch duration; the tensor pipe executes 3 tf32 MMAs per algorithmic MAC and tf32 runs at half
+        # the bf16 rate, so bf16_peak/6 is this arithmetic's ceiling -- reported alongside.
         bf16 = float(peaks.get("bf16_tflops", 1687.0))
-        flops = sum(s["flops"] for s in rstats)
-        ach = flops / (rpn_ms * 1e-3) / 1e12
-        roofline = {"kernel": "k_conv_tc (all %d RPN layers of one step, %d frames)" % (len(rstats), B),
+        n_l = len(rstats)
+        flops = sum(s["flops"] for s in rstats) / n_l
+        launch_ms = rpn_ms / n_l
+        ach = flops / (launch_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # dram read+write bytes per launch from the committed ncu --set full capture of this kernel
+            traffic = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))["k_conv3x3_tc2"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"kernel": "k_conv3x3_tc2 (per launch; %d launches per step, %d frames)" % (n_l, B),
                     "bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                    "traffic": None, "peak_source": "measured bf16 dense" if peaks else "fallback",
-                    "algorithmic_flops_per_step": flops, "algorithmic_bytes_per_step": sum(s["bytes"] for s in rstats),
-                    "ms_per_step": rpn_ms, "issued_tf32_tflops": 3 * ach, "tf32_peak": bf16 / 2,
+                    "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full)",
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback",
+                    "algorithmic_flops_per_launch": flops,
+                    "algorithmic_bytes_per_launch": sum(s["bytes"] for s in rstats) / n_l,
+                    "ms_per_launch": launch_ms, "issued_tf32_tflops": 3 * ach, "tf32_peak": bf16 / 2,
                     "frac_of_tf32_pipe": 3 * ach / (bf16 / 2),
                     "note": "fp32-parity arithmetic: each MAC = 3 tf32 MMAs (hi*hi, hi*lo, lo*hi); tf32 runs at half "
                             "the bf16 rate, so 1/6 of the bf16 peak is this kernel's arithmetic ceiling",

@@ -377,13 +377,19 @@ class InferenceEngine:
         self._mark("rpn")
         src = self.tc_bev
         bufs = [self.tc_ping, self.tc_pong]
+        marked_1x1 = False
         for i, lyr in enumerate(self.tc_plan[:-1]):
+            if lyr["taps"] == 1 and not marked_1x1:
+                self._mark("rpn_1x1")          # the 3x3 stack (k_conv3x3_tc2) is timed apart from the 1x1 tail
+                marked_1x1 = True
             dst = bufs[i % 2]
             L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, lyr["cin"], L.ptr(lyr["w_hi"]),
                                       L.ptr(lyr["w_lo"]), lyr["taps"], lyr["cout"], lyr["n_pad"], L.ptr(lyr["scale"]),
                                       L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(dst[0]), L.ptr(dst[1]), 1,
                                       lyr["cout"], st), "b2s_conv2d_tc")
             src = dst
+        if not marked_1x1:
+            self._mark("rpn_1x1")
         hd = self.tc_plan[-1]
         S = self.tc_head_stride
         L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, hd["cin"], L.ptr(hd["w_hi"]),

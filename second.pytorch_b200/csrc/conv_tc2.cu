@@ -48,6 +48,7 @@ struct Conv2Params {
     int B, H, W, Cin, Cout, relu;
     int tiles_h, tiles_w, num_tiles;
     int out_stride;
+    int coll;                        // use the A collector buffer for the two W_hi MMAs (B2S_CONV_COLL, default 1)
     const float *scale, *shift;
     float *out_hi, *out_lo;          // [B, H+2, W+2, out_stride] halo-padded planes (interior written)
 };
@@ -147,8 +148,13 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                            umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
-                            umma_tf32(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                            if (p.coll) {     // W_hi fetched from shared memory once for the two MMAs
+                                umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
+                                umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                            } else {
+                                umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
+                                umma_tf32(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                            }
                         }
                         umma_commit(&bar_wempty[ws]);
                     }
@@ -266,6 +272,11 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
     p.tiles_w = (W + T2_W - 1) / T2_W;
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.out_stride = out_stride;
+    {
+        static int coll = -1;
+        if (coll < 0) { const char *e = getenv("B2S_CONV_COLL"); coll = (e && e[0] == '0') ? 0 : 1; }
+        p.coll = coll;
+    }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;
     static bool attr = false;
