@@ -129,58 +129,82 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         constexpr uint32_t idesc = make_idesc_tf32(N_PIX);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t sx0 = smem_u32(smem_x), sw0 = smem_u32(smem_w);
-        int xs = 0, ws = 0, acc = 0;
-        uint32_t xph = 0, wph = 0, aph = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
-            for (int g = 0; g < 3 * kchunks; ++g) {
-                mbar_wait(&bar_tempty[acc], aph ^ 1);            // epilogue has drained this accumulator
-                mbar_wait(&bar_xfull[xs], xph);
-                tc_fence_after();
+        // Software-pipelined issue: the barrier of the NEXT burst's operands is waited for while the current burst
+        // still has MMAs to issue, so the tensor queue never runs dry between bursts.  (tests/cuda/mma_probe2.cu
+        // shows the pipe sustains 128 cycles per N=256 MMA on exactly this operand pattern; with a
+        // wait -> fence -> elect -> issue sequence between bursts the kernel measured 188.)
+        const int my_tiles = (blockIdx.x < (unsigned)p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int total_g = my_tiles * 3 * kchunks;
+        if (elect_one_sync() && total_g > 0) {
+            int xs = 0, ws = 0, acc = 0;
+            uint32_t xph = 0, wph = 0, aph = 0;
+            mbar_wait(&bar_tempty[0], 1);
+            mbar_wait(&bar_xfull[0], 0);
+            mbar_wait(&bar_wfull[0], 0);
+            tc_fence_after();
+            for (int gi = 0; gi < total_g; ++gi) {
                 const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N_PIX);
                 const uint32_t sx = sx0 + (uint32_t)xs * X_STAGE_BYTES;
                 for (int dy = 0; dy < 3; ++dy) {
                     const uint64_t x_hi = make_desc_sw128(sx + dy * DY_BYTES);
                     const uint64_t x_lo = make_desc_sw128(sx + X_PLANE_BYTES + dy * DY_BYTES);
-                    mbar_wait(&bar_wfull[ws], wph);                  // W_hi plane
-                    tc_fence_after();
                     const uint64_t w_hi = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
-                    if (elect_one_sync()) {
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                            if (p.coll) {     // W_hi fetched from shared memory once for the two MMAs
-                                umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
-                                umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
-                            } else {
-                                umma_tf32(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
-                                umma_tf32(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
-                            }
-                        }
-                        umma_commit(&bar_wempty[ws]);
+                    for (int k = 0; k < 3; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
+                        umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
+                        umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
                     }
-                    __syncwarp();
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-                    mbar_wait(&bar_wfull[ws], wph);                  // W_lo plane
+                    // look ahead: the W_lo plane of this K block
+                    int wsn = ws + 1;
+                    uint32_t wphn = wph;
+                    if (wsn == W_STAGES) { wsn = 0; wphn ^= 1; }
+                    mbar_wait(&bar_wfull[wsn], wphn);
                     tc_fence_after();
-                    const uint64_t w_lo = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
-                    if (elect_one_sync()) {
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
-                        }
-                        umma_commit(&bar_wempty[ws]);
-                        if (dy == 2) {
-                            umma_commit(&bar_xempty[xs]);
-                            umma_commit(&bar_tfull[acc]);            // this group's partial sum is complete
-                        }
+                    {
+                        const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
+                        umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, 1);
+                        umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
                     }
-                    __syncwarp();
-                    if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                    umma_commit(&bar_wempty[ws]);
+                    ws = wsn; wph = wphn;
+                    const uint64_t w_lo = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                        umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
+                    }
+                    // look ahead: the next K block's W_hi plane, and at a group boundary the next accumulator and
+                    // activation stage
+                    wsn = ws + 1; wphn = wph;
+                    if (wsn == W_STAGES) { wsn = 0; wphn ^= 1; }
+                    const bool last = (gi == total_g - 1) && (dy == 2);
+                    if (!last) {
+                        mbar_wait(&bar_wfull[wsn], wphn);
+                        if (dy == 2) {
+                            const int accn = acc ^ 1, xsn = xs ^ 1;
+                            mbar_wait(&bar_tempty[accn], (accn == 0 ? (aph ^ 1) : aph) ^ 1);
+                            mbar_wait(&bar_xfull[xsn], xsn == 0 ? (xph ^ 1) : xph);
+                        }
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (int k = 2; k < 4; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
+                        umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
+                    }
+                    umma_commit(&bar_wempty[ws]);
+                    if (dy == 2) {
+                        umma_commit(&bar_xempty[xs]);
+                        umma_commit(&bar_tfull[acc]);            // this group's partial sum is complete
+                    }
+                    ws = wsn; wph = wphn;
                 }
                 if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
                 if (++acc == ACC2) { acc = 0; aph ^= 1; }
             }
+        }
+        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;                     // TMEM lane quarter this warp may read

@@ -41,6 +41,7 @@ struct SpParams {
     const int *nbr;
     const int *n_out_dev;
     int cap_out, K, relu;
+    int zskip;               // skip shared-memory writes for empty neighbours whose slot already holds zeros (B2S_SP_ZSKIP)
     const float *scale, *shift;
     float *out_hi, *out_lo;
 };
@@ -55,8 +56,14 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     constexpr int KCH = CIN / BLOCK_K;                        // 32-channel chunks per offset
     constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    constexpr uint32_t TMEM_COLS = (ACC_SLOTS * N <= 128) ? 128 : (ACC_SLOTS * N <= 256) ? 256 : 512;
-    static_assert(N % 16 == 0 && ACC_SLOTS * N <= 512, "TMEM capacity");
+    // B-operand concatenation: the stage holds W_hi (N rows) directly followed by W_lo (N rows), so ONE MMA with
+    // UMMA N = 2N computes A_hi*W_hi (accumulator columns [0,N)) and A_hi*W_lo (columns [N,2N)) while reading A_hi
+    // from shared memory once; a second MMA (UMMA N = N) adds A_lo*W_hi into columns [0,N).  Same tensor cycles as
+    // three N-wide MMAs, 22 % fewer shared-memory operand bytes (14 KB instead of 18 KB per K step at N = 64) --
+    // the shared-memory data pipe is what bounds this kernel (ncu, round 1).  The epilogue adds the two halves.
+    constexpr int ACC_W = 2 * N;                              // accumulator slot width in TMEM columns
+    constexpr uint32_t TMEM_COLS = (ACC_SLOTS * ACC_W <= 128) ? 128 : (ACC_SLOTS * ACC_W <= 256) ? 256 : 512;
+    static_assert(N % 16 == 0 && ACC_SLOTS * ACC_W <= 512, "TMEM capacity");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -111,7 +118,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         // ===================== MMA issuer =====================
         // whole warp walks the loops with warp-uniform values, one elected lane issues (tc_common.cuh)
         {
-            constexpr uint32_t idesc = make_idesc_tf32(N);
+            constexpr uint32_t idesc = make_idesc_tf32(N), idesc2 = make_idesc_tf32(2 * N);
             const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
             const uint32_t smem0 = smem_u32(smem);
             const int n_out_u = __shfl_sync(0xffffffffu, n_out, 0);
@@ -124,22 +131,20 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 for (int g = 0; g < num_groups; ++g) {
                     mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
+                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
                     const int kb_end = (min(K, (g + 1) * GROUP) - g * GROUP) * KCH;   // K blocks of this chain
                     for (int kb = 0; kb < kb_end; ++kb) {
                         mbar_wait(&bar_full[stage], phase);
                         tc_fence_after();
                         const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
                         const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                        const uint64_t b_hi = make_desc_sw128(sa + 2 * A_TILE_BYTES);
-                        const uint64_t b_lo = make_desc_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+                        const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
                         if (elect_one_sync()) {
 #pragma unroll
                             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                                 const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                                umma_tf32(tmem_d, a_lo + koff, b_hi + koff, idesc, (kb | kk) != 0);
-                                umma_tf32(tmem_d, a_hi + koff, b_lo + koff, idesc, 1);
-                                umma_tf32(tmem_d, a_hi + koff, b_hi + koff, idesc, 1);
+                                umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
+                                umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
                             }
                             umma_commit(&bar_empty[stage]);
                             if (kb == kb_end - 1) umma_commit(&bar_tfull[acc]);
@@ -161,6 +166,11 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         const uint32_t chunk = (uint32_t)(lane & 7);           // 16-byte chunk of the 128-byte row
         int stage = 0;
         uint32_t phase = 0;
+        // ~70 % of the neighbour slots are empty.  Bit (stage*8 + i) of `zeroed` remembers that this lane's 16-byte
+        // chunks of row slot i in that stage already hold zeros (from an earlier empty neighbour), so an empty
+        // neighbour needs no shared-memory write at all.  All 8 lanes of a row agree (same src), the issue stays
+        // uniform (predication, no branch).
+        uint32_t zeroed = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             // stage the tile's neighbour table in shared memory (coalesced), shared by the 4 gather warps
             asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
@@ -185,10 +195,12 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                         const uint32_t nbytes = src >= 0 ? 16u : 0u;           // src-size 0 -> 16 bytes of zeros
                         const size_t off = (size_t)(src >= 0 ? src : 0) * CIN + ch * BLOCK_K + chunk * 4;
                         const uint32_t dst = sa + (uint32_t)rl * 128u + ((chunk ^ (uint32_t)(rl & 7)) << 4);
-                        // uniform issue (no per-lane branch): skipping already-zero rows was tried and was SLOWER
-                        // (divergent cp.async issue), measured round 1
-                        cp_async16(dst, p.in_hi + off, nbytes);
-                        cp_async16(dst + A_TILE_BYTES, p.in_lo + off, nbytes);
+                        const uint32_t bit = 1u << (stage * 8 + i);
+                        if (src >= 0 || !(zeroed & bit) || !p.zskip) {
+                            cp_async16(dst, p.in_hi + off, nbytes);
+                            cp_async16(dst + A_TILE_BYTES, p.in_lo + off, nbytes);
+                        }
+                        zeroed = (src >= 0) ? (zeroed & ~bit) : (zeroed | bit);
                     }
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -209,14 +221,16 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             for (int g = 0; g < num_groups; ++g) {
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
+                const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_W);
 #pragma unroll
                 for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t rr[16];
-                    tmem_ld16(taddr + c0, rr);
+                    uint32_t rr[16], rl[16];
+                    tmem_ld16(taddr + c0, rr);            // A_hi*W_hi + A_lo*W_hi
+                    tmem_ld16(taddr + N + c0, rl);        // A_hi*W_lo
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
+                    for (int j = 0; j < 16; ++j)
+                        sum[c0 + j] = __fadd_rn(sum[c0 + j], __fadd_rn(__uint_as_float(rr[j]), __uint_as_float(rl[j])));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -311,6 +325,11 @@ extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, in
     if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
     SpParams p;
     p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
+    {
+        static int zs = -1;
+        if (zs < 0) { const char *e = getenv("B2S_SP_ZSKIP"); zs = (e && e[0] == '0') ? 0 : 1; }
+        p.zskip = zs;
+    }
     p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     if (cin == 64 && cout == 64) return launch<64, 64, 4>(m_hi, m_lo, p, num_sms, stream);
     if (cin == 32 && cout == 64) return launch<32, 64, 4>(m_hi, m_lo, p, num_sms, stream);
