@@ -48,7 +48,8 @@ struct Conv2Params {
     int B, H, W, Cin, Cout, relu;
     int tiles_h, tiles_w, num_tiles;
     int out_stride;
-    int coll;                        // use the A collector buffer for the two W_hi MMAs (B2S_CONV_COLL, default 1)
+    int dbg;                         // B2S_CONV2_DBG diagnostics (results wrong): 1 no activation loads, 2 no weight
+                                     // loads, 4 no TMEM drain, 8 no global stores
     const float *scale, *shift;
     float *out_hi, *out_lo;          // [B, H+2, W+2, out_stride] halo-padded planes (interior written)
 };
@@ -97,6 +98,11 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     for (int chunk = 0; chunk < kchunks; ++chunk) {
                         mbar_wait(&bar_xempty[xs], xph ^ 1);
                         uint8_t *st = smem_x + (size_t)xs * X_STAGE_BYTES;
+                        if (p.dbg & 1) {                  // diagnostic: no activation loads (results wrong)
+                            mbar_arrive(&bar_xfull[xs]);
+                            if (++xs == X_STAGES) { xs = 0; xph ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&bar_xfull[xs], X_STAGE_BYTES);
                         // padded coordinates: output (h, w) reads padded rows h..h+2 and cols w..w+2
                         tma_load_4d(st, &map_x_hi, &bar_xfull[xs], chunk * BLOCK_K, w0 + dx, h0, b);
@@ -116,6 +122,11 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                         for (int dy = 0; dy < 3; ++dy)
                             for (int pl = 0; pl < 2; ++pl) {           // hi plane, then lo plane
                                 mbar_wait(&bar_wempty[ws], wph ^ 1);
+                                if (p.dbg & 2) {          // diagnostic: no weight loads (results wrong)
+                                    mbar_arrive(&bar_wfull[ws]);
+                                    if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+                                    continue;
+                                }
                                 mbar_arrive_expect_tx(&bar_wfull[ws], W_PLANE_BYTES);
                                 tma_load_3d(smem_w + (size_t)ws * W_PLANE_BYTES, pl ? &map_w_lo : &map_w_hi,
                                             &bar_wfull[ws], chunk * BLOCK_K, 0, dy * 3 + dx);
@@ -224,13 +235,15 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                 mbar_wait(&bar_tfull[acc], aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * N_PIX + half * 128);
+                if (!(p.dbg & 4)) {
 #pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 16) {
-                    uint32_t r[16];
-                    tmem_ld16(taddr + c0, r);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < 128; c0 += 16) {
+                        uint32_t r[16];
+                        tmem_ld16(taddr + c0, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                        for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(r[j]));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -253,7 +266,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     if (p.relu) x = fmaxf(x, 0.f);
                     const float hi = to_tf32_rn(x);
                     const float lo = to_tf32_rn(x - hi);
-                    if (c_ok && wbase + cw < p.W) {
+                    if (c_ok && wbase + cw < p.W && !(p.dbg & 8)) {
                         oh[(size_t)cw * p.out_stride] = hi;
                         ol[(size_t)cw * p.out_stride] = lo;
                     }
@@ -297,9 +310,9 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.out_stride = out_stride;
     {
-        static int coll = -1;
-        if (coll < 0) { const char *e = getenv("B2S_CONV_COLL"); coll = (e && e[0] == '0') ? 0 : 1; }
-        p.coll = coll;
+        static int dbg = -1;
+        if (dbg < 0) { const char *e = getenv("B2S_CONV2_DBG"); dbg = e ? atoi(e) : 0; }
+        p.dbg = dbg;
     }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;

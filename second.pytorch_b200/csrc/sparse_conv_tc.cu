@@ -23,7 +23,9 @@
 namespace {
 
 using namespace b2s_tc;
-constexpr int kThreads = 384;
+constexpr int GW = 8;                     // gather warps (warps 4 .. 4+GW-1); epilogue = the 4 warps after them
+constexpr int RI = 128 / GW / 4;          // 4-row copy iterations per gather warp and K block
+constexpr int kThreads = 32 * (4 + GW + 4);
 constexpr int GROUP = 3;        // kernel offsets per accumulation chain
 constexpr int ACC_SLOTS = 4;
 
@@ -84,7 +86,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 128 + 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 32 * GW + 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -108,6 +110,11 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     for (int ch = 0; ch < KCH; ++ch) {
                         mbar_wait(&bar_empty[stage], phase ^ 1);
                         uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                        if (p.zskip & 4) {                 // diagnostic: no weight loads (results wrong)
+                            mbar_arrive(&bar_full[stage]);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
                         tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], ch * BLOCK_K, 0, k);
                         tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], ch * BLOCK_K, 0, k);
@@ -123,40 +130,74 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             const uint32_t smem0 = smem_u32(smem);
             const int n_out_u = __shfl_sync(0xffffffffu, n_out, 0);
             const int num_tiles_u = (n_out_u + BLOCK_M - 1) / BLOCK_M;
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
-                for (int g = 0; g < num_groups; ++g) {
-                    mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
-                    const int kb_end = (min(K, (g + 1) * GROUP) - g * GROUP) * KCH;   // K blocks of this chain
-                    for (int kb = 0; kb < kb_end; ++kb) {
-                        mbar_wait(&bar_full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
-                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                        const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
-                        if (elect_one_sync()) {
+            // Software-pipelined single-lane issue: the barriers of the NEXT K block (and, at a chain end, of the next
+            // accumulator) are waited for before the current K block's last two MMAs are issued, so the tensor queue
+            // does not drain between the short 8-MMA bursts (tests/cuda/mma_probe2.cu: 448 cycles per K block when
+            // issued back to back; the wait->fence->elect->issue version measured ~1080).
+            if (elect_one_sync() && blockIdx.x < (unsigned)num_tiles_u) {
+                int stage = 0;
+                uint32_t phase = 0;
+                int acc = 0;
+                uint32_t acc_phase = 0;
+                const bool timing = (p.zskip & 16) != 0;      // B2S_SP_ZSKIP bit 16: print the issuer's wait times
+                long long t_full = 0, t_tempty = 0, t_begin = clock64();
+                int n_kb = 0;
+                mbar_wait(&bar_tempty[0], 1);
+                mbar_wait(&bar_full[0], 0);
+                tc_fence_after();
+                for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
+                    const bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
+                    for (int g = 0; g < num_groups; ++g) {
+                        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
+                        const int kb_end = (min(K, (g + 1) * GROUP) - g * GROUP) * KCH;   // K blocks of this chain
+                        int accn = acc + 1;
+                        uint32_t acc_phase_n = acc_phase;
+                        if (accn == ACC_SLOTS) { accn = 0; acc_phase_n ^= 1; }
+                        for (int kb = 0; kb < kb_end; ++kb) {
+                            const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+                            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                            const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
 #pragma unroll
-                            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                            for (int kk = 0; kk < 3; ++kk) {
                                 const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
                                 umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
                                 umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
                             }
+                            // look ahead
+                            int stn = stage + 1;
+                            uint32_t phn = phase;
+                            if (stn == STAGES) { stn = 0; phn ^= 1; }
+                            const bool chain_end = kb == kb_end - 1;
+                            const bool last = last_tile && chain_end && g == num_groups - 1;
+                            if (!last) {
+                                const long long w0 = timing ? clock64() : 0;
+                                mbar_wait(&bar_full[stn], phn);
+                                const long long w1 = timing ? clock64() : 0;
+                                if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
+                                tc_fence_after();
+                                if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; ++n_kb; }
+                            }
+                            {
+                                const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
+                                umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
+                                umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
+                            }
                             umma_commit(&bar_empty[stage]);
-                            if (kb == kb_end - 1) umma_commit(&bar_tfull[acc]);
+                            if (chain_end) umma_commit(&bar_tfull[acc]);
+                            stage = stn; phase = phn;
                         }
-                        __syncwarp();
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        acc = accn; acc_phase = acc_phase_n;
                     }
-                    if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
                 }
+                if (timing && blockIdx.x == 0)
+                    printf("[sparse_tc<%d,%d>] issuer: %d K blocks, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
+                           "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
+                           (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1), t_tempty,
+                           (double)t_tempty / (n_kb + 1));
             }
+            __syncwarp();
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 4 + GW) {
         // ===================== gather producers =====================
         // Lane mapping: one warp instruction covers 4 rows x 8 sixteen-byte chunks, so the 32 lanes write 4 whole
         // 128-byte smem rows (bank-conflict free under the 128B swizzle) and read 4 x 128 contiguous global bytes.
@@ -171,46 +212,65 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         // neighbour needs no shared-memory write at all.  All 8 lanes of a row agree (same src), the issue stays
         // uniform (predication, no branch).
         uint32_t zeroed = 0;
+        uint32_t dst_off[RI];                                   // swizzled byte offset of (row slot i, chunk) in a stage
+#pragma unroll
+        for (int i = 0; i < RI; ++i) {
+            const uint32_t rl = (uint32_t)(gw * (4 * RI) + i * 4 + sub);
+            dst_off[i] = rl * 128u + ((chunk ^ (rl & 7u)) << 4);
+        }
+        const ptrdiff_t lo_delta = reinterpret_cast<const char *>(p.in_lo) - reinterpret_cast<const char *>(p.in_hi);
+        const bool zskip_on = (p.zskip & 1) != 0;
+        const uint32_t copy_mask = (p.zskip & 2) ? 0u : 0xFFu;  // diagnostic bit 2: no copies at all
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             // stage the tile's neighbour table in shared memory (coalesced), shared by the 4 gather warps
-            asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");     // previous tile's readers are done
             {
                 const int row0 = tile * BLOCK_M;
                 const int valid = min(BLOCK_M, n_out - row0) * K;
                 const int *src = p.nbr + (size_t)row0 * K;
-                for (int i = gw * 32 + lane; i < BLOCK_M * K; i += 128) s_nbr[i] = i < valid ? __ldg(&src[i]) : -1;
+                if (!(p.zskip & 8))                    // (diagnostic bit 8: skip the table staging)
+                    for (int i = gw * 32 + lane; i < BLOCK_M * K; i += 32 * GW) s_nbr[i] = i < valid ? __ldg(&src[i]) : -1;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
+            // The issuer's clock64 instrumentation (B2S_SP_ZSKIP bit 16) showed ~940 of ~1340 cycles per K block spent
+            // waiting for THIS loop, and removing the copies altogether bought only 4 %: the producers were bound by
+            // their own instruction stream (~250 instructions per lane per K block for 16 copies).  Everything that
+            // does not change per K block is therefore hoisted: destination offsets once per kernel, source
+            // pointers / validity once per kernel offset.
             for (int k = 0; k < K; ++k) {
-                int srcs[8];
+                const char *g_hi[RI], *g_lo[RI];   // addresses of this lane's 16-byte chunk of neighbour row i (chunk 0)
+                uint32_t valid = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) srcs[i] = s_nbr[(gw * 32 + i * 4 + sub) * K + k];
-                for (int ch = 0; ch < KCH; ++ch) {
+                for (int i = 0; i < RI; ++i) {
+                    const int src = s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k];
+                    valid |= (src >= 0 ? 1u : 0u) << i;
+                    g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 4);
+                    g_lo[i] = g_hi[i] + lo_delta;
+                }
+#pragma unroll
+                for (int ch = 0; ch < KCH; ++ch) {             // unrolled: ch * 128 folds into the address immediates
                     mbar_wait(&bar_empty[stage], phase ^ 1);
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+                    const uint32_t sa = smem_u32(smem) + (uint32_t)stage * STAGE_BYTES;
+                    const uint32_t zst = (zeroed >> (stage * 8)) & 0xFFu;          // slots of this stage holding zeros
+                    const uint32_t need = (valid | ~zst | (zskip_on ? 0u : 0xFFu)) & copy_mask;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rl = gw * 32 + i * 4 + sub;                  // row inside the tile
-                        const int src = srcs[i];
-                        const uint32_t nbytes = src >= 0 ? 16u : 0u;           // src-size 0 -> 16 bytes of zeros
-                        const size_t off = (size_t)(src >= 0 ? src : 0) * CIN + ch * BLOCK_K + chunk * 4;
-                        const uint32_t dst = sa + (uint32_t)rl * 128u + ((chunk ^ (uint32_t)(rl & 7)) << 4);
-                        const uint32_t bit = 1u << (stage * 8 + i);
-                        if (src >= 0 || !(zeroed & bit) || !p.zskip) {
-                            cp_async16(dst, p.in_hi + off, nbytes);
-                            cp_async16(dst + A_TILE_BYTES, p.in_lo + off, nbytes);
+                    for (int i = 0; i < RI; ++i) {
+                        if (need & (1u << i)) {
+                            const uint32_t nbytes = (valid >> i) & 1u ? 16u : 0u;     // src-size 0 -> 16 bytes of zeros
+                            cp_async16(sa + dst_off[i], g_hi[i] + ch * (BLOCK_K * 4), nbytes);
+                            cp_async16(sa + dst_off[i] + A_TILE_BYTES, g_lo[i] + ch * (BLOCK_K * 4), nbytes);
                         }
-                        zeroed = (src >= 0) ? (zeroed & ~bit) : (zeroed | bit);
                     }
+                    zeroed = (zeroed & ~(0xFFu << (stage * 8))) | ((~valid & 0xFFu) << (stage * 8));
                     cp_async_mbar_arrive_noinc(&bar_full[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp >= 8) {
+    } else if (warp >= 4 + GW) {
         // ===================== epilogue =====================
-        const int ew = warp - 8;                 // == warp % 4: TMEM lane quarter
+        const int ew = warp - (4 + GW);                // == warp % 4: TMEM lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -224,13 +284,15 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_W);
 #pragma unroll
                 for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t rr[16], rl[16];
+                    uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);            // A_hi*W_hi + A_lo*W_hi
-                    tmem_ld16(taddr + N + c0, rl);        // A_hi*W_lo
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        sum[c0 + j] = __fadd_rn(sum[c0 + j], __fadd_rn(__uint_as_float(rr[j]), __uint_as_float(rl[j])));
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
+                    tmem_ld16(taddr + N + c0, rr);        // A_hi*W_lo
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -327,7 +389,9 @@ extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, in
     p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
     {
         static int zs = -1;
-        if (zs < 0) { const char *e = getenv("B2S_SP_ZSKIP"); zs = (e && e[0] == '0') ? 0 : 1; }
+        // bit 0: zero-slot skip (default on); diagnostics with wrong results: 2 no gather copies, 4 no weight
+        // loads, 8 no neighbour-table staging
+        if (zs < 0) { const char *e = getenv("B2S_SP_ZSKIP"); zs = e ? atoi(e) : 1; }
         p.zskip = zs;
     }
     p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
