@@ -166,8 +166,10 @@ class InferenceEngine:
                 max_ws = max(max_ws, self.lib.b2s_rulebook_conv_workspace_bytes(self.B, self._L.i3(out_shape)))
                 level = new
             lyr["out"] = torch.zeros(lyr["out_level"].cap, m.out_channels, dtype=torch.float32, device=self.dev)
-            # tensor-pipe core (csrc/sparse_conv_tc.cu) for the wide layers; thin layers stay on the fp32 FMA core
-            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in (32, 64) and m.out_channels in (32, 64))
+            # tensor-pipe core (csrc/sparse_conv_tc.cu); thin layers (Cin 4/16) pack 8/2 kernel offsets per K block.
+            # Other widths (e.g. 3 input features) stay on the fp32 FMA core.
+            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in (4, 16, 32, 64)
+                         and m.out_channels in (16, 32, 64) and K <= 27)
             self.layers.append(lyr)
             i += 1 + (1 if bn is not None else 0) + (1 if relu else 0)
         # once a layer runs on the tensor pipe all later ones must too (hi/lo planes flow forward)
@@ -181,7 +183,7 @@ class InferenceEngine:
         from . import tc as _tc
         for j, lyr in enumerate(self.layers):
             if lyr["tc"]:
-                lyr["w_hi"], lyr["w_lo"] = _tc.split_tf32(lyr["w"].transpose(1, 2).contiguous())   # [K, Cout, Cin]
+                lyr["w_hi"], lyr["w_lo"] = _tc.split_tf32(_tc.pack_sparse_weights(lyr["w"]))
                 lyr["out_lo"] = torch.zeros_like(lyr["out"])
                 if j == 0 or not self.layers[j - 1]["tc"]:
                     # first tensor-pipe layer: its fp32 input rows are split into hi/lo planes first

@@ -25,6 +25,25 @@ def split_tf32(t):
     return hi.contiguous(), lo.contiguous()
 
 
+SPARSE_TC_CIN = (4, 16, 32, 64)
+SPARSE_TC_COUT = (16, 32, 64)
+
+
+def pack_sparse_weights(w):
+    """spconv weight [K, Cin, Cout] -> the K-major B operand b2s_sparse_conv_tc expects.
+    Cin >= 32: [K, Cout, Cin].  Cin < 32 (4 or 16): PACK = 32/Cin kernel offsets share one 128-byte K block, so the
+    rows are packed [ceil(K/PACK), Cout, 32] with column (offset-in-pack * Cin + cin) and zero columns past K."""
+    K, cin, cout = w.shape
+    wt = w.detach().float().transpose(1, 2).contiguous()            # [K, Cout, Cin]
+    if cin >= 32:
+        return wt
+    pack = 32 // cin
+    nkb = (K + pack - 1) // pack
+    out = torch.zeros(nkb * pack, cout, cin, dtype=wt.dtype, device=wt.device)
+    out[:K] = wt
+    return out.view(nkb, pack, cout, cin).permute(0, 2, 1, 3).reshape(nkb, cout, 32).contiguous()
+
+
 def _fold_bn2d(bn):
     scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
     shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()

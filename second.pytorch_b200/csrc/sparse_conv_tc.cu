@@ -5,19 +5,30 @@
 //     D[128 rows, Cout] += A[128 gathered rows, 32 channels] * W[k][Cout, 32 channels]^T
 // is a tcgen05.mma (kind::tf32) on the 3xTF32 hi/lo split (see conv_tc.cu), accumulating in TMEM.
 //
-// Warp roles (12 warps):
+// K block = one 128-byte-wide slice of the reduction:
+//   Cin >= 32 : (kernel offset k, 32-channel chunk ch)                      -- K * Cin/32 K blocks per tile
+//   Cin <  32 : PACK = 32/Cin consecutive kernel offsets side by side        -- ceil(K / PACK) K blocks per tile
+//               (Cin = 16: 2 offsets x 16 channels, Cin = 4: 8 offsets x 4 channels; the weights arrive
+//               pre-packed as [K block][Cout][32], see b2second/tc.py: pack_sparse_weights)
+//
+// Warp roles (16 warps):
 //   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
-//   warp 1      MMA issuer (one elected lane)
+//   warp 1      MMA issuer (one elected lane, software-pipelined)
 //   warp 2      TMEM allocator
-//   warps 4-7   gather producers: 16-byte cp.async copies of the neighbour rows (hi and lo planes) into the
+//   warps 4-11  gather producers: 16-byte cp.async copies of the neighbour rows (hi and lo planes) into the
 //               K-major SWIZZLE_128B A tile, zero-fill for missing neighbours, completion signalled on the
 //               stage's mbarrier with cp.async.mbarrier.arrive.noinc.  (A TMA tile::gather4 producer was tried
 //               -- tests/cuda/gather4_probe.cu proves the instruction works -- but 64 four-row TMA ops per K
 //               block ran 3x SLOWER than cp.async: ~60+ cycles per gather4 issue, measured round 1.)
-//   warps 8-11  epilogue: drain per-group partial sums from TMEM (round-to-nearest adds in registers, the
+//   warps 12-15 epilogue: drain per-chain partial sums from TMEM (round-to-nearest adds in registers, the
 //               tensor core's own accumulate is not RN -- see conv_tc.cu), BN scale/shift + ReLU, hi/lo split,
-//               one contiguous row store per thread
-// K block = (kernel offset, 32-channel chunk); accumulation group = GROUP offsets (short chains).
+//               coalesced row stores through a small staging tile
+//
+// What bounds it (clock64 instrumentation, B2S_SP_ZSKIP bit 16, round 1): the gather producers' own instruction
+// stream.  With 4 gather warps and address arithmetic inside the K-block loop the MMA issuer waited ~940 of
+// ~1340 cycles per K block for them although the copies themselves cost 4 %; hoisting everything that is constant
+// per kernel offset, unrolling the channel chunks and doubling the gather warps brought the K block to ~760
+// cycles (tensor pipe 448 of them, tests/cuda/mma_probe2.cu).
 #include "tc_common.cuh"
 
 namespace {
@@ -26,7 +37,7 @@ using namespace b2s_tc;
 constexpr int GW = 8;                     // gather warps (warps 4 .. 4+GW-1); epilogue = the 4 warps after them
 constexpr int RI = 128 / GW / 4;          // 4-row copy iterations per gather warp and K block
 constexpr int kThreads = 32 * (4 + GW + 4);
-constexpr int GROUP = 3;        // kernel offsets per accumulation chain
+constexpr int GROUP = 3;                  // kernel offsets per accumulation chain (Cin >= 32)
 constexpr int ACC_SLOTS = 4;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
@@ -43,29 +54,34 @@ struct SpParams {
     const int *nbr;
     const int *n_out_dev;
     int cap_out, K, relu;
-    int zskip;               // skip shared-memory writes for empty neighbours whose slot already holds zeros (B2S_SP_ZSKIP)
+    int flags;               // B2S_SP_ZSKIP: bit 0 zero-slot skip (default on); diagnostics (wrong results): 2 no gather
+                             // copies, 4 no weight loads, 8 no neighbour-table staging; 16 print the issuer's wait times
     const float *scale, *shift;
     float *out_hi, *out_lo;
 };
 
-// CIN in {32, 64}; COUT (= UMMA N) in {32, 64}
+// CIN in {4, 16, 32, 64}; COUT (= UMMA N) in {16, 32, 64}
 template <int CIN, int COUT, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SpParams p)
 {
     constexpr int N = COUT;
-    constexpr int KCH = CIN / BLOCK_K;                        // 32-channel chunks per offset
+    constexpr bool PACKED = CIN < 32;
+    constexpr int PACK = PACKED ? 32 / CIN : 1;               // kernel offsets per K block
+    constexpr int KCH = PACKED ? 1 : CIN / BLOCK_K;           // 32-channel chunks per offset
+    constexpr int CPO = 8 / PACK;                             // 16-byte chunks per offset inside a 128-byte row
+    constexpr int CHAIN_KB = PACKED ? 2 : GROUP * KCH;        // K blocks per accumulation chain (short chains)
     constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     // B-operand concatenation: the stage holds W_hi (N rows) directly followed by W_lo (N rows), so ONE MMA with
-    // UMMA N = 2N computes A_hi*W_hi (accumulator columns [0,N)) and A_hi*W_lo (columns [N,2N)) while reading A_hi
-    // from shared memory once; a second MMA (UMMA N = N) adds A_lo*W_hi into columns [0,N).  Same tensor cycles as
-    // three N-wide MMAs, 22 % fewer shared-memory operand bytes (14 KB instead of 18 KB per K step at N = 64) --
-    // the shared-memory data pipe is what bounds this kernel (ncu, round 1).  The epilogue adds the two halves.
+    // UMMA N = 2N computes A_hi*W_hi (accumulator columns [0,N)) and A_hi*W_lo (columns [N,2N)); a second MMA
+    // (UMMA N = N) adds A_lo*W_hi into columns [0,N).  8 instead of 12 MMAs per K block for the same products
+    // (tests/cuda/mma_probe2.cu: 448 instead of 576 tensor cycles at N = 64).  The epilogue adds the two halves.
     constexpr int ACC_W = 2 * N;                              // accumulator slot width in TMEM columns
     constexpr uint32_t TMEM_COLS = (ACC_SLOTS * ACC_W <= 128) ? 128 : (ACC_SLOTS * ACC_W <= 256) ? 256 : 512;
     static_assert(N % 16 == 0 && ACC_SLOTS * ACC_W <= 512, "TMEM capacity");
+    static_assert(STAGES * 8 <= 32, "zero-slot bookkeeping uses 8 bits per stage");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,13 +89,14 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
     __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
-    __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 rows x 32 ch transpose tile
+    __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 rows x <=32 ch transpose tile
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
     const int num_tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
     const int K = p.K;
-    const int num_groups = (K + GROUP - 1) / GROUP;
+    const int num_kb = PACKED ? (K + PACK - 1) / PACK : K * KCH;
+    const int num_chains = (num_kb + CHAIN_KB - 1) / CHAIN_KB;
 
     if (threadIdx.x < N) {
         s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
@@ -106,111 +123,104 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int k = 0; k < K; ++k)
-                    for (int ch = 0; ch < KCH; ++ch) {
-                        mbar_wait(&bar_empty[stage], phase ^ 1);
-                        uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
-                        if (p.zskip & 4) {                 // diagnostic: no weight loads (results wrong)
-                            mbar_arrive(&bar_full[stage]);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                            continue;
-                        }
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
+                    if (p.flags & 4) {                     // diagnostic: no weight loads (results wrong)
+                        mbar_arrive(&bar_full[stage]);
+                    } else {
+                        const int c0 = PACKED ? 0 : (kb % KCH) * BLOCK_K, c2 = PACKED ? kb : kb / KCH;
                         mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
-                        tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], ch * BLOCK_K, 0, k);
-                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], ch * BLOCK_K, 0, k);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], c0, 0, c2);
+                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], c0, 0, c2);
                     }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // whole warp walks the loops with warp-uniform values, one elected lane issues (tc_common.cuh)
-        {
-            constexpr uint32_t idesc = make_idesc_tf32(N), idesc2 = make_idesc_tf32(2 * N);
-            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-            const uint32_t smem0 = smem_u32(smem);
-            const int n_out_u = __shfl_sync(0xffffffffu, n_out, 0);
-            const int num_tiles_u = (n_out_u + BLOCK_M - 1) / BLOCK_M;
-            // Software-pipelined single-lane issue: the barriers of the NEXT K block (and, at a chain end, of the next
-            // accumulator) are waited for before the current K block's last two MMAs are issued, so the tensor queue
-            // does not drain between the short 8-MMA bursts (tests/cuda/mma_probe2.cu: 448 cycles per K block when
-            // issued back to back; the wait->fence->elect->issue version measured ~1080).
-            if (elect_one_sync() && blockIdx.x < (unsigned)num_tiles_u) {
-                int stage = 0;
-                uint32_t phase = 0;
-                int acc = 0;
-                uint32_t acc_phase = 0;
-                const bool timing = (p.zskip & 16) != 0;      // B2S_SP_ZSKIP bit 16: print the issuer's wait times
-                long long t_full = 0, t_tempty = 0, t_begin = clock64();
-                int n_kb = 0;
-                mbar_wait(&bar_tempty[0], 1);
-                mbar_wait(&bar_full[0], 0);
-                tc_fence_after();
-                for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
-                    const bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
-                    for (int g = 0; g < num_groups; ++g) {
-                        const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
-                        const int kb_end = (min(K, (g + 1) * GROUP) - g * GROUP) * KCH;   // K blocks of this chain
-                        int accn = acc + 1;
-                        uint32_t acc_phase_n = acc_phase;
-                        if (accn == ACC_SLOTS) { accn = 0; acc_phase_n ^= 1; }
-                        for (int kb = 0; kb < kb_end; ++kb) {
-                            const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
-                            const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                            const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
+        // Software-pipelined single-lane issue: the barriers of the NEXT K block (and, at a chain end, of the next
+        // accumulator) are waited for before the current K block's last two MMAs are issued, so the tensor queue
+        // does not drain between the short 8-MMA bursts.
+        constexpr uint32_t idesc = make_idesc_tf32(N), idesc2 = make_idesc_tf32(2 * N);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t smem0 = smem_u32(smem);
+        const int num_tiles_u = __shfl_sync(0xffffffffu, num_tiles, 0);
+        if (elect_one_sync() && blockIdx.x < (unsigned)num_tiles_u) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            const bool timing = (p.flags & 16) != 0;
+            long long t_full = 0, t_tempty = 0, t_begin = clock64();
+            int n_kb = 0;
+            mbar_wait(&bar_tempty[0], 1);
+            mbar_wait(&bar_full[0], 0);
+            tc_fence_after();
+            for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
+                const bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
+                for (int g = 0; g < num_chains; ++g) {
+                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
+                    const int kb_end = min(num_kb, (g + 1) * CHAIN_KB) - g * CHAIN_KB;   // K blocks of this chain
+                    int accn = acc + 1;
+                    uint32_t acc_phase_n = acc_phase;
+                    if (accn == ACC_SLOTS) { accn = 0; acc_phase_n ^= 1; }
+                    for (int kb = 0; kb < kb_end; ++kb) {
+                        const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                        const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
 #pragma unroll
-                            for (int kk = 0; kk < 3; ++kk) {
-                                const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                                umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
-                                umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
-                            }
-                            // look ahead
-                            int stn = stage + 1;
-                            uint32_t phn = phase;
-                            if (stn == STAGES) { stn = 0; phn ^= 1; }
-                            const bool chain_end = kb == kb_end - 1;
-                            const bool last = last_tile && chain_end && g == num_groups - 1;
-                            if (!last) {
-                                const long long w0 = timing ? clock64() : 0;
-                                mbar_wait(&bar_full[stn], phn);
-                                const long long w1 = timing ? clock64() : 0;
-                                if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
-                                tc_fence_after();
-                                if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; ++n_kb; }
-                            }
-                            {
-                                const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
-                                umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
-                                umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
-                            }
-                            umma_commit(&bar_empty[stage]);
-                            if (chain_end) umma_commit(&bar_tfull[acc]);
-                            stage = stn; phase = phn;
+                        for (int kk = 0; kk < 3; ++kk) {
+                            const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
+                            umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
+                            umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
                         }
-                        acc = accn; acc_phase = acc_phase_n;
+                        // look ahead
+                        int stn = stage + 1;
+                        uint32_t phn = phase;
+                        if (stn == STAGES) { stn = 0; phn ^= 1; }
+                        const bool chain_end = kb == kb_end - 1;
+                        const bool last = last_tile && chain_end && g == num_chains - 1;
+                        if (!last) {
+                            const long long w0 = timing ? clock64() : 0;
+                            mbar_wait(&bar_full[stn], phn);
+                            const long long w1 = timing ? clock64() : 0;
+                            if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
+                            tc_fence_after();
+                            if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; ++n_kb; }
+                        }
+                        {
+                            const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
+                            umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
+                            umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
+                        }
+                        umma_commit(&bar_empty[stage]);
+                        if (chain_end) umma_commit(&bar_tfull[acc]);
+                        stage = stn; phase = phn;
                     }
+                    acc = accn; acc_phase = acc_phase_n;
                 }
-                if (timing && blockIdx.x == 0)
-                    printf("[sparse_tc<%d,%d>] issuer: %d K blocks, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
-                           "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
-                           (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1), t_tempty,
-                           (double)t_tempty / (n_kb + 1));
             }
-            __syncwarp();
+            if (timing && blockIdx.x == 0)
+                printf("[sparse_tc<%d,%d>] issuer: %d K blocks, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
+                       "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
+                       (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1), t_tempty,
+                       (double)t_tempty / (n_kb + 1));
         }
+        __syncwarp();
     } else if (warp >= 4 && warp < 4 + GW) {
         // ===================== gather producers =====================
         // Lane mapping: one warp instruction covers 4 rows x 8 sixteen-byte chunks, so the 32 lanes write 4 whole
         // 128-byte smem rows (bank-conflict free under the 128B swizzle) and read 4 x 128 contiguous global bytes.
         // (One lane per row -- the first version -- was a 4-way bank conflict on every cp.async.)
-        const int gw = warp - 4;                               // rows 32*gw .. 32*gw+31 of the tile
+        const int gw = warp - 4;                               // rows 4*RI*gw .. of the tile
         const int sub = lane >> 3;                             // row within a group of 4
         const uint32_t chunk = (uint32_t)(lane & 7);           // 16-byte chunk of the 128-byte row
         int stage = 0;
         uint32_t phase = 0;
         // ~70 % of the neighbour slots are empty.  Bit (stage*8 + i) of `zeroed` remembers that this lane's 16-byte
-        // chunks of row slot i in that stage already hold zeros (from an earlier empty neighbour), so an empty
-        // neighbour needs no shared-memory write at all.  All 8 lanes of a row agree (same src), the issue stays
-        // uniform (predication, no branch).
+        // chunk of row slot i in that stage already holds zeros (from an earlier empty neighbour), so an empty
+        // neighbour needs no shared-memory write at all (predication, uniform issue).
         uint32_t zeroed = 0;
         uint32_t dst_off[RI];                                   // swizzled byte offset of (row slot i, chunk) in a stage
 #pragma unroll
@@ -219,51 +229,73 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             dst_off[i] = rl * 128u + ((chunk ^ (rl & 7u)) << 4);
         }
         const ptrdiff_t lo_delta = reinterpret_cast<const char *>(p.in_lo) - reinterpret_cast<const char *>(p.in_hi);
-        const bool zskip_on = (p.zskip & 1) != 0;
-        const uint32_t copy_mask = (p.zskip & 2) ? 0u : 0xFFu;  // diagnostic bit 2: no copies at all
+        const bool zskip_on = (p.flags & 1) != 0;
+        const uint32_t copy_mask = (p.flags & 2) ? 0u : 0xFFu;  // diagnostic bit 2: no copies at all
+        const uint32_t smem0 = smem_u32(smem);
+
+        // one K block: wait for the stage, issue this lane's (predicated) copies, arrive
+        auto copy_block = [&](uint32_t valid, const char *const *g_hi, const char *const *g_lo, int byte_off) {
+            mbar_wait(&bar_empty[stage], phase ^ 1);
+            const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+            const uint32_t zst = (zeroed >> (stage * 8)) & 0xFFu;          // slots of this stage holding zeros
+            const uint32_t need = (valid | ~zst | (zskip_on ? 0u : 0xFFu)) & copy_mask;
+#pragma unroll
+            for (int i = 0; i < RI; ++i) {
+                if (need & (1u << i)) {
+                    const uint32_t nbytes = (valid >> i) & 1u ? 16u : 0u;     // src-size 0 -> 16 bytes of zeros
+                    cp_async16(sa + dst_off[i], g_hi[i] + byte_off, nbytes);
+                    cp_async16(sa + dst_off[i] + A_TILE_BYTES, g_lo[i] + byte_off, nbytes);
+                }
+            }
+            zeroed = (zeroed & ~(0xFFu << (stage * 8))) | ((~valid & 0xFFu) << (stage * 8));
+            cp_async_mbar_arrive_noinc(&bar_full[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        };
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            // stage the tile's neighbour table in shared memory (coalesced), shared by the 4 gather warps
+            // stage the tile's neighbour table in shared memory (coalesced), shared by the gather warps
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");     // previous tile's readers are done
             {
                 const int row0 = tile * BLOCK_M;
-                const int valid = min(BLOCK_M, n_out - row0) * K;
+                const int valid_n = min(BLOCK_M, n_out - row0) * K;
                 const int *src = p.nbr + (size_t)row0 * K;
-                if (!(p.zskip & 8))                    // (diagnostic bit 8: skip the table staging)
-                    for (int i = gw * 32 + lane; i < BLOCK_M * K; i += 32 * GW) s_nbr[i] = i < valid ? __ldg(&src[i]) : -1;
+                if (!(p.flags & 8))                    // (diagnostic bit 8: skip the table staging)
+                    for (int i = gw * 32 + lane; i < BLOCK_M * K; i += 32 * GW) s_nbr[i] = i < valid_n ? __ldg(&src[i]) : -1;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
-            // The issuer's clock64 instrumentation (B2S_SP_ZSKIP bit 16) showed ~940 of ~1340 cycles per K block spent
-            // waiting for THIS loop, and removing the copies altogether bought only 4 %: the producers were bound by
-            // their own instruction stream (~250 instructions per lane per K block for 16 copies).  Everything that
-            // does not change per K block is therefore hoisted: destination offsets once per kernel, source
-            // pointers / validity once per kernel offset.
-            for (int k = 0; k < K; ++k) {
-                const char *g_hi[RI], *g_lo[RI];   // addresses of this lane's 16-byte chunk of neighbour row i (chunk 0)
-                uint32_t valid = 0;
-#pragma unroll
-                for (int i = 0; i < RI; ++i) {
-                    const int src = s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k];
-                    valid |= (src >= 0 ? 1u : 0u) << i;
-                    g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 4);
-                    g_lo[i] = g_hi[i] + lo_delta;
-                }
-#pragma unroll
-                for (int ch = 0; ch < KCH; ++ch) {             // unrolled: ch * 128 folds into the address immediates
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
-                    const uint32_t sa = smem_u32(smem) + (uint32_t)stage * STAGE_BYTES;
-                    const uint32_t zst = (zeroed >> (stage * 8)) & 0xFFu;          // slots of this stage holding zeros
-                    const uint32_t need = (valid | ~zst | (zskip_on ? 0u : 0xFFu)) & copy_mask;
+            if constexpr (!PACKED) {
+                // addresses and validity are constant per kernel offset; the channel chunks are unrolled so that
+                // ch * 128 folds into the copy instructions' address immediates
+                for (int k = 0; k < K; ++k) {
+                    const char *g_hi[RI], *g_lo[RI];
+                    uint32_t valid = 0;
 #pragma unroll
                     for (int i = 0; i < RI; ++i) {
-                        if (need & (1u << i)) {
-                            const uint32_t nbytes = (valid >> i) & 1u ? 16u : 0u;     // src-size 0 -> 16 bytes of zeros
-                            cp_async16(sa + dst_off[i], g_hi[i] + ch * (BLOCK_K * 4), nbytes);
-                            cp_async16(sa + dst_off[i] + A_TILE_BYTES, g_lo[i] + ch * (BLOCK_K * 4), nbytes);
-                        }
+                        const int src = s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k];
+                        valid |= (src >= 0 ? 1u : 0u) << i;
+                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 4);
+                        g_lo[i] = g_hi[i] + lo_delta;
                     }
-                    zeroed = (zeroed & ~(0xFFu << (stage * 8))) | ((~valid & 0xFFu) << (stage * 8));
-                    cp_async_mbar_arrive_noinc(&bar_full[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int ch = 0; ch < KCH; ++ch) copy_block(valid, g_hi, g_lo, ch * (BLOCK_K * 4));
+                }
+            } else {
+                // PACK offsets side by side: this lane's chunk belongs to offset kb*PACK + chunk/CPO and carries
+                // channels (chunk % CPO)*4 .. +3 of that neighbour's row
+                const int ko = (int)chunk / CPO;
+                const int cofs = ((int)chunk % CPO) * 4;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const int k = kb * PACK + ko;
+                    const char *g_hi[RI], *g_lo[RI];
+                    uint32_t valid = 0;
+#pragma unroll
+                    for (int i = 0; i < RI; ++i) {
+                        const int src = k < K ? s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k] : -1;
+                        valid |= (src >= 0 ? 1u : 0u) << i;
+                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + cofs);
+                        g_lo[i] = g_hi[i] + lo_delta;
+                    }
+                    copy_block(valid, g_hi, g_lo, 0);
                 }
             }
         }
@@ -274,11 +306,10 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int row = tile * BLOCK_M + ew * 32 + lane;
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;
-            for (int g = 0; g < num_groups; ++g) {
+            for (int g = 0; g < num_chains; ++g) {
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_W);
@@ -299,19 +330,22 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);
                 if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
             }
-            // coalesced stores: transpose 32 rows x 32 channels through a padded shared tile so every store
-            // instruction writes four whole 128-byte lines (a lane-per-row store is 16 B at a 256-B stride)
+            // coalesced stores: transpose 32 rows x CW channels through a padded shared tile so every store
+            // instruction writes whole contiguous row segments (a lane-per-row store is 16 B at a row stride)
+            constexpr int CW = N < 32 ? N : 32;                // channels per pass
+            constexpr int CH4 = CW / 4;                        // 16-byte chunks per row segment
+            constexpr int RPI = 32 / CH4;                      // rows per store instruction
             float *stg = s_stage[ew];
-            const int sp = lane >> 3, sq = lane & 7;
+            const int sp = lane / CH4, sq = lane % CH4;
             const int row_w0 = tile * BLOCK_M + ew * 32;       // first row of this warp
             const int planes = p.out_lo ? 2 : 1;
             for (int pl_i = 0; pl_i < planes; ++pl_i) {
                 float *outp = pl_i ? p.out_lo : p.out_hi;
 #pragma unroll
-                for (int cc = 0; cc < N; cc += 32) {
+                for (int cc = 0; cc < N; cc += CW) {
                     __syncwarp();
 #pragma unroll
-                    for (int c0 = 0; c0 < 32; c0 += 4) {
+                    for (int c0 = 0; c0 < CW; c0 += 4) {
                         float v[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -324,15 +358,14 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     }
                     __syncwarp();
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rr = row_w0 + it * 4 + sp;
+                    for (int it = 0; it < 32 / RPI; ++it) {
+                        const int rr = row_w0 + it * RPI + sp;
                         if (rr < n_out)
                             *reinterpret_cast<float4 *>(outp + (size_t)rr * N + cc + sq * 4) =
-                                *reinterpret_cast<const float4 *>(stg + (it * 4 + sp) * 36 + sq * 4);
+                                *reinterpret_cast<const float4 *>(stg + (it * RPI + sp) * 36 + sq * 4);
                     }
                 }
             }
-            (void)row;
         }
     }
     tc_fence_before();
@@ -363,14 +396,16 @@ int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, 
 
 }  // namespace
 
+// Weight layout: Cin >= 32: [K][Cout][Cin]; Cin < 32 (4 or 16): packed [ceil(K / (32/Cin))][Cout][32] with column
+// (offset-in-pack * Cin + cin) and zero columns for offsets >= K (b2second/tc.py: pack_sparse_weights).
 extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in, int cin, const float *w_hi,
                                   const float *w_lo, const int *nbr, int K, const int *num_out_dev, int cap_out,
                                   const float *scale, const float *shift, int relu, float *out_hi, float *out_lo,
                                   int cout, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B2S_REQUIRE((cin == 32 || cin == 64) && (cout == 32 || cout == 64),
-                "b2s_sparse_conv_tc: built for Cin, Cout in {32, 64} (thin layers use b2s_sparse_conv)");
+    B2S_REQUIRE((cin == 4 || cin == 16 || cin == 32 || cin == 64) && (cout == 16 || cout == 32 || cout == 64),
+                "b2s_sparse_conv_tc: built for Cin in {4, 16, 32, 64}, Cout in {16, 32, 64} (others: b2s_sparse_conv)");
     B2S_REQUIRE(K >= 1 && K <= 27 && cap_out >= 0 && rows_in >= 0, "b2s_sparse_conv_tc: K must be 1..27");
     if (cap_out == 0) return 0;
     static int num_sms = 0;
@@ -379,24 +414,29 @@ extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, in
         B2S_CUDA_OK(cudaGetDevice(&dev));
         B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // weights [K][Cout][Cin] (K-major B operand), hi and lo planes
     CUtensorMap m_hi, m_lo;
-    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)K};
-    cuuint64_t str[2] = {(cuuint64_t)cin * 4, (cuuint64_t)cout * cin * 4};
-    cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
-    if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
+    {
+        const bool packed = cin < 32;
+        const int pack = packed ? 32 / cin : 1;
+        cuuint64_t row = packed ? 32 : (cuuint64_t)cin;          // floats per weight row
+        cuuint64_t nkb = packed ? (cuuint64_t)((K + pack - 1) / pack) : (cuuint64_t)K;
+        cuuint64_t dims[3] = {row, (cuuint64_t)cout, nkb};
+        cuuint64_t str[2] = {row * 4, (cuuint64_t)cout * row * 4};
+        cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
+        if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
+    }
     SpParams p;
     p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
     {
-        static int zs = -1;
-        // bit 0: zero-slot skip (default on); diagnostics with wrong results: 2 no gather copies, 4 no weight
-        // loads, 8 no neighbour-table staging
-        if (zs < 0) { const char *e = getenv("B2S_SP_ZSKIP"); zs = e ? atoi(e) : 1; }
-        p.zskip = zs;
+        static int fl = -1;
+        if (fl < 0) { const char *e = getenv("B2S_SP_ZSKIP"); fl = e ? atoi(e) : 1; }
+        p.flags = fl;
     }
     p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
-    if (cin == 64 && cout == 64) return launch<64, 64, 4>(m_hi, m_lo, p, num_sms, stream);
-    if (cin == 32 && cout == 64) return launch<32, 64, 4>(m_hi, m_lo, p, num_sms, stream);
-    if (cin == 32 && cout == 32) return launch<32, 32, 4>(m_hi, m_lo, p, num_sms, stream);
-    return launch<64, 32, 4>(m_hi, m_lo, p, num_sms, stream);
+#define B2S_TC_CASE(CI, CO) if (cin == CI && cout == CO) return launch<CI, CO, 4>(m_hi, m_lo, p, num_sms, stream);
+    B2S_TC_CASE(64, 64) B2S_TC_CASE(32, 64) B2S_TC_CASE(32, 32) B2S_TC_CASE(64, 32) B2S_TC_CASE(16, 16)
+    B2S_TC_CASE(16, 32) B2S_TC_CASE(4, 16) B2S_TC_CASE(16, 64) B2S_TC_CASE(4, 32)
+#undef B2S_TC_CASE
+    b2s_set_error("b2s_sparse_conv_tc: Cin=%d Cout=%d not built", cin, cout);
+    return -2;
 }

@@ -19,7 +19,7 @@ def random_sparse(rng, shape, batch, n, cin):
 
 
 @pytest.mark.timeout(180)
-@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 64), (64, 64), (64, 32)])
+@pytest.mark.parametrize("cin,cout", [(32, 32), (32, 64), (64, 64), (64, 32), (4, 16), (16, 16), (16, 32)])
 @pytest.mark.parametrize("subm", [True, False])
 @pytest.mark.parametrize("n", [5000, 100, 0])
 def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
@@ -46,7 +46,7 @@ def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
     if rb.num_out == 0:
         return
     w = oc.weight.detach().view(27, cin, cout).cuda()
-    w_hi, w_lo = tc.split_tf32(w.transpose(1, 2).contiguous())
+    w_hi, w_lo = tc.split_tf32(tc.pack_sparse_weights(w))   # [K,Cout,Cin], or packed K blocks for Cin < 32
     f_hi, f_lo = tc.split_tf32(feats.cuda())
     o_hi = torch.zeros(rb.num_out, cout, device="cuda")
     o_lo = torch.zeros_like(o_hi)
