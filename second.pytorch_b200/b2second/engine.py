@@ -19,6 +19,7 @@ Output per batch: ``det [B, post_max, code+2]`` (box, score, label) + ``det_coun
 record the multi-GPU path all-gathers.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -168,7 +169,8 @@ class InferenceEngine:
             lyr["out"] = torch.zeros(lyr["out_level"].cap, m.out_channels, dtype=torch.float32, device=self.dev)
             # tensor-pipe core (csrc/sparse_conv_tc.cu); thin layers (Cin 4/16) pack 8/2 kernel offsets per K block.
             # Other widths (e.g. 3 input features) stay on the fp32 FMA core.
-            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in (4, 16, 32, 64)
+            thin_ok = os.environ.get("B2S_THIN_TC", "1") != "0"      # A/B switch: thin layers on the FMA core
+            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in ((4, 16, 32, 64) if thin_ok else (32, 64))
                          and m.out_channels in (16, 32, 64) and K <= 27)
             self.layers.append(lyr)
             i += 1 + (1 if bn is not None else 0) + (1 if relu else 0)

@@ -149,7 +149,7 @@ __global__ void k_scan_sums(int *block_sums, int nblk, int *num_out_dev, int cap
 // warp per 32 bitmap words; the bits of each non-empty word are expanded by the 32 lanes in parallel
 __global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nwords,
                             const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
-                            ConvGeom g, int cap_out, int *coors_out)
+                            ConvGeom g, int cap_out, int *coors_out, int *nbr_fill)
 {
     const int lane = threadIdx.x & 31;
     const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -165,6 +165,12 @@ __global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nword
             nonempty &= nonempty - 1;
             unsigned wbits = __shfl_sync(0xffffffffu, bits, src);
             int row0 = __shfl_sync(0xffffffffu, my_row0, src);
+            if (nbr_fill) {
+                // the rows of one bitmap word are consecutive: pre-fill their neighbour-table entries with -1
+                // (coalesced) for k_conv_scatter_nbr, instead of a capacity-sized memset
+                const int cnt = min(__popc(wbits), max(cap_out - row0, 0));
+                for (int i = lane; i < cnt * g.K; i += 32) nbr_fill[(size_t)row0 * g.K + i] = -1;
+            }
             if (wbits & (1u << lane)) {
                 int row = row0 + __popc(wbits & ((1u << lane) - 1u));
                 if (row < cap_out) {
@@ -210,6 +216,49 @@ __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restr
             r = b2s_hash_find(keys_in, vals_in, mask_in,
                               b2s_flat_key(c.x, ic[0], ic[1], ic[2], g.in_shape[0], g.in_shape[1], g.in_shape[2]));
         nbr[gid] = r;
+    }
+}
+
+// The same table built from the INPUT side: every input row visits the (<= ceil(k/s)^3) output cells it feeds,
+// ranks each cell in the occupancy bitmap (block prefix + word prefix + popcount of the lower bits = its output
+// row, exactly what k_conv_emit assigns) and writes nbr[row_out][k] = row_in.  Work is proportional to the
+// (input, output) pairs instead of rows_out * K hash probes of which ~70 % miss (k_conv_nbr: 36 us vs the
+// level's 14 us mark pass, ncu launch list round 1); nbr is pre-filled with -1 by the caller.
+__global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *__restrict__ n_in_dev, int cap_in,
+                                   ConvGeom g, const unsigned *__restrict__ bitmap,
+                                   const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
+                                   int cap_out, int *nbr)
+{
+    const int n = min(*n_in_dev, cap_in);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+        int4 c = *reinterpret_cast<const int4 *>(coors_in + (size_t)row * 4);
+        const int ic[3] = {c.y, c.z, c.w};
+        int oc[3][4], okk[3][4], cnt[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            cnt[j] = 0;
+            for (int kk = 0; kk < g.k[j]; ++kk) {
+                int num = ic[j] + g.p[j] - kk * g.d[j];
+                if (num < 0 || num % g.s[j] != 0) continue;
+                int o = num / g.s[j];
+                if (o >= g.out_shape[j] || cnt[j] >= 4) continue;
+                oc[j][cnt[j]] = o;
+                okk[j][cnt[j]] = kk;
+                ++cnt[j];
+            }
+        }
+        for (int a = 0; a < cnt[0]; ++a)
+            for (int b = 0; b < cnt[1]; ++b)
+                for (int e = 0; e < cnt[2]; ++e) {
+                    const unsigned long long key = b2s_flat_key(c.x, oc[0][a], oc[1][b], oc[2][e], g.out_shape[0],
+                                                                g.out_shape[1], g.out_shape[2]);
+                    const long long w = (long long)(key >> 5);
+                    const unsigned bit = (unsigned)(key & 31);
+                    const int row_out = block_prefix[w / kScanThreads] + word_prefix[w] +
+                                        __popc(bitmap[w] & ((1u << bit) - 1u));
+                    const int k = (okk[0][a] * g.k[1] + okk[1][b]) * g.k[2] + okk[2][e];
+                    if (row_out < cap_out) nbr[(size_t)row_out * g.K + k] = row;
+                }
     }
 }
 
@@ -346,16 +395,23 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
     B2S_LAUNCH_OK();
     k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblk, num_out_dev, cap_out, status_dev);
     B2S_LAUNCH_OK();
+    static int use_scatter = -1;   // B2S_RB_SCATTER=0: neighbour table by hash probes from the output side (k_conv_nbr)
+    if (use_scatter < 0) { const char *e = getenv("B2S_RB_SCATTER"); use_scatter = (e && e[0] == '0') ? 0 : 1; }
     k_conv_emit<<<bounded_grid(w.nwords, kThreads), kThreads, 0, stream>>>(
-        w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out, coors_out);
+        w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out, coors_out, use_scatter ? nbr : nullptr);
     B2S_LAUNCH_OK();
     if (cap_out > 0) {
         k_hash_build<<<bounded_grid(cap_out, kThreads), kThreads, 0, stream>>>(
             coors_out, num_out_dev, cap_out, g.out_shape[0], g.out_shape[1], g.out_shape[2], hash_keys_out,
             hash_vals_out, hash_cap_out - 1, status_dev);
         B2S_LAUNCH_OK();
-        k_conv_nbr<<<bounded_grid((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
-            coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
+        if (use_scatter && cap_in > 0) {
+            k_conv_scatter_nbr<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(
+                coors_in, num_in_dev, cap_in, g, w.bitmap, w.word_prefix, w.block_sums, cap_out, nbr);
+        } else {
+            k_conv_nbr<<<bounded_grid((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
+                coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
+        }
         B2S_LAUNCH_OK();
     }
     return 0;

@@ -259,8 +259,22 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 const int row0 = tile * BLOCK_M;
                 const int valid_n = min(BLOCK_M, n_out - row0) * K;
                 const int *src = p.nbr + (size_t)row0 * K;
-                if (!(p.flags & 8))                    // (diagnostic bit 8: skip the table staging)
-                    for (int i = gw * 32 + lane; i < BLOCK_M * K; i += 32 * GW) s_nbr[i] = i < valid_n ? __ldg(&src[i]) : -1;
+                if (!(p.flags & 8)) {                  // (diagnostic bit 8: skip the table staging)
+                    // fixed trip count (K <= 27) so the loads are all in flight together instead of one L2 round
+                    // trip per iteration
+                    constexpr int NLD = (BLOCK_M * 27 + 32 * GW - 1) / (32 * GW);
+                    int v[NLD];
+#pragma unroll
+                    for (int j = 0; j < NLD; ++j) {
+                        const int i = gw * 32 + lane + j * 32 * GW;
+                        v[j] = i < valid_n ? __ldg(&src[i]) : -1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NLD; ++j) {
+                        const int i = gw * 32 + lane + j * 32 * GW;
+                        if (i < BLOCK_M * K) s_nbr[i] = v[j];
+                    }
+                }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
             if constexpr (!PACKED) {
