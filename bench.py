@@ -316,7 +316,8 @@ def run_gpu_arm(args):
         ach = flops / (launch_ms * 1e-3) / 1e12
         traffic = None
         try:   # dram read+write bytes per launch from the committed ncu --set full capture of this kernel
-            traffic = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))["k_conv3x3_tc2"]["dram_bytes_per_launch"]
+            tj = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))
+            traffic = tj["k_conv3x3_tc2"]["dram_bytes_per_launch"] * B / tj["frames_in_capture"]
         except Exception:
             pass
         roofline = {"kernel": "k_conv3x3_tc2 (per launch; %d launches per step, %d frames)" % (n_l, B),
