@@ -51,7 +51,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=32,
                     help="frames per GPU per step (serving batch; measured clouds/s at 8/16/32/64: 1950/2320/2460/2516)")
     ap.add_argument("--points", type=int, default=29000, help="points per synthetic cloud (29k -> ~17k voxels)")
-    ap.add_argument("--cpu-frames", type=int, default=2, help="frames in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=24,
+                    help="frames in the bounded CPU-baseline sample (~0.4 s each on 16 host threads -> ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sparse", default="tc", choices=["tc", "fma"],
                     help="sparse-conv inner product: tc = tcgen05 3xTF32 (wide layers), fma = fp32 FMA tiles")
