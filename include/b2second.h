@@ -128,8 +128,11 @@ int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const in
                     const int *num_out_dev, int cap_out, const float *scale, const float *shift,
                     int relu, float *feat_out, int cout, void *stream);
 
-/* same contraction on the tensor pipe (tcgen05, 3xTF32 hi/lo split, fp32-grade): Cin, Cout in {32, 64}.
+/* same contraction on the tensor pipe (tcgen05, 3xTF32 hi/lo split, fp32-grade): Cin in {4,16,32,64}, Cout in
+ * {16,32,64}, K <= 27.
  *   feat_hi/lo [rows_in, Cin] hi/lo planes; w_hi/lo [K, Cout, Cin] (the reference weight [K,Cin,Cout] transposed);
+ *   for Cin < 32 the 32/Cin consecutive kernel offsets that share one 128-byte K block are packed side by side:
+ *   w_hi/lo [ceil(K/(32/Cin)), Cout, 32], column = offset_in_pack*Cin + cin, zero columns past K;
  *   out_hi/out_lo [cap_out, Cout] (out_lo NULL -> out_hi holds the full fp32 value). */
 int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in /*row capacity of the feature planes
                        (the TMA gather's tensor extent; rows >= rows_in read as zeros)*/,
