@@ -48,6 +48,7 @@ struct Conv2Params {
     int B, H, W, Cin, Cout, relu;
     int tiles_h, tiles_w, num_tiles;
     int out_stride;
+    int dephase;                     // B2S_CONV2_DEPHASE: start delay step in cycles (CTA i waits (i & 3) steps)
     int dbg;                         // B2S_CONV2_DBG diagnostics (results wrong): 1 no activation loads, 2 no weight
                                      // loads, 4 no TMEM drain, 8 no global stores
     const float *scale, *shift;
@@ -91,6 +92,13 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         if (lane == 0) {
             int xs = 0;
             uint32_t xph = 0;
+            if (p.dephase > 0) {
+                // All CTAs run equal-length tiles in lock step, so their end-of-tile store bursts (256 KB per SM) hit
+                // L2 together; starting CTA i (i mod 4) quarter-tiles late spreads them out.  B2S_CONV2_DEPHASE
+                // = cycles per step (0 = off).
+                const long long t0 = clock64(), d = (long long)(blockIdx.x & 3) * p.dephase;
+                while (clock64() - t0 < d) { }
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
                 const int h0 = th * T2_H, w0 = tw * T2_W;
@@ -267,8 +275,13 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     const float hi = to_tf32_rn(x);
                     const float lo = to_tf32_rn(x - hi);
                     if (c_ok && wbase + cw < p.W && !(p.dbg & 8)) {
-                        oh[(size_t)cw * p.out_stride] = hi;
-                        ol[(size_t)cw * p.out_stride] = lo;
+                        if (p.dbg & 16) {            // experiment: streaming (evict-first) stores
+                            __stcs(&oh[(size_t)cw * p.out_stride], hi);
+                            __stcs(&ol[(size_t)cw * p.out_stride], lo);
+                        } else {
+                            oh[(size_t)cw * p.out_stride] = hi;
+                            ol[(size_t)cw * p.out_stride] = lo;
+                        }
                     }
                 }
             }
@@ -310,9 +323,11 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.out_stride = out_stride;
     {
-        static int dbg = -1;
+        static int dbg = -1, deph = -1;
         if (dbg < 0) { const char *e = getenv("B2S_CONV2_DBG"); dbg = e ? atoi(e) : 0; }
+        if (deph < 0) { const char *e = getenv("B2S_CONV2_DEPHASE"); deph = e ? atoi(e) : 0; }
         p.dbg = dbg;
+        p.dephase = deph;
     }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
     const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;
