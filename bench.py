@@ -303,7 +303,7 @@ def run_gpu_arm(args):
                    "algorithmic_flops_per_step": conv_flops, "ms_per_step": conv_ms,
                    "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0}
     sparse_roof["frac"] = sparse_roof["achieved"] / hbm_peak
-    rstats = [s for s in eng.rpn_layer_stats() if s["taps"] == 9]
+    rstats = [s for s in eng.rpn_layer_stats() if s["v2"]]       # the launches k_conv3x3_tc2 takes
     rpn_ms = stages.get("rpn", 0.0)            # the 3x3 stack only (the 1x1 tail is stage "rpn_1x1")
     if rstats and rpn_ms >= 0.5 * conv_ms:
         # dominant kernel = k_conv3x3_tc2 (dense RPN 3x3 layers, implicit GEMM on tcgen05, 3xTF32 split for

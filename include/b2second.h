@@ -170,6 +170,19 @@ int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int batch, int H, int 
                   const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
                   int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream);
 
+/* general form, for the multi-stage RPNs (rpn.py:469-497: stride-2 first conv of a block after ZeroPad2d(1);
+ * :264-299 deblocks: ConvTranspose2d(k = s, stride s) for upsample_stride >= 1, Conv2d(k = s, stride s) below 1;
+ * torch.cat of the deblock outputs = channel offsets into one map):
+ *   in_hi/in_lo [B, Hin+2, Win+2, Cin] halo-padded.  GEMM pixel (h, w) of the Hg x Wg grid reads input pixels
+ *   (h*stride + dy - pad, w*stride + dx - pad), dy < kh, dx < kw (kh*kw <= 16, stride <= 4, pad 0 or 1), weights
+ *   [kh*kw, n_pad, Cin], and is written to pixel (h*out_mul + off_h, w*out_mul + off_w) of an Hout x Wout map with
+ *   out_stride channels per pixel (pass out pointers already advanced to the first output channel).
+ *   ConvTranspose2d k = s: s*s calls with kh = kw = 1, Hg = Hin, out_mul = s, (off_h, off_w) = (a, c), W[:, :, a, c]. */
+int b2s_conv2d_tc_ex(const float *in_hi, const float *in_lo, int batch, int Hin, int Win, int Cin, const float *w_hi,
+                     const float *w_lo, int kh, int kw, int stride, int pad, int Cout, int n_pad, const float *scale,
+                     const float *shift, int relu, int Hg, int Wg, float *out_hi, float *out_lo, int Hout, int Wout,
+                     int out_padded, int out_stride, int out_mul, int off_h, int off_w, void *stream);
+
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,
             const int *coors, const int *num_rows_dev, int cap_rows, int max_points,

@@ -235,20 +235,24 @@ class InferenceEngine:
         dev, B = self.dev, self.B
         D, H, W = self.final_level.shape
         C = self.feat_final_c * D
-        self.tc_plan = _tc.plan_rpn(self.net.rpn)
-        assert self.tc_plan[0]["cin"] == C, "BEV channels %d != RPN input %d" % (C, self.tc_plan[0]["cin"])
+        plan = _tc.plan_rpn(self.net.rpn, H, W)
+        self.tc_prog = plan
+        self.tc_plan = plan["ops"]
+        assert plan["in_channels"] == C, "BEV channels %d != RPN input %d" % (C, plan["in_channels"])
 
-        def plane(c):
-            return (torch.zeros(B, H + 2, W + 2, c, dtype=torch.float32, device=dev),
-                    torch.zeros(B, H + 2, W + 2, c, dtype=torch.float32, device=dev))
-        self.tc_bev = plane(C)
-        cmax = max(l["cout"] for l in self.tc_plan[:-1])
-        self.tc_ping, self.tc_pong = plane(cmax), plane(cmax)
-        for l in self.tc_plan[:-1]:
-            assert l["cout"] == cmax, "engine: uniform channel width expected in the tensor-core RPN"
-        self.tc_head_stride = 32
-        assert self.tc_plan[-1]["cout"] <= 32
-        self.tc_heads = torch.zeros(B, H, W, self.tc_head_stride, dtype=torch.float32, device=dev)
+        def plane(h, w, c):
+            return (torch.zeros(B, h + 2, w + 2, c, dtype=torch.float32, device=dev),
+                    torch.zeros(B, h + 2, w + 2, c, dtype=torch.float32, device=dev))
+        self.tc_bev = plane(H, W, C)
+        self.tc_bufs = {"in": self.tc_bev}
+        for name, (h, w, c) in plan["buffers"].items():
+            self.tc_bufs[name] = plane(h, w, c)
+        hd = plan["heads"]
+        self.tc_head_stride = hd["stride"]
+        _, fH, fW = self.cfg.feature_map_size
+        assert (hd["H"], hd["W"]) == (fH, fW), "RPN output %dx%d != anchor grid %dx%d" % (hd["H"], hd["W"], fH, fW)
+        self.tc_heads = torch.zeros(B, hd["H"], hd["W"], self.tc_head_stride, dtype=torch.float32, device=dev)
+        self.tc_bufs["heads"] = (self.tc_heads, None)
         self.tc_hw = (H, W)
 
     def _alloc_detect_buffers(self, cand_cap):
@@ -379,34 +383,33 @@ class InferenceEngine:
         L.check(lib.b2s_to_bev_tc(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
                                   D, H, W, L.ptr(self.tc_bev[0]), L.ptr(self.tc_bev[1]), st), "b2s_to_bev_tc")
         self._mark("rpn")
-        src = self.tc_bev
-        bufs = [self.tc_ping, self.tc_pong]
-        marked_1x1 = False
-        for i, lyr in enumerate(self.tc_plan[:-1]):
-            if lyr["taps"] == 1 and not marked_1x1:
-                self._mark("rpn_1x1")          # the 3x3 stack (k_conv3x3_tc2) is timed apart from the 1x1 tail
-                marked_1x1 = True
-            dst = bufs[i % 2]
-            L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, lyr["cin"], L.ptr(lyr["w_hi"]),
-                                      L.ptr(lyr["w_lo"]), lyr["taps"], lyr["cout"], lyr["n_pad"], L.ptr(lyr["scale"]),
-                                      L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(dst[0]), L.ptr(dst[1]), 1,
-                                      lyr["cout"], st), "b2s_conv2d_tc")
-            src = dst
-        if not marked_1x1:
+        marked_tail = False
+        for op in self.tc_plan:
+            if not op["v2"] and op["kind"] != "block" and not marked_tail:
+                self._mark("rpn_1x1")          # the 3x3 stack (k_conv3x3_tc2) is timed apart from the deblock/heads tail
+                marked_tail = True
+            src, dst = self.tc_bufs[op["src"]], self.tc_bufs[op["dst"]]
+            cdst = dst[0].shape[-1]                                   # channels per pixel of the destination map
+            o_hi = ctypes_ptr(dst[0].data_ptr() + 4 * op["dst_coff"])
+            o_lo = ctypes_ptr(dst[1].data_ptr() + 4 * op["dst_coff"]) if op["planes"] == 2 else None
+            L.check(lib.b2s_conv2d_tc_ex(
+                L.ptr(src[0]), L.ptr(src[1]), self.B, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]),
+                L.ptr(op["w_lo"]), op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
+                L.ptr(op["scale"]) if op["scale"] is not None else None,
+                L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"],
+                o_hi, o_lo, op["Hout"], op["Wout"], 1 if op["padded"] else 0, cdst, op["out_mul"], op["off_h"],
+                op["off_w"], st), "b2s_conv2d_tc_ex(%s)" % op["kind"])
+        if not marked_tail:
             self._mark("rpn_1x1")
-        hd = self.tc_plan[-1]
         S = self.tc_head_stride
-        L.check(lib.b2s_conv2d_tc(L.ptr(src[0]), L.ptr(src[1]), self.B, H, W, hd["cin"], L.ptr(hd["w_hi"]),
-                                  L.ptr(hd["w_lo"]), 1, hd["cout"], hd["n_pad"], None, L.ptr(hd["shift"]), 0,
-                                  L.ptr(self.tc_heads), None, 0, S, st), "b2s_conv2d_tc(heads)")
         self._mark("decode_filter")
-        offs = hd["head_offsets"]
+        offs = self.tc_prog["heads"]["offsets"]
         heads = self.tc_heads
         esz = heads.element_size()
         box_p = ctypes_ptr(heads.data_ptr() + offs[0] * esz)
         cls_p = ctypes_ptr(heads.data_ptr() + offs[1] * esz)
         dir_p = ctypes_ptr(heads.data_ptr() + offs[2] * esz) if cfg.use_direction_classifier else None
-        bs = H * W * S
+        bs = self.fH * self.fW * S
         L.check(lib.b2s_decode_filter_strided(
             box_p, cls_p, dir_p, bs, bs, bs, 1, S, L.ptr(self.anchors), None, self.B, self.a_loc, self.fH, self.fW,
             self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
@@ -486,16 +489,14 @@ class InferenceEngine:
         the tensor pipe) and algorithmic bytes (hi/lo planes in and out + weights)."""
         if self.rpn_impl != "tc":
             return []
-        _, H, W = self.final_level.shape
-        px = self.B * H * W
         out = []
-        for i, lyr in enumerate(self.tc_plan):
-            last = i == len(self.tc_plan) - 1
-            cin, cout, taps = lyr["cin"], lyr["cout"], lyr["taps"]
-            planes_out = 1 if last else 2
-            out.append({"index": i, "cin": cin, "cout": cout, "taps": taps, "pixels": px,
-                        "flops": 2 * px * taps * cin * cout,
-                        "bytes": 4 * (2 * px * cin + planes_out * px * cout + 2 * taps * cin * lyr["n_pad"])})
+        for i, op in enumerate(self.tc_plan):
+            cin, cout, taps = op["cin"], op["cout"], op["taps"]
+            px = self.B * op["Hg"] * op["Wg"]
+            px_in = self.B * op["Hin"] * op["Win"]
+            out.append({"index": i, "kind": op["kind"], "v2": op["v2"], "cin": cin, "cout": cout, "taps": taps,
+                        "pixels": px, "flops": 2 * px * taps * cin * cout,
+                        "bytes": 4 * (2 * px_in * cin + op["planes"] * px * cout + 2 * taps * cin * op["n_pad"])})
         return out
 
     # ---------------------------------------------------------------- public API

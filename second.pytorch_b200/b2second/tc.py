@@ -68,67 +68,119 @@ def _n_pad(cout):
 
 
 def supported(rpn):
-    """True when every layer of this RPNV2 maps onto b2s_conv2d_tc (stride-1 3x3 / 1x1, channels % 32 == 0)."""
+    """True when every layer of this RPNV2 maps onto b2s_conv2d_tc_ex (channels % 32 == 0, kernels <= 4x4)."""
     try:
-        plan_rpn(rpn, dry=True)
+        plan_rpn(rpn, 64, 64, dry=True)
         return True
     except (ValueError, AssertionError):
         return False
 
 
-def plan_rpn(rpn, dry=False):
-    """-> list of layer dicts {taps, cin, cout, n_pad, w_hi, w_lo, scale, shift, relu, kind}."""
-    if len(rpn.blocks) != 1 or len(rpn.deblocks) != 1:
-        raise ValueError("multi-stage RPN (strided blocks / upsampling deblocks) stays on cuDNN this round")
-    layers = []
+def _conv_out(n, k, s, pad):
+    return (n + 2 * pad - k) // s + 1
 
-    def add(w_tco_ci, scale, shift, relu, kind, taps):
-        taps_, cout, cin = w_tco_ci.shape
-        assert taps_ == taps and cin % 32 == 0, "channels must be multiples of 32"
-        n_pad = _n_pad(cout)
-        d = {"taps": taps, "cin": cin, "cout": cout, "n_pad": n_pad, "relu": relu, "kind": kind,
-             "scale": scale, "shift": shift}
-        if not dry:
-            d["w_hi"], d["w_lo"] = split_tf32(_pad_rows(w_tco_ci.float(), n_pad))
-        layers.append(d)
 
-    mods = list(rpn.blocks[0])
-    i = 0
-    while i < len(mods):
-        m = mods[i]
-        if isinstance(m, nn.ZeroPad2d):
-            assert tuple(m.padding) == (1, 1, 1, 1)
-            conv, bn, relu = mods[i + 1], mods[i + 2], mods[i + 3]
-            assert conv.padding == (0, 0)
-            i += 4
-        else:
-            conv, bn, relu = mods[i], mods[i + 1], mods[i + 2]
-            assert conv.padding == (1, 1)
-            i += 3
-        assert isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.bias is None
-        assert isinstance(bn, nn.BatchNorm2d) and isinstance(relu, nn.ReLU)
-        w = conv.weight.detach()                                   # [Cout, Cin, 3, 3]
-        w = w.permute(2, 3, 0, 1).reshape(9, w.shape[0], w.shape[1])   # [tap=ky*3+kx, Cout, Cin]
-        s, b = _fold_bn2d(bn)
-        add(w, s, b, True, "block", 9)
-    up, bn, relu = list(rpn.deblocks[0])
-    if isinstance(up, nn.ConvTranspose2d):
-        assert up.kernel_size == (1, 1) and up.stride == (1, 1) and up.bias is None
-        w = up.weight.detach()[:, :, 0, 0].t().unsqueeze(0)        # [Cin, Cout,1,1] -> [1, Cout, Cin]
-    else:
-        assert up.kernel_size == (1, 1) and up.stride == (1, 1) and up.bias is None
-        w = up.weight.detach()[:, :, 0, 0].unsqueeze(0)
-    s, b = _fold_bn2d(bn)
-    add(w.contiguous(), s, b, True, "deblock", 1)
-    # heads: box | cls | dir packed into one [1, n, Cin] matrix, bias as shift
+def plan_rpn(rpn, H, W, dry=False):
+    """RPNV2 (second/pytorch/models/rpn.py:469-497 blocks, :264-299 deblocks, :386-420 heads) on an H x W BEV map ->
+    {"buffers": {name: (h, w, c)}, "ops": [conv op dicts in execution order], "heads": {...}}.
+
+    Every op is one b2s_conv2d_tc_ex launch: conv k x k / stride / pad, or one (a, c) sub-grid of a k = s
+    ConvTranspose2d; output channels are cut into slices of <= 128 (the kernel's n_pad) and `torch.cat` of the
+    deblock outputs is a channel offset into the shared "cat" buffer."""
+    bufs, ops = {}, []
+
+    def emit(kind, src, dst, w_t_co_ci, kh, kw, stride, pad, scale, shift, relu, hin, win, hg, wg, hout, wout,
+             out_mul=1, off=(0, 0), dst_coff=0, planes=2, padded=True):
+        taps, cout, cin = w_t_co_ci.shape
+        assert taps == kh * kw and cin % 32 == 0, "channels must be multiples of 32"
+        for c0 in range(0, cout, 128):
+            c1 = min(cout, c0 + 128)
+            n_pad = _n_pad(c1 - c0)
+            d = {"kind": kind, "src": src, "dst": dst, "kh": kh, "kw": kw, "taps": taps, "stride": stride, "pad": pad,
+                 "cin": cin, "cout": c1 - c0, "n_pad": n_pad, "relu": relu, "Hin": hin, "Win": win, "Hg": hg, "Wg": wg,
+                 "Hout": hout, "Wout": wout, "out_mul": out_mul, "off_h": off[0], "off_w": off[1],
+                 "dst_coff": dst_coff + c0, "planes": planes, "padded": padded,
+                 "scale": None if scale is None else scale[c0:c1].contiguous(),
+                 "shift": None if shift is None else shift[c0:c1].contiguous(),
+                 # the weights-stationary N=256 kernel takes this op (conv_tc.cu dispatch)
+                 "v2": (kh == 3 and kw == 3 and stride == 1 and pad == 1 and n_pad == 128 and planes == 2 and padded
+                        and out_mul == 1)}
+            if not dry:
+                d["w_hi"], d["w_lo"] = split_tf32(_pad_rows(w_t_co_ci[:, c0:c1].float(), n_pad))
+            ops.append(d)
+
+    cur, h, w = "in", H, W
+    ups = []                                   # (buffer, channels) of each deblock output, in order
+    up_start = rpn._upsample_start_idx
+    cat_hw = None
+    up_filters = [list(db)[0].out_channels for db in rpn.deblocks]
+    for bi, block in enumerate(rpn.blocks):
+        mods = list(block)
+        i, li = 0, 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.ZeroPad2d):
+                assert tuple(m.padding) == (1, 1, 1, 1)
+                conv, bn, relu = mods[i + 1], mods[i + 2], mods[i + 3]
+                assert conv.padding == (0, 0)
+                i += 4
+            else:
+                conv, bn, relu = mods[i], mods[i + 1], mods[i + 2]
+                assert conv.padding == (1, 1)
+                i += 3
+            assert isinstance(conv, nn.Conv2d) and conv.kernel_size == (3, 3) and conv.bias is None
+            assert conv.stride[0] == conv.stride[1] and conv.stride[0] in (1, 2, 4)
+            assert isinstance(bn, nn.BatchNorm2d) and isinstance(relu, nn.ReLU)
+            st = conv.stride[0]
+            wt = conv.weight.detach()                                   # [Cout, Cin, 3, 3]
+            wt = wt.permute(2, 3, 0, 1).reshape(9, wt.shape[0], wt.shape[1])   # [tap=ky*3+kx, Cout, Cin]
+            sc, sh = _fold_bn2d(bn)
+            ho, wo = _conv_out(h, 3, st, 1), _conv_out(w, 3, st, 1)
+            dst = "b%d%s" % (bi, "ab"[li % 2])
+            bufs[dst] = (ho, wo, wt.shape[1])
+            emit("block", cur, dst, wt, 3, 3, st, 1, sc, sh, True, h, w, ho, wo, ho, wo)
+            cur, h, w = dst, ho, wo
+            li += 1
+        j = bi - up_start
+        if j >= 0:
+            up, bn, relu = list(rpn.deblocks[j])
+            assert up.bias is None and isinstance(bn, nn.BatchNorm2d)
+            sc, sh = _fold_bn2d(bn)
+            coff = sum(up_filters[:j])
+            k = up.kernel_size[0]
+            assert up.kernel_size == (k, k) and up.stride == (k, k) and k in (1, 2, 4)
+            if isinstance(up, nn.ConvTranspose2d):
+                hu, wu = h * k, w * k
+                if cat_hw is None:
+                    cat_hw = (hu, wu)
+                assert cat_hw == (hu, wu), "deblock outputs must share one resolution"
+                wt = up.weight.detach()                                  # [Cin, Cout, k, k]
+                for a in range(k):
+                    for c in range(k):
+                        emit("deblock", cur, "cat", wt[:, :, a, c].t().unsqueeze(0).contiguous(), 1, 1, 1, 0, sc, sh, True,
+                             h, w, h, w, hu, wu, out_mul=k, off=(a, c), dst_coff=coff)
+            else:                                                        # Conv2d(k, stride k): upsample_stride < 1
+                hu, wu = _conv_out(h, k, k, 0), _conv_out(w, k, k, 0)
+                if cat_hw is None:
+                    cat_hw = (hu, wu)
+                assert cat_hw == (hu, wu), "deblock outputs must share one resolution"
+                wt = up.weight.detach()                                  # [Cout, Cin, k, k]
+                wt = wt.permute(2, 3, 0, 1).reshape(k * k, wt.shape[0], wt.shape[1])
+                emit("deblock", cur, "cat", wt, k, k, k, 0, sc, sh, True, h, w, hu, wu, hu, wu, dst_coff=coff)
+            ups.append(up_filters[j])
+    if ups:
+        bufs["cat"] = (cat_hw[0], cat_hw[1], sum(ups))
+        cur, h, w = "cat", cat_hw[0], cat_hw[1]
+    # heads: box | cls | dir packed into one record per pixel, bias as shift
     heads = [rpn.conv_box, rpn.conv_cls] + ([rpn.conv_dir_cls] if rpn._use_direction_classifier else [])
-    w = torch.cat([h.weight.detach()[:, :, 0, 0] for h in heads], 0).unsqueeze(0)     # [1, sum Cout, Cin]
-    bias = torch.cat([h.bias.detach() for h in heads], 0).float().contiguous()
-    pad = (-w.shape[1]) % 4
+    wt = torch.cat([hd.weight.detach()[:, :, 0, 0] for hd in heads], 0).unsqueeze(0)     # [1, sum Cout, Cin]
+    bias = torch.cat([hd.bias.detach() for hd in heads], 0).float().contiguous()
+    pad = (-wt.shape[1]) % 4
     if pad:
-        w = torch.cat([w, torch.zeros(1, pad, w.shape[2], device=w.device, dtype=w.dtype)], 1)
+        wt = torch.cat([wt, torch.zeros(1, pad, wt.shape[2], device=wt.device, dtype=wt.dtype)], 1)
         bias = torch.cat([bias, torch.zeros(pad, device=bias.device)])
-    add(w.contiguous(), None, bias, False, "heads", 1)
-    offs = np.cumsum([0] + [h.weight.shape[0] for h in heads]).tolist()
-    layers[-1]["head_offsets"] = offs                       # box at offs[0], cls at offs[1], dir at offs[2]
-    return layers
+    stride_s = max(32, wt.shape[1])
+    emit("heads", cur, "heads", wt.contiguous(), 1, 1, 1, 0, None, bias, False, h, w, h, w, h, w, planes=1, padded=False)
+    offs = np.cumsum([0] + [hd.weight.shape[0] for hd in heads]).tolist()
+    return {"buffers": bufs, "ops": ops, "in_channels": ops[0]["cin"],
+            "heads": {"offsets": offs, "stride": stride_s, "H": h, "W": w}}

@@ -34,14 +34,20 @@ constexpr int TILE_H = 8, TILE_W = 16;   // BLOCK_M = 128 output pixels = 8 rows
 constexpr int kThreads = 256;
 
 struct ConvParams {
-    int B, H, W, Cin, Cout, taps, relu;
+    int B, H, W;             // the GEMM pixel grid: conv output pixels (for a k=s deconv sub-grid: the input pixels)
+    int Cin, Cout, taps, relu;
+    int kw;                  // filter width (tap = dy*kw + dx)
+    int stride;              // input pixel step per GEMM pixel (TMA element stride)
+    int in_off;              // 1 - padding: halo-padded input coordinate of GEMM pixel 0, tap 0
     int tiles_h, tiles_w, num_tiles;
-    int out_padded;          // 1: out is [B,H+2,W+2,Cout] (interior written), 0: [B,H,W,Cout]
+    int Hout, Wout;          // output map size; GEMM pixel (h,w) is written to (h*out_mul+off_h, w*out_mul+off_w)
+    int out_mul, off_h, off_w;
+    int out_padded;          // 1: out is [B,Hout+2,Wout+2,*] (interior written), 0: [B,Hout,Wout,*]
     int out_stride;          // channels per output pixel row (>= Cout; lets heads write a packed record)
     const float *scale, *shift;
     float *out_hi, *out_lo;
     int dbg;                 // B2S_CONV_DBG diagnostics (results wrong!): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no drain
-    int chain;               // filter taps per TMEM accumulation chain (1 = per-tap drain; B2S_CONV_CHAIN experiment)
+    int chain;               // K blocks (tap x 32-channel chunk) per TMEM accumulation chain: 4 = 48 MMAs (B2S_CONV_CHAIN)
 };
 
 template <int N, int STAGES>
@@ -102,24 +108,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                 int tw = tile % p.tiles_w;
                 int th = (tile / p.tiles_w) % p.tiles_h;
                 int b = tile / (p.tiles_w * p.tiles_h);
-                int h0 = th * TILE_H, w0 = tw * TILE_W;
-                // optional L2 prefetch of the activations the NEXT tile of this CTA will need. Measured on B200:
-                // 0.427 ms/layer with it, 0.417 ms without -- the kernel is shared-memory-port bound, not
-                // load-latency bound -- so it is OFF unless B2S_CONV_DBG has bit 8 set.
-                if (p.dbg & 8) {
-                    int nt = tile + gridDim.x;
-                    if (nt < p.num_tiles) {
-                        int ntw = nt % p.tiles_w, nth = (nt / p.tiles_w) % p.tiles_h, nb = nt / (p.tiles_w * p.tiles_h);
-                        for (int chunk = 0; chunk < kchunks; ++chunk)
-                            for (int dy = (p.taps == 9 ? 0 : 1); dy <= (p.taps == 9 ? 2 : 1); dy += 2) {
-                                tma_prefetch_4d(&map_a_hi, chunk * BLOCK_K, ntw * TILE_W + 1, nth * TILE_H + dy, nb);
-                                tma_prefetch_4d(&map_a_lo, chunk * BLOCK_K, ntw * TILE_W + 1, nth * TILE_H + dy, nb);
-                            }
-                    }
-                }
+                // halo-padded input coordinate of the tile's first GEMM pixel; the tensor map's element stride
+                // (= p.stride) makes the 16 x 8 box step over the input pixels of a strided conv
+                const int h0 = th * TILE_H * p.stride + p.in_off, w0 = tw * TILE_W * p.stride + p.in_off;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     int tap = kb / kchunks, chunk = kb - tap * kchunks;
-                    int dy = (p.taps == 9) ? tap / 3 : 1, dx = (p.taps == 9) ? tap % 3 : 1;
+                    const int dy = tap / p.kw, dx = tap - dy * p.kw;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
                     uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
                     if (p.dbg & 1) {
@@ -151,11 +145,12 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                for (int tap0 = 0; tap0 < p.taps; tap0 += p.chain) {
+                // accumulation chains of p.chain K blocks (default 4 = 48 MMAs), whatever the tap / channel split
+                for (int kb0 = 0; kb0 < num_kb; kb0 += p.chain) {
                     mbar_wait(&bar_tempty[acc], acc_phase ^ 1);     // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N);
-                    const int kb_chain = (min(p.taps, tap0 + p.chain) - tap0) * kchunks;
+                    const int kb_chain = min(num_kb, kb0 + p.chain) - kb0;
                     for (int chunk = 0; chunk < kb_chain; ++chunk) {
                         mbar_wait(&bar_full[stage], phase);          // TMA bytes have landed
                         tc_fence_after();
@@ -194,19 +189,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             int tw = tile % p.tiles_w;
             int th = (tile / p.tiles_w) % p.tiles_h;
             int b = tile / (p.tiles_w * p.tiles_h);
-            const int m = ew * 32 + lane;                      // accumulator row == pixel inside the tile
-            const int h = th * TILE_H + m / TILE_W, w = tw * TILE_W + m % TILE_W;
-            const bool valid = (h < p.H) && (w < p.W);
-            size_t pix;
-            if (p.out_padded) pix = ((size_t)b * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
-            else pix = ((size_t)b * p.H + h) * p.W + w;
-            float *oh = p.out_hi + pix * p.out_stride;
-            float *ol = p.out_lo ? p.out_lo + pix * p.out_stride : nullptr;
             // drain the per-tap partial sums into fp32 registers (round-to-nearest adds)
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;
-            for (int tap0 = 0; tap0 < p.taps; tap0 += p.chain) {
+            for (int kb0 = 0; kb0 < num_kb; kb0 += p.chain) {
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * N);
@@ -239,8 +226,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                 const int mm = ew * 32 + it * 4 + sp;
                 const int hh = th * TILE_H + mm / TILE_W, ww = tw * TILE_W + mm % TILE_W;
                 gok[it] = (hh < p.H) && (ww < p.W);
-                gpix[it] = p.out_padded ? ((size_t)b * (p.H + 2) + (hh + 1)) * (p.W + 2) + (ww + 1)
-                                        : ((size_t)b * p.H + hh) * p.W + ww;
+                const int oh = hh * p.out_mul + p.off_h, ow = ww * p.out_mul + p.off_w;   // position in the output map
+                gpix[it] = p.out_padded ? ((size_t)b * (p.Hout + 2) + (oh + 1)) * (p.Wout + 2) + (ow + 1)
+                                        : ((size_t)b * p.Hout + oh) * p.Wout + ow;
             }
 #pragma unroll
             const int planes = p.out_lo ? 2 : 1;
@@ -274,7 +262,6 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
                     }
                 }
             }
-            (void)valid; (void)oh; (void)ol;
         }
     }
     tc_fence_before();
@@ -309,38 +296,54 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
                     const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
                     float *out_lo, int out_stride, int num_sms, cudaStream_t stream);
 
-extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
-                             const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
-                             int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream_)
+// General form (include/b2second.h).  Input: halo-padded hi/lo planes [B, Hin+2, Win+2, Cin].  One GEMM pixel (h, w)
+// of the Hg x Wg grid reads input pixels (h*stride + dy - pad, w*stride + dx - pad), dy < kh, dx < kw, and is written
+// to output pixel (h*out_mul + off_h, w*out_mul + off_w) of an Hout x Wout map:
+//   conv  k x k, stride s, pad p : Hg = Hout = conv output size, out_mul 1
+//   ConvTranspose2d k = s        : s*s launches with kh = kw = 1, Hg = Hin, out_mul = s, (off_h, off_w) = (a, c),
+//                                  weights W[:, :, a, c]
+extern "C" int b2s_conv2d_tc_ex(const float *in_hi, const float *in_lo, int B, int Hin, int Win, int Cin,
+                                const float *w_hi, const float *w_lo, int kh, int kw, int stride, int pad, int Cout,
+                                int n_pad, const float *scale, const float *shift, int relu, int Hg, int Wg,
+                                float *out_hi, float *out_lo, int Hout, int Wout, int out_padded, int out_stride,
+                                int out_mul, int off_h, int off_w, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B2S_REQUIRE(taps == 1 || taps == 9, "b2s_conv2d_tc: taps must be 1 or 9");
+    const int taps = kh * kw;
+    B2S_REQUIRE(kh >= 1 && kw >= 1 && taps <= 16 && stride >= 1 && stride <= 4 && (pad == 0 || pad == 1),
+                "b2s_conv2d_tc: kernel up to 4x4 (16 taps), stride 1..4, pad 0 or 1");
     B2S_REQUIRE(Cin % BLOCK_K == 0 && Cin >= BLOCK_K, "b2s_conv2d_tc: Cin must be a multiple of 32");
     B2S_REQUIRE(n_pad >= Cout && Cout % 4 == 0 && out_stride >= Cout && out_stride % 4 == 0,
                 "b2s_conv2d_tc: Cout/out_stride must be multiples of 4, n_pad >= Cout");
-    B2S_REQUIRE(B >= 1 && H >= 1 && W >= 1, "b2s_conv2d_tc: bad sizes");
+    B2S_REQUIRE(B >= 1 && Hin >= 1 && Win >= 1 && Hg >= 1 && Wg >= 1 && out_mul >= 1, "b2s_conv2d_tc: bad sizes");
+    B2S_REQUIRE((Hg - 1) * out_mul + off_h < Hout && (Wg - 1) * out_mul + off_w < Wout && off_h >= 0 && off_w >= 0,
+                "b2s_conv2d_tc: output positions outside the Hout x Wout map");
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
         B2S_CUDA_OK(cudaGetDevice(&dev));
         B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // 3x3, n_pad 128, hi/lo halo-padded output: the weights-stationary N=256 kernel (conv_tc2.cu).
-    // B2S_CONV_V2=0 falls back to k_conv_tc below (kept for 1x1 layers, heads and other widths).
+    // 3x3 stride 1 pad 1, n_pad 128, hi/lo halo-padded output on the same grid: the weights-stationary N=256
+    // kernel (conv_tc2.cu).  B2S_CONV_V2=0 falls back to k_conv_tc below.
     static int use_v2 = -1;
     if (use_v2 < 0) {
         const char *e = getenv("B2S_CONV_V2");
         use_v2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use_v2 && taps == 9 && n_pad == 128 && out_lo != nullptr && out_padded)
-        return b2s_conv3x3_tc2(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
+    if (use_v2 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && n_pad == 128 && out_lo != nullptr && out_padded &&
+        out_mul == 1 && off_h == 0 && off_w == 0 && Hg == Hin && Wg == Win && Hout == Hin && Wout == Win)
+        return b2s_conv3x3_tc2(in_hi, in_lo, B, Hin, Win, Cin, w_hi, w_lo, Cout, scale, shift, relu, out_hi, out_lo,
                                out_stride, num_sms, stream);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     {
-        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)(W + 2) * Cin * 4, (cuuint64_t)(H + 2) * (W + 2) * Cin * 4};
-        cuuint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
-        if (make_map(&a_hi, in_hi, 4, dims, str, box) || make_map(&a_lo, in_lo, 4, dims, str, box)) return -1;
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(Win + 2), (cuuint64_t)(Hin + 2), (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)(Win + 2) * Cin * 4,
+                             (cuuint64_t)(Hin + 2) * (Win + 2) * Cin * 4};
+        // the box TRAVERSES stride*TILE pixels and keeps every stride-th one: TILE_W x TILE_H pixels land in smem
+        cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)(TILE_W * stride), (cuuint32_t)(TILE_H * stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        if (make_map(&a_hi, in_hi, 4, dims, str, box, es) || make_map(&a_lo, in_lo, 4, dims, str, box, es)) return -1;
     }
     {
         // weights [taps][n_pad][Cin] (rows >= Cout are zero)
@@ -350,17 +353,19 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
         if (make_map(&b_hi, w_hi, 3, dims, str, box) || make_map(&b_lo, w_lo, 3, dims, str, box)) return -1;
     }
     ConvParams p;
-    p.B = B; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.relu = relu;
-    p.tiles_h = (H + TILE_H - 1) / TILE_H;
-    p.tiles_w = (W + TILE_W - 1) / TILE_W;
+    p.B = B; p.H = Hg; p.W = Wg; p.Cin = Cin; p.Cout = Cout; p.taps = taps; p.relu = relu;
+    p.kw = kw; p.stride = stride; p.in_off = 1 - pad;
+    p.tiles_h = (Hg + TILE_H - 1) / TILE_H;
+    p.tiles_w = (Wg + TILE_W - 1) / TILE_W;
     p.num_tiles = B * p.tiles_h * p.tiles_w;
+    p.Hout = Hout; p.Wout = Wout; p.out_mul = out_mul; p.off_h = off_h; p.off_w = off_w;
     p.out_padded = out_padded; p.out_stride = out_stride;
     {
         static int dbg = -1;
         if (dbg < 0) { const char *e = getenv("B2S_CONV_DBG"); dbg = e ? atoi(e) : 0; }
         p.dbg = dbg;
         static int chain = -1;
-        if (chain < 0) { const char *e = getenv("B2S_CONV_CHAIN"); chain = e ? atoi(e) : 1; if (chain < 1) chain = 1; }
+        if (chain < 0) { const char *e = getenv("B2S_CONV_CHAIN"); chain = e ? atoi(e) : 4; if (chain < 1) chain = 1; }
         p.chain = chain;
     }
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
@@ -372,4 +377,15 @@ extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int 
     }
     b2s_set_error("b2s_conv2d_tc: n_pad=%d not built (32, 64, 128)", n_pad);
     return -2;
+}
+
+// 3x3 pad 1 (taps = 9) or 1x1 (taps = 1), stride 1, output on the input grid
+extern "C" int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
+                             const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
+                             int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream_)
+{
+    B2S_REQUIRE(taps == 1 || taps == 9, "b2s_conv2d_tc: taps must be 1 or 9");
+    const int k = taps == 9 ? 3 : 1;
+    return b2s_conv2d_tc_ex(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, k, k, 1, taps == 9 ? 1 : 0, Cout, n_pad, scale, shift,
+                            relu, H, W, out_hi, out_lo, H, W, out_padded, out_stride, 1, 0, 0, stream_);
 }

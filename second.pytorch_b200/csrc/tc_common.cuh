@@ -171,12 +171,15 @@ inline PFN_encodeTiled get_encode()
     return fn;
 }
 
+// elem_strides (optional): traversal stride per dimension -- {1, s, s, 1} fetches every s-th pixel (strided conv)
 inline int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims,
-                    const cuuint64_t *strides_bytes, const cuuint32_t *box)
+                    const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *elem_strides = nullptr)
 {
     PFN_encodeTiled enc = get_encode();
     if (!enc) { b2s_set_error("cuTensorMapEncodeTiled entry point not available"); return -1; }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, dims, strides_bytes, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -40,9 +40,17 @@ def assert_detections_close(got, fix, box_tol=1e-4, score_tol=1e-5):
     # labels: argmax over class logits; only decided where the top-2 logit margin is above fp32 noise
     decided = np.asarray(fix["label_margin"]) > 1e-3 if "label_margin" in fix else np.ones(rl.shape, bool)
     np.testing.assert_array_equal(gl[decided], rl[decided])
-    # decoded boxes reach |x| ~ 70 m: absolute bar 1e-4 (the bar on the O(1) regression outputs, checked
-    # separately on the raw head tensors) plus 2e-5 relative for the decoded magnitude
-    np.testing.assert_allclose(gb[:, :6], rb[:, :6], rtol=2e-5, atol=box_tol)
+    # The bar (BASELINE.json north_star) is 1e-4 on the box REGRESSION outputs.  The decode
+    # (box_torch_ops.py:56-102) multiplies them by the anchor: x = xt*diag + xa, z = zt*h + za, w = exp(wt)*wa ...,
+    # so a decoded coordinate may move by 1e-4 * max(1, diag, h) of its own box (NuScenes buses: diag ~ 12 m),
+    # plus 2e-5 relative for fp32 rounding of the decoded magnitude (|x| ~ 70 m).
+    scale = np.maximum(1.0, np.maximum(np.hypot(rb[:, 3], rb[:, 4]), rb[:, 5]))[:, None]
+    err = np.abs(gb[:, :6] - rb[:, :6])
+    bound = 2e-5 * np.abs(rb[:, :6]) + box_tol * scale
+    bad = err > bound
+    assert not bad.any(), "decoded boxes differ: %d elements, worst %g (bound %g)" % (
+        int(bad.sum()), float((err - bound).max() + bound[np.unravel_index(np.argmax(err - bound), err.shape)]),
+        float(bound[np.unravel_index(np.argmax(err - bound), err.shape)]))
     # angles are compared modulo 2*pi (direction fix-up adds multiples of the period)
     d = np.abs(gb[:, 6] - rb[:, 6])
     d = np.minimum(d, np.abs(d - 2 * np.pi))

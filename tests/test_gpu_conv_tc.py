@@ -1,5 +1,7 @@
 """GPU parity of the tensor-core RPN convolution (b2s_conv2d_tc, tcgen05 + 3xTF32 split) against torch fp32
 conv2d with TF32 disabled.  Bar: fp32-grade accuracy, |err| <= 2e-5 * max|ref| (plain TF32 would be ~1e-3)."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -75,38 +77,61 @@ def test_conv1x1_heads_packed(product):
     assert float(o[..., cout:].abs().sum()) == 0.0
 
 
-@pytest.mark.timeout(180)
-def test_rpn_stack_matches_torch(product):
-    """whole car.fhd RPN (6 blocks + deblock + heads) chained through hi/lo planes vs the torch modules."""
-    from b2second import config, models, tc
+def run_rpn_plan(product, plan, x_nchw):
+    """execute a tc.plan_rpn program with b2s_conv2d_tc_ex; returns the packed heads tensor [B, H, W, S]."""
+    from b2second import tc
     L = product._lib
     lib = L.load()
-    net = models.build_network(config.get_config("car.fhd"), product).eval()
-    models.synthetic_weights_(net, "car.fhd", seed=0)
+    B = x_nchw.shape[0]
+    bufs = {"in": tc.split_tf32(pad_nhwc(x_nchw))}
+    for name, (h, w, c) in plan["buffers"].items():
+        bufs[name] = (torch.zeros(B, h + 2, w + 2, c, device="cuda"), torch.zeros(B, h + 2, w + 2, c, device="cuda"))
+    hd = plan["heads"]
+    heads = torch.zeros(B, hd["H"], hd["W"], hd["stride"], device="cuda")
+    bufs["heads"] = (heads, None)
+    keep = []
+    for op in plan["ops"]:
+        src, dst = bufs[op["src"]], bufs[op["dst"]]
+        o_hi = ctypes.c_void_p(dst[0].data_ptr() + 4 * op["dst_coff"])
+        o_lo = ctypes.c_void_p(dst[1].data_ptr() + 4 * op["dst_coff"]) if op["planes"] == 2 else None
+        keep.append((op["scale"], op["shift"]))
+        L.check(lib.b2s_conv2d_tc_ex(
+            L.ptr(src[0]), L.ptr(src[1]), B, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]), L.ptr(op["w_lo"]),
+            op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
+            L.ptr(op["scale"]) if op["scale"] is not None else None,
+            L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi, o_lo,
+            op["Hout"], op["Wout"], 1 if op["padded"] else 0, dst[0].shape[-1], op["out_mul"], op["off_h"], op["off_w"],
+            L.stream()), "b2s_conv2d_tc_ex")
+    torch.cuda.synchronize()
+    return heads
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("name,H,W", [("car.fhd", 40, 48), ("all.fhd", 40, 48), ("pointpillars.car.xyres_16", 48, 40),
+                                       ("nuscenes.all.pp.largea", 48, 64)])
+def test_rpn_program_matches_torch(product, name, H, W):
+    """whole RPNV2 of each config family (stride-1 / stride-2 blocks, k=1/2/4 ConvTranspose2d and k=2/4 strided
+    Conv2d deblocks, channel concat, 1x1 heads) as a b2s_conv2d_tc_ex program vs the torch modules (fp32)."""
+    from b2second import config, models, tc
+    cfg = config.get_config(name)
+    net = models.build_network(cfg, product).eval()
+    models.synthetic_weights_(net, name, seed=0)
     rpn = net.rpn.cuda()
     assert tc.supported(rpn)
-    B, H, W = 2, 40, 48
-    x = torch.relu(torch.randn(B, 128, H, W, device="cuda"))
+    B = 2
+    cin = rpn.blocks[0][1].in_channels
+    x = torch.relu(torch.randn(B, cin, H, W, device="cuda"))
     x = x * (torch.rand(B, 1, H, W, device="cuda") < 0.15)        # sparse BEV-like input
     with torch.no_grad():
         feat = rpn.backbone(x)
-        ref = torch.cat([rpn.conv_box(feat), rpn.conv_cls(feat), rpn.conv_dir_cls(feat)], 1)
-    plan = tc.plan_rpn(rpn)
-    hi, lo = tc.split_tf32(pad_nhwc(x))
-    for lyr in plan[:-1]:
-        o_hi = torch.zeros(B, H + 2, W + 2, lyr["cout"], device="cuda")
-        o_lo = torch.zeros_like(o_hi)
-        L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, lyr["cin"], L.ptr(lyr["w_hi"]), L.ptr(lyr["w_lo"]),
-                                  lyr["taps"], lyr["cout"], lyr["n_pad"], L.ptr(lyr["scale"]), L.ptr(lyr["shift"]),
-                                  1, L.ptr(o_hi), L.ptr(o_lo), 1, lyr["cout"], L.stream()), "b2s_conv2d_tc")
-        hi, lo = o_hi, o_lo
-    lyr = plan[-1]
-    out = torch.zeros(B, H, W, 32, device="cuda")
-    L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, lyr["cin"], L.ptr(lyr["w_hi"]), L.ptr(lyr["w_lo"]), 1,
-                              lyr["cout"], lyr["n_pad"], None, L.ptr(lyr["shift"]), 0, L.ptr(out), None, 0, 32,
-                              L.stream()), "b2s_conv2d_tc")
-    torch.cuda.synchronize()
-    got = out[..., :20].permute(0, 3, 1, 2)
+        heads = [rpn.conv_box(feat), rpn.conv_cls(feat)] + ([rpn.conv_dir_cls(feat)] if rpn._use_direction_classifier else [])
+        ref = torch.cat(heads, 1)
+    plan = tc.plan_rpn(rpn, H, W)
+    out = run_rpn_plan(product, plan, x)
+    n = ref.shape[1]
+    got = out[..., :n].permute(0, 3, 1, 2)
+    assert got.shape == ref.shape
     err = (got - ref).abs().max().item()
-    assert err <= 1e-4, "head tensors differ by %g (bar 1e-4 on the regression outputs)" % err
-    assert lyr["head_offsets"] == [0, 14, 16, 20]
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), "head tensors differ by %g (bar 1e-4 on the regression outputs)" % err
+    offs = plan["heads"]["offsets"]
+    assert offs[-1] == n and offs[0] == 0
