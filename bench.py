@@ -14,9 +14,10 @@ Prints ONE JSON line (rank 0):
   e2e       same metric through the public call with HOST (pinned) clouds: H2D of the points and D2H of the
             detections inside the timed region
   roofline  the dominant hand-written kernel, timed live with CUDA events (eager replay of the same pipeline):
-            k_conv_tc (tcgen05 dense RPN; bound "tensor": algorithmic fp32 flops / time against
-            MEASURED_PEAKS.json bf16_tflops, with the 3xTF32 ceiling spelled out), and as `second_kernel`
-            the sparse middle layers (bound "hbm": SURVEY.md §8d bytes / time against hbm_gbs)
+            k_conv3x3_tc2 (tcgen05 3x3 RPN layers; bound "tensor": algorithmic fp32 flops per launch / average
+            launch time against MEASURED_PEAKS.json bf16_tflops, with the 3xTF32 ceiling spelled out; `traffic`
+            from the committed ncu capture), and as `second_kernel` the sparse middle layers (bound "hbm":
+            SURVEY.md §8d bytes / time against hbm_gbs)
   cpu_baseline  the same network through the CPU oracle (`port`: C voxelizer/NMS + torch-CPU sparse conv/RPN)
             on a bounded sample of the same workload, host cores of this box
 --impl reference: the reference arm = the reference's CPU implementation of the path.  spconv 1.x is not
