@@ -82,7 +82,7 @@ class InferenceEngine:
             rpn_impl = "tc" if _tc.supported(net.rpn) else "cudnn"
         assert rpn_impl in ("tc", "cudnn")
         if rpn_impl == "tc" and not _tc.supported(net.rpn):
-            raise ValueError("rpn_impl='tc': this RPN has strided/upsampling stages (cuDNN only this round)")
+            raise ValueError("rpn_impl='tc': this RPN has a layer b2s_conv2d_tc_ex does not cover (channels % 32, kernel > 4)")
         self.rpn_impl = rpn_impl
         assert sparse_impl in ("tc", "fma")       # sparse-conv inner product: tcgen05 3xTF32 | fp32 FMA tiles
         self.sparse_impl = sparse_impl

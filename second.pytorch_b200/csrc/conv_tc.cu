@@ -19,7 +19,7 @@
 // CTA = 8 warps, persistent over output tiles (static round robin):
 //   warp 0  TMA producer   : per K block (tap, 32-channel chunk) 4 bulk-tensor loads into a 3-stage smem ring
 //   warp 1  MMA issuer     : one elected lane issues 3 x 4 tcgen05.mma per K block, tcgen05.commit frees the stage
-//   warp 2  TMEM allocator : 2 accumulator stages x N columns
+//   warp 2  TMEM allocator : 4 accumulator slots x N columns
 //   warps 4-7 epilogue     : tcgen05.ld accumulator -> BN scale/shift -> ReLU -> hi/lo split -> NHWC stores
 // mbarrier pipelines: smem full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), so the epilogue of
 // tile i overlaps the main loop of tile i+1.
@@ -59,10 +59,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
     constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     // The tensor core's fp32 accumulate is not round-to-nearest: a long accumulation chain (432 MMAs for a
-    // 3x3x128 tap stack) showed a systematic ~2e-5 relative error (measured, round 1).  So every filter TAP is
-    // accumulated in its own short chain (48 MMAs) into one of ACC_SLOTS TMEM accumulators, and the epilogue
-    // warps drain the per-tap partial sums into fp32 registers with round-to-nearest adds while the tensor core
-    // already works on the next tap.
+    // 3x3x128 tap stack) showed a systematic ~2e-5 relative error (measured, round 1).  So the reduction is cut
+    // into short chains of p.chain K blocks (default 4 = 48 MMAs) into one of ACC_SLOTS TMEM accumulators, and the
+    // epilogue warps drain the partial sums into fp32 registers with round-to-nearest adds while the tensor core
+    // already works on the next chain.
     constexpr int ACC_SLOTS = 4;
     constexpr uint32_t TMEM_COLS = (ACC_SLOTS * N <= 32) ? 32 : (ACC_SLOTS * N <= 64) ? 64 : (ACC_SLOTS * N <= 128) ? 128
                                    : (ACC_SLOTS * N <= 256) ? 256 : 512;
@@ -189,7 +189,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ 
             int tw = tile % p.tiles_w;
             int th = (tile / p.tiles_w) % p.tiles_h;
             int b = tile / (p.tiles_w * p.tiles_h);
-            // drain the per-tap partial sums into fp32 registers (round-to-nearest adds)
+            // drain the per-chain partial sums into fp32 registers (round-to-nearest adds)
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;

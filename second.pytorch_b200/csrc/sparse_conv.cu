@@ -8,8 +8,8 @@
 // exactly once (no atomics, no scatter-add), with the BatchNorm1d(eval)+ReLU that always follows a
 // sparse conv in second.pytorch (middle.py:146-191) folded into the epilogue.
 //
-// Round-1 core: fp32 FMA register tiles (exact fp32 parity with the oracle).  The tcgen05 (3xTF32)
-// GEMM core that replaces the inner product is staged separately.
+// fp32 FMA register tiles (exact fp32 parity with the oracle): the fallback for channel widths the tensor-pipe
+// kernel (sparse_conv_tc.cu: Cin in {4,16,32,64}) does not cover, and the `sparse_impl="fma"` cross-check.
 //
 // Algorithmic traffic per layer: 4*(N_in*Cin + N_out*Cout) + 4*K*N_out (nbr table)
 // + 4*K*Cin*Cout (weights) bytes; flops = 2*pairs*Cin*Cout.
