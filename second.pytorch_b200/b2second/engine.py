@@ -8,12 +8,13 @@ keeps every data-dependent count in device memory and runs a fixed launch sequen
 capacity-sized buffers, so the whole frame batch is ONE CUDA graph:
 
   b2s_voxelize (+ fused SimpleVoxel mean)                     voxelnet.py:325-328, preprocess.py:303-315
-  per sparse layer: b2s_rulebook_{subm,conv} (cached per indice_key) + b2s_sparse_conv with the
-      BatchNorm1d/ReLU folded into the epilogue                middle.py:145-192
+  per sparse layer: b2s_rulebook_{subm,conv} (cached per indice_key) + b2s_sparse_conv_tc (tcgen05, hi/lo
+      planes flow from layer to layer) with BatchNorm1d/ReLU folded into the epilogue      middle.py:145-192
   b2s_pfn (PointPillars)                                       pointpillars.py:203-237
-  b2s_to_bev                                                   middle.py:206-209 / pointpillars.py:444-476
-  RPN backbone + 1x1 heads (torch/cuDNN, fp32, TF32 off)       rpn.py:314-331,393-420
-  b2s_decode_filter + b2s_nms (+ direction/range epilogue)     voxelnet.py:377-645
+  b2s_to_bev_tc (NHWC + halo, hi/lo)                           middle.py:206-209 / pointpillars.py:444-476
+  RPN as a program of b2s_conv2d_tc_ex launches (tc.plan_rpn)  rpn.py:314-331,393-420,467-497
+      (rpn_impl="cudnn" keeps the torch modules as a cross-check: fp32, TF32 off)
+  b2s_decode_filter_strided + b2s_nms (+ direction/range epilogue)   voxelnet.py:377-645
 
 Output per batch: ``det [B, post_max, code+2]`` (box, score, label) + ``det_count [B]`` -- the fixed-stride
 record the multi-GPU path all-gathers.
