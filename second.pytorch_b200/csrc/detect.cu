@@ -329,37 +329,55 @@ k_iou_mask(const float *__restrict__ geo, const int *__restrict__ n_sorted, int 
 {
     const int b = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
     const int n = n_sorted ? n_sorted[b] : pre_max;
-    if (rb * 64 >= n || cb * 64 >= n) return;
-    __shared__ float s_col[64][12];
+    if (rb * 64 >= n || cb * 64 >= n || cb < rb) return;      // only the upper triangle of tiles is ever read
+    __shared__ float s_col[64][12], s_row[64][12];
+    __shared__ unsigned long long s_bits[64];
+    __shared__ unsigned short s_queue[64 * 64];               // (row << 6 | col) of the pairs that need the polygon clip
+    __shared__ int s_nq;
     const int tid = threadIdx.x;
     const float *gb = geo + (size_t)b * pre_max * 12;
     for (int i = tid; i < 64 * 12; i += 256) {
         int r = i / 12, q = i % 12;
-        int j = cb * 64 + r;
+        int j = cb * 64 + r, ii = rb * 64 + r;
         s_col[r][q] = (j < n) ? gb[(size_t)j * 12 + q] : 0.f;
+        s_row[r][q] = (ii < n) ? gb[(size_t)ii * 12 + q] : 0.f;
     }
+    if (tid < 64) s_bits[tid] = 0ull;
+    if (tid == 0) s_nq = 0;
     __syncthreads();
     const int r = tid >> 2, quarter = tid & 3;
     const int i = rb * 64 + r;
-    unsigned bits = 0;
-    if (i < n && cb >= rb) {
-        float gi[12];
-#pragma unroll
-        for (int q = 0; q < 12; ++q) gi[q] = gb[(size_t)i * 12 + q];
+    if (i < n) {
+        unsigned long long bits = 0ull;
         for (int cc = 0; cc < 16; ++cc) {
-            int jl = quarter * 16 + cc;
-            int j = cb * 64 + jl;
+            const int jl = quarter * 16 + cc;
+            const int j = cb * 64 + jl;
             if (j >= n || j <= i) continue;
-            bool sup = rotated ? suppress_rotated(gi, gi + 8, s_col[jl], s_col[jl] + 8, thresh)
-                               : suppress_aligned(gi + 8, s_col[jl] + 8, thresh, eps, inclusive != 0);
-            if (sup) bits |= 1u << cc;
+            if (rotated) {
+                // cheap stand-up test here; the (divergent, ~500-instruction) polygon clip of the surviving pairs
+                // is queued and spread evenly over the CTA below -- overlapping boxes cluster in a few rows, and a
+                // warp would otherwise wait for its busiest lane
+                const float *si = s_row[r] + 8, *sj = s_col[jl] + 8;
+                const float iw = fminf(si[2], sj[2]) - fmaxf(si[0], sj[0]);
+                const float ih = fminf(si[3], sj[3]) - fmaxf(si[1], sj[1]);
+                if (iw > 0.f && ih > 0.f) s_queue[atomicAdd(&s_nq, 1)] = (unsigned short)((r << 6) | jl);
+            } else if (suppress_aligned(s_row[r] + 8, s_col[jl] + 8, thresh, eps, inclusive != 0)) {
+                bits |= 1ull << jl;
+            }
         }
+        if (bits) atomicOr(&s_bits[r], bits);
     }
-    // combine the four 16-bit quarters of a row (adjacent lanes)
-    unsigned long long w = (unsigned long long)bits << (16 * quarter);
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    if (quarter == 0 && i < n) mask[((size_t)b * pre_max + i) * words + cb] = w;
+    __syncthreads();
+    if (rotated) {
+        const int nq = s_nq;
+        for (int q = tid; q < nq; q += 256) {
+            const int rr = s_queue[q] >> 6, jl = s_queue[q] & 63;
+            if (suppress_rotated(s_row[rr], s_row[rr] + 8, s_col[jl], s_col[jl] + 8, thresh))
+                atomicOr(&s_bits[rr], 1ull << jl);
+        }
+        __syncthreads();
+    }
+    if (tid < 64 && rb * 64 + tid < n) mask[((size_t)b * pre_max + rb * 64 + tid) * words + cb] = s_bits[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
