@@ -106,3 +106,38 @@ def test_forward_contract_on_oracle(oracle):
         bad = dict(ex)
         bad["anchors"] = ex["anchors"][:, :100]
         net(bad)
+
+
+def test_pack_sparse_weights_layout():
+    """b2second.tc.pack_sparse_weights: the packed K-block GEMM (32 columns = PACK offsets x Cin channels) must equal
+    the per-offset contraction sum_k in[nbr[o,k]] @ W[k] that b2s_sparse_conv_tc's gather assembles for Cin < 32."""
+    import torch
+    from b2second import tc
+    g = torch.Generator().manual_seed(0)
+    for cin, cout in ((4, 16), (16, 32), (32, 32)):
+        K, n = 27, 50
+        w = torch.randn(K, cin, cout, generator=g)
+        x = torch.randn(n, cin, generator=g)
+        nbr = torch.randint(-1, n, (n, K), generator=g)
+        ref = torch.zeros(n, cout)
+        for k in range(K):
+            ok = nbr[:, k] >= 0
+            ref[ok] += x[nbr[ok, k]] @ w[k]
+        p = tc.pack_sparse_weights(w)
+        if cin >= 32:
+            assert p.shape == (K, cout, cin) and torch.equal(p, w.transpose(1, 2))
+            continue
+        pack = 32 // cin
+        nkb = (K + pack - 1) // pack
+        assert p.shape == (nkb, cout, 32)
+        got = torch.zeros(n, cout)
+        for kb in range(nkb):
+            a = torch.zeros(n, 32)                      # the gathered A tile row: PACK neighbours side by side
+            for ko in range(pack):
+                k = kb * pack + ko
+                if k >= K:
+                    continue
+                ok = nbr[:, k] >= 0
+                a[ok, ko * cin:(ko + 1) * cin] = x[nbr[ok, k]]
+            got += a @ p[kb].t()
+        assert float((got - ref).abs().max()) < 1e-4
