@@ -11,13 +11,17 @@ step ends with the single all-gather of detection records (N > 1).
 Prints ONE JSON line (rank 0):
   value     whole-job clouds/s with the clouds already resident in HBM, CUDA-event timed per step, L2
             flushed between steps, max over ranks
-  e2e       same metric through the public call with HOST (pinned) clouds: H2D of the points and D2H of the
-            detections inside the timed region
+  e2e       same metric through the reference-facing call -- net(example), the VoxelNet.forward contract, bound to
+            the fused engine by b2second.fastpath.accelerate -- with HOST (pinned) clouds: H2D of the points and D2H of
+            the detection records inside the timed region
   roofline  the dominant hand-written kernel, timed live with CUDA events (eager replay of the same pipeline):
             k_conv3x3_tc2 (tcgen05 3x3 RPN layers; bound "tensor": algorithmic fp32 flops per launch / average
-            launch time against MEASURED_PEAKS.json bf16_tflops, with the 3xTF32 ceiling spelled out; `traffic`
+            launch time against MEASURED_PEAKS.json bf16_tflops, with the 3xF16 ceiling spelled out; `traffic`
             from the committed ncu capture), and as `second_kernel` the sparse middle layers (bound "hbm":
             SURVEY.md §8d bytes / time against hbm_gbs)
+  configs   short runs of the other BASELINE.json configurations (car.lite, pointpillars xyres_16, all.fhd at 32
+            frames split over the ranks, NuScenes at ~300 k points per cloud) and the bs=1 latency of the headline
+            config, each with its stage split and RPN tensor rate
   cpu_baseline  the same network through the CPU oracle (`port`: C voxelizer/NMS + torch-CPU sparse conv/RPN)
             on a bounded sample of the same workload, host cores of this box
 --impl reference: the reference arm = the reference's CPU implementation of the path.  spconv 1.x is not
@@ -55,6 +59,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=24,
                     help="frames in the bounded CPU-baseline sample (~0.4 s each on 16 host threads -> ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--sparse", default="tc", choices=["tc", "fma"],
                     help="sparse-conv inner product: tc = tcgen05 3xTF32 (wide layers), fma = fp32 FMA tiles")
     ap.add_argument("--rpn", default="auto", choices=["auto", "tc", "cudnn"],
@@ -79,7 +84,8 @@ def workload_desc(args, n_voxels=None):
          "points_per_cloud": args.points, "frames_per_gpu_per_step": args.batch,
          "parallelism": "frames sharded dp%d, one all-gather of detections" % args.gpus,
          "l2": "flushed between steps (512 MiB write), per-step CUDA events",
-         "rpn": args.rpn, "sparse_conv": args.sparse, "precision": "fp32 (RPN tc = 3xTF32 split on tcgen05, fp32-grade)"}
+         "rpn": args.rpn, "sparse_conv": args.sparse,
+         "precision": "fp32-grade (tcgen05 kind::f16 on a 3-term fp16 hi/lo split, fp32 accumulation)"}
     if n_voxels is not None:
         d["active_voxels_per_cloud"] = n_voxels
     return d
@@ -107,6 +113,11 @@ def cpu_path_clouds_per_s(name, clouds, threads):
             net(ex)
     dt = time.perf_counter() - t0
     return len(clouds) / dt, dt
+
+
+CPU_KIND = ("port: mirror model (b2second.models, reference state-dict keys) on the oracle spconv package -- C voxelizer "
+            "and NMS (single thread, as upstream) + torch-CPU sparse conv / RPN; the unmodified reference cannot run "
+            "here (spconv 1.x absent, /root/reference not on the GPU box)")
 
 
 def cpu_threads():
@@ -140,6 +151,7 @@ def run_reference_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_desc(args),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "kind_detail": CPU_KIND,
                              "sample": "%d clouds per step, %d steps, whole hot path on host cores"
                                        % (len(clouds), len(vals))},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,10 +199,102 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _timed(fn, steps, warmup, flush, world, dev):
+    """W untimed steps, then K steps each bracketed by CUDA events (L2 flushed between steps, outside the pair);
+    barrier + synchronize on both sides; max over ranks.  Returns total ms."""
+    import torch.distributed as dist
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = []
+    for i in range(steps):
+        flush.fill_(float(i))          # evict L2 between steps (outside the event pair)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn(warmup + i)
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _rpn_tensor_rate(eng, stages, peaks):
+    """algorithmic fp32 TFLOP/s of the k_conv3x3_tc2 launches of one step (stage "rpn") against the measured bf16 peak."""
+    rstats = [s for s in eng.rpn_layer_stats() if s["v2"]]
+    rpn_ms = stages.get("rpn", 0.0)
+    if not rstats or rpn_ms <= 0:
+        return None
+    bf16 = float(peaks.get("bf16_tflops", 1687.0))
+    n_l = len(rstats)
+    flops = sum(s["flops"] for s in rstats) / n_l
+    launch_ms = rpn_ms / n_l
+    ach = flops / (launch_ms * 1e-3) / 1e12
+    return {"launches": n_l, "ms_per_launch": launch_ms, "achieved": ach, "peak": bf16, "frac": ach / bf16,
+            "algorithmic_flops_per_launch": flops,
+            "bytes_moved_per_launch": sum(s["bytes"] for s in rstats) / n_l,
+            "algorithmic_bytes_per_launch_fp32": sum(s["bytes_fp32_algorithmic"] for s in rstats) / n_l}
+
+
+def _group_stages(stages):
+    grouped = {}
+    for k, v in stages.items():
+        g = "sparse_conv" if k.startswith("sparse_conv") else ("rulebook" if k.startswith("rulebook") else k)
+        grouped[g] = grouped.get(g, 0.0) + v
+    return grouped
+
+
+def measure_config(name, B, points, steps, warm, dev, world, rank, flush, peaks):
+    """short run of one BASELINE configuration through net(example): resident clouds/s, e2e clouds/s, stage split."""
+    from b2second import config, fastpath, loader, models
+    sp = loader.product_spconv()
+    cfg = config.get_config(name)
+    net = models.build_network(cfg, sp).eval()
+    models.synthetic_weights_(net, name, seed=0)
+    net = fastpath.accelerate(net.to(dev), max_points=points + 1000, output="host")
+    eng = net.b2s_fastpath.engine(B)
+    uniq = make_clouds(name, min(2 * B, 4), points, seed0=1000 * rank + 7)   # a few distinct clouds, tiled over the slots
+    clouds = [uniq[i % len(uniq)] for i in range(2 * B)]
+    host = [[torch.from_numpy(c).pin_memory() for c in clouds[s * B:(s + 1) * B]] for s in range(2)]
+    devc = [[h.to(dev) for h in hs] for hs in host]
+    anchors = torch.from_numpy(net.anchors()[None]).to(dev)
+    ms_res = _timed(lambda i: eng.infer(devc[i % 2]), steps, warm, flush, world, dev)
+    ms_e2e = _timed(lambda i: net({"points": host[i % 2], "anchors": anchors}), steps, warm, flush, world, dev)
+    eng.check_status()
+    out = {"config": name, "frames_per_gpu_per_step": B, "points_per_cloud": int(np.mean([c.shape[0] for c in clouds])),
+           "steps": steps, "ms_per_step": ms_res / steps, "clouds_per_s": world * B * steps / (ms_res / 1e3),
+           "e2e_ms_per_step": ms_e2e / steps, "e2e_clouds_per_s": world * B * steps / (ms_e2e / 1e3)}
+    if rank == 0:
+        eng.load_points(devc[0])
+        stages = eng.run_timed(iters=3)
+        out["active_voxels_per_cloud"] = int(eng.num_voxels[0].item()) // B
+        out["stage_ms_eager"] = _group_stages(stages)
+        out["rpn_3x3_tensor"] = _rpn_tensor_rate(eng, stages, peaks)
+        out["gpu_launches_per_step"] = eng.kernel_launches_per_step()
+    del eng, net
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
-    from b2second import config, dist as b2dist, loader, models
-    from b2second.engine import InferenceEngine
+    from b2second import config, dist as b2dist, fastpath, loader, models
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -203,59 +307,35 @@ def run_gpu_arm(args):
     cfg = config.get_config(args.config)
     net = models.build_network(cfg, sp).eval()
     models.synthetic_weights_(net, args.config, seed=0)
-    net = net.to(dev)
     B = args.batch
-    eng = InferenceEngine(net, batch_size=B, max_points=args.points + 1000, use_cuda_graph=True, rpn_impl=args.rpn,
-                          sparse_impl=args.sparse)
+    # the public call: net(example) (VoxelNet.forward contract), bound to the fused engine
+    net = fastpath.accelerate(net.to(dev), max_points=args.points + 1000, output="host", rpn_impl=args.rpn,
+                              sparse_impl=args.sparse)
+    fast = net.b2s_fastpath
+    eng = fast.engine(B)
     args.rpn = eng.rpn_impl
     gather = b2dist.DetectionGatherer(B, eng.post_max, eng.code + 2, dev) if world > 1 else None
+    if gather is not None:
+        fast.post_run = lambda e: gather.gather_records(e.det_record)     # the one collective of a step
     # distinct clouds per rank and per slot; two alternating batches so consecutive steps differ
     n_sets = 2
     clouds = make_clouds(args.config, n_sets * B, args.points, seed0=1000 * rank)
     host = [[torch.from_numpy(c).pin_memory() for c in clouds[s * B:(s + 1) * B]] for s in range(n_sets)]
     devc = [[h.to(dev) for h in hs] for hs in host]
+    anchors = torch.from_numpy(net.anchors()[None]).to(dev)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
     h2d_bytes = sum(int(h.numel()) * 4 for h in host[0])
-    det_host = torch.empty_like(eng.det, device="cpu").pin_memory()
-    cnt_host = torch.empty_like(eng.det_count, device="cpu").pin_memory()
-    d2h_bytes = det_host.numel() * 4 + cnt_host.numel() * 4
+    d2h_bytes = eng.det_record.numel() * 4 + 4
 
     def step_resident(i):
         eng.infer(devc[i % n_sets])        # device->device staging of the batch + one graph replay
         if gather is not None:
-            gather.gather(eng.det, eng.det_count)
+            gather.gather_records(eng.det_record)
 
     def step_e2e(i):
-        eng.infer(host[i % n_sets])        # pinned host -> HBM inside the timed region
-        if gather is not None:
-            gather.gather(eng.det, eng.det_count)
-        det_host.copy_(eng.det, non_blocking=True)
-        cnt_host.copy_(eng.det_count, non_blocking=True)
-
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = []
-        for i in range(steps):
-            flush.fill_(float(i))          # evict L2 between steps (outside the event pair)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn(warmup + i)
-            b.record()
-            evs.append((a, b))
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        # pinned host clouds in, host tensors out: H2D of the points, the graph, the all-gather (N > 1) and ONE D2H
+        # of the detection records all happen inside this call
+        net({"points": host[i % n_sets], "anchors": anchors})
 
     warm = max(args.warmup, 3)
     sampler = ClockSampler(local)
@@ -271,13 +351,30 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    ms_res = timed(step_resident, args.steps, warm)
-    ms_e2e = timed(step_e2e, args.steps, warm)
+    ms_res = _timed(step_resident, args.steps, warm, flush, world, dev)
+    ms_e2e = _timed(step_e2e, args.steps, warm, flush, world, dev)
     clocks = sampler.stop() if rank == 0 else None
     eng.check_status()
     frames = world * B * args.steps
     value = frames / (ms_res / 1e3)
     e2e = frames / (ms_e2e / 1e3)
+    peaks = _peaks()
+    # ---- short runs of the other BASELINE configs (every rank takes part: all.fhd is split over the ranks)
+    extra = []
+    if not args.no_configs and args.config == "car.fhd":
+        k = max(3, min(5, args.steps))
+        plan = [("car.fhd", 1, args.points),                                  # bs=1 latency of the headline config
+                ("car.lite", B, args.points),
+                ("pointpillars.car.xyres_16", B, args.points),
+                ("all.fhd", max(1, 32 // world), args.points),               # BASELINE config 4: bs=32 over the ranks
+                ("nuscenes.all.pp.largea", 4, 300000)]                       # BASELINE config 5: ~300 k points / cloud
+        del devc
+        for name, b, pts in plan:
+            try:
+                extra.append(measure_config(name, b, pts, k, 3, dev, world, rank, flush, peaks))
+            except Exception as e:      # a side measurement must not take the headline line down
+                extra.append({"config": name, "error": "%s: %s" % (type(e).__name__, e)})
+        devc = [[h.to(dev) for h in hs] for hs in host]
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -291,71 +388,66 @@ def run_gpu_arm(args):
     conv_ms = sum(v for k, v in stages.items() if k.startswith("sparse_conv"))
     conv_bytes = sum(s["bytes"] for s in stats)
     conv_flops = sum(s["flops"] for s in stats)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sparse_roof = {"kernel": "k_sparse_conv%s (all %d sparse layers of one step, %d frames)"
                              % ("_tc" if args.sparse == "tc" else "", len(stats), B),
                    "bound": "hbm", "achieved": conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms > 0 else 0.0,
                    "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes_per_step": conv_bytes,
                    "algorithmic_flops_per_step": conv_flops, "ms_per_step": conv_ms,
-                   "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0}
+                   "achieved_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0,
+                   "useful_mma_frac_per_layer": [round(s["useful_mma_frac"], 3) for s in stats]}
     sparse_roof["frac"] = sparse_roof["achieved"] / hbm_peak
-    rstats = [s for s in eng.rpn_layer_stats() if s["v2"]]       # the launches k_conv3x3_tc2 takes
-    rpn_ms = stages.get("rpn", 0.0)            # the 3x3 stack only (the 1x1 tail is stage "rpn_1x1")
-    if rstats and rpn_ms >= 0.5 * conv_ms:
-        # dominant kernel = k_conv3x3_tc2 (dense RPN 3x3 layers, implicit GEMM on tcgen05, 3xTF32 split for
-        # fp32-grade results).  `achieved` counts ALGORITHMIC fp32 flops per launch (2*px*9*cin*cout) over the
-        # average launch duration; the tensor pipe executes 3 tf32 MMAs per algorithmic MAC and tf32 runs at half
-        # the bf16 rate, so bf16_peak/6 is this arithmetic's ceiling -- reported alongside.
-        bf16 = float(peaks.get("bf16_tflops", 1687.0))
-        n_l = len(rstats)
-        flops = sum(s["flops"] for s in rstats) / n_l
-        launch_ms = rpn_ms / n_l
-        ach = flops / (launch_ms * 1e-3) / 1e12
+    rt = _rpn_tensor_rate(eng, stages, peaks)
+    if rt is not None and stages.get("rpn", 0.0) >= 0.5 * conv_ms:
+        # dominant kernel = k_conv3x3_tc2 (dense RPN 3x3 layers, implicit GEMM on tcgen05, 3xF16 split for fp32-grade
+        # results).  `achieved` counts ALGORITHMIC fp32 flops per launch (2*px*9*cin*cout) over the average launch
+        # duration; the tensor pipe executes 3 fp16 MMAs per algorithmic MAC, so bf16_peak/3 is this arithmetic's
+        # ceiling -- reported alongside.
         traffic = None
         try:   # dram read+write bytes per launch from the committed ncu --set full capture of this kernel
-            tj = json.load(open(os.path.join(REPO, "profiles", "r1_traffic.json")))
+            tj = json.load(open(os.path.join(REPO, "profiles", "r2_traffic.json")))
             traffic = tj["k_conv3x3_tc2"]["dram_bytes_per_launch"] * B / tj["frames_in_capture"]
         except Exception:
             pass
-        roofline = {"kernel": "k_conv3x3_tc2 (per launch; %d launches per step, %d frames)" % (n_l, B),
-                    "bound": "tensor", "achieved": ach, "peak": bf16, "unit": "TFLOP/s", "frac": ach / bf16,
-                    "traffic": traffic, "traffic_source": "profiles/r1_traffic.json (ncu --set full)",
+        roofline = {"kernel": "k_conv3x3_tc2 (per launch; %d launches per step, %d frames)" % (rt["launches"], B),
+                    "bound": "tensor", "achieved": rt["achieved"], "peak": rt["peak"], "unit": "TFLOP/s",
+                    "frac": rt["frac"], "traffic": traffic,
+                    "traffic_source": "profiles/r2_traffic.json (ncu --set full)" if traffic else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback",
-                    "algorithmic_flops_per_launch": flops,
-                    "algorithmic_bytes_per_launch": sum(s["bytes"] for s in rstats) / n_l,
-                    "ms_per_launch": launch_ms, "issued_tf32_tflops": 3 * ach, "tf32_peak": bf16 / 2,
-                    "frac_of_tf32_pipe": 3 * ach / (bf16 / 2),
-                    "note": "fp32-parity arithmetic: each MAC = 3 tf32 MMAs (hi*hi, hi*lo, lo*hi); tf32 runs at half "
-                            "the bf16 rate, so 1/6 of the bf16 peak is this kernel's arithmetic ceiling",
+                    "algorithmic_flops_per_launch": rt["algorithmic_flops_per_launch"],
+                    "algorithmic_bytes_per_launch": rt["algorithmic_bytes_per_launch_fp32"],
+                    "bytes_moved_per_launch": rt["bytes_moved_per_launch"],
+                    "ms_per_launch": rt["ms_per_launch"], "issued_f16_tflops": 3 * rt["achieved"],
+                    "frac_of_pipe_issued": 3 * rt["achieved"] / rt["peak"],
+                    "note": "fp32-parity arithmetic: each MAC = 3 fp16 MMAs (hi*hi, hi*lo, lo*hi) with fp32 accumulation, "
+                            "so 1/3 of the bf16/fp16 peak is this kernel's arithmetic ceiling",
                     "second_kernel": sparse_roof}
     else:
         roofline = dict(sparse_roof, traffic=None, peak_source="measured" if peaks else "fallback")
-    grouped = {}
-    for k, v in stages.items():
-        g = "sparse_conv" if k.startswith("sparse_conv") else ("rulebook" if k.startswith("rulebook") else k)
-        grouped[g] = grouped.get(g, 0.0) + v
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = cpu_threads()
         sample = clouds[:max(1, args.cpu_frames)]
         v, dt = cpu_path_clouds_per_s(args.config, sample, threads)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+        n1 = max(1, min(4, args.cpu_frames // 6))
+        v1, dt1 = cpu_path_clouds_per_s(args.config, clouds[:n1], 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "kind_detail": CPU_KIND,
                         "sample": "%d clouds of the same workload (%.1f s), whole hot path: C voxelizer + torch-CPU "
-                                  "sparse conv/RPN + C NMS" % (len(sample), dt)}
+                                  "sparse conv/RPN + C NMS" % (len(sample), dt),
+                        "one_thread": {"value": v1, "unit": UNIT, "cores": 1,
+                                       "sample": "%d clouds (%.1f s)" % (n1, dt1)}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "b2second",
             "config": workload_desc(args, n_vox),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "net(example) = VoxelNet.forward(example) bound by b2second.fastpath.accelerate; example = "
+                           "{'points': pinned host clouds, 'anchors'}; returns the reference's list of dicts (host)"},
             "gpu_launches": eng.kernel_launches_per_step() * args.steps,
             "gpu_launches_per_step": eng.kernel_launches_per_step(),
-            "clocks": clocks, "roofline": roofline, "stage_ms_eager": grouped, "cpu_baseline": cpu_baseline}
+            "clocks": clocks, "roofline": roofline, "stage_ms_eager": _group_stages(stages),
+            "cpu_baseline": cpu_baseline, "configs": extra}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

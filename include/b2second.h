@@ -49,13 +49,18 @@
 extern "C" {
 #endif
 
-#define B2S_VERSION 100
+#define B2S_VERSION 200
 
 /* status bits raised in *status_dev */
 #define B2S_STATUS_VOXEL_OVERFLOW 1u   /* more voxels than max_voxels (extra voxels dropped, as spconv) */
 #define B2S_STATUS_ROWS_OVERFLOW 2u    /* strided conv produced more rows than cap_out (rows dropped)   */
 #define B2S_STATUS_HASH_FULL 4u        /* hash table too small                                            */
 #define B2S_STATUS_CAND_OVERFLOW 8u    /* more score-threshold survivors than cand_cap (lowest dropped)  */
+#define B2S_STATUS_F16_RANGE 16u       /* an activation left the fp16 range (|x| > 65504) on the tensor-core path;
+                                          it was clamped -- results are not fp32-grade for that frame batch      */
+
+/* IEEE binary16 bit pattern (the tensor-core kernels' operand planes; torch.float16 storage) */
+typedef uint16_t b2s_half;
 
 int b2s_version(void);
 const char *b2s_last_error(void);
@@ -88,6 +93,12 @@ int b2s_voxelize(const float *points, const int *frame_offsets_dev, int num_poin
                  int hash_key_depth /*D of the flat (b,z,y,x) hash key = spatial_shape[0] of the tensor that will
                                       look rows up (SECOND: grid_z + 1, middle.py:139); 0 = grid z*/,
                  void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream);
+
+/* SimpleVoxel / SimpleVoxelRadius (second/pytorch/models/voxel_encoder.py:220-225,246-255) over voxels that arrive
+ * already gathered -- the reference's own example dict: voxels [rows, T, F] zero padded, num_points_per_voxel
+ * [rows]; rows = *num_rows_dev.  vfe_mode B2S_VFE_MEAN -> vfe_out [rows, nf]; B2S_VFE_MEAN_RADIUS -> [rows, nf-1]. */
+int b2s_vfe_mean(const float *voxels, const int *num_points_per_voxel, const int *num_rows_dev, int cap_rows, int T,
+                 int F, int vfe_mode, int vfe_num_features, float *vfe_out, void *stream);
 
 /* ---- rulebook --------------------------------------------------------------------------------- */
 /* coordinate -> row hash over `shape` (D,H,W).  hash_cap must be a power of two >= 2*cap_rows. */
@@ -128,24 +139,30 @@ int b2s_sparse_conv(const float *feat_in, int cin, const float *weight, const in
                     const int *num_out_dev, int cap_out, const float *scale, const float *shift,
                     int relu, float *feat_out, int cout, void *stream);
 
-/* same contraction on the tensor pipe (tcgen05, 3xTF32 hi/lo split, fp32-grade): Cin in {4,16,32,64}, Cout in
- * {16,32,64}, K <= 27.
- *   feat_hi/lo [rows_in, Cin] hi/lo planes; w_hi/lo [K, Cout, Cin] (the reference weight [K,Cin,Cout] transposed);
- *   for Cin < 32 the 32/Cin consecutive kernel offsets that share one 128-byte K block are packed side by side:
- *   w_hi/lo [ceil(K/(32/Cin)), Cout, 32], column = offset_in_pack*Cin + cin, zero columns past K;
- *   out_hi/out_lo [cap_out, Cout] (out_lo NULL -> out_hi holds the full fp32 value). */
-int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in /*row capacity of the feature planes
-                       (the TMA gather's tensor extent; rows >= rows_in read as zeros)*/,
-                       int cin, const float *w_hi, const float *w_lo,
-                       const int *nbr, int K, const int *num_out_dev, int cap_out, const float *scale,
-                       const float *shift, int relu, float *out_hi, float *out_lo, int cout, void *stream);
+/* same contraction on the tensor pipe (tcgen05 kind::f16, 3xF16 hi/lo split, fp32-grade): Cin in {8,16,32,64}, Cout in
+ * {16,32,64}, K <= 27 (b2s_sparse_conv_tc_supported).  Every fp32 operand x travels as two fp16 planes hi = fp16(x),
+ * lo = fp16(x - hi); per K step the kernel issues A_hi*W_hi + A_hi*W_lo + A_lo*W_hi with fp32 accumulation.
+ *   feat_hi/lo  rows of in_stride halves (>= Cin, multiple of 8; e.g. interleaved [row][hi Cin | lo Cin] with
+ *               feat_lo = feat_hi + Cin, in_stride = 2*Cin); a 3/4-feature input layer is zero-padded to Cin = 8;
+ *   w_hi/lo     [K, Cout, 64] for Cin = 64; for Cin < 64 the 64/Cin consecutive kernel offsets that share one
+ *               128-byte K block are packed side by side: [ceil(K/(64/Cin)), Cout, 64], column = offset_in_pack*Cin +
+ *               cin, zero columns past K.  Weights may be pre-scaled by a power of two folded into `scale`;
+ *   out_hi/lo   rows of out_stride halves; out_lo NULL -> out_hi is float [cap_out, Cout] (full fp32 value). */
+int b2s_sparse_conv_tc_supported(int cin, int cout);
+int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride,
+                       int rows_in /*row capacity of the feature planes*/, int cin, const b2s_half *w_hi,
+                       const b2s_half *w_lo, const int *nbr, int K, const int *num_out_dev, int cap_out,
+                       const float *scale, const float *shift, int relu, void *out_hi, b2s_half *out_lo, int out_stride,
+                       int cout, unsigned *status_dev, void *stream);
 
-/* fp32 rows <-> hi/lo planes (hi = tf32 round-to-nearest, lo = tf32-rounded remainder; hi + lo is exact in fp32).
- * rows = *num_rows_dev (NULL: cap_rows); row_floats multiple of 4. */
-int b2s_split_tf32(const float *x, float *hi, float *lo, const int *num_rows_dev, int cap_rows, int row_floats,
-                   void *stream);
-int b2s_merge_hilo(const float *hi, const float *lo, float *x, const int *num_rows_dev, int cap_rows,
-                   int row_floats, void *stream);
+/* fp32 rows <-> fp16 hi/lo planes (hi = fp16 round-to-nearest, lo = fp16-rounded remainder; saturating).
+ * split: x [rows, row_floats] -> rows of out_stride halves (>= row_floats, multiple of 8, zero padded).
+ * merge: rows of in_stride halves -> x [rows, row_floats] = hi + lo (exact in fp32).
+ * rows = *num_rows_dev (NULL: cap_rows). */
+int b2s_split_f16(const float *x, b2s_half *hi, b2s_half *lo, const int *num_rows_dev, int cap_rows, int row_floats,
+                  int out_stride, void *stream);
+int b2s_merge_f16(const b2s_half *hi, const b2s_half *lo, float *x, const int *num_rows_dev, int cap_rows,
+                  int row_floats, int in_stride, void *stream);
 
 /* ---- dense BEV map ----------------------------------------------------------------------------- */
 #define B2S_LAYOUT_NCHW 0 /* out[b, c*D+z, y, x]  (== dense() [B,C,D,H,W] viewed [B,C*D,H,W]) */
@@ -153,22 +170,27 @@ int b2s_merge_hilo(const float *hi, const float *lo, float *x, const int *num_ro
 int b2s_to_bev(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C,
                int batch, int D, int H, int W, float *out, int layout, void *stream);
 
-/* BEV map for the tensor-core RPN: NHWC with a one-pixel zero halo, [B, H+2, W+2, C*D], as two planes
- * hi = tf32-rounded value, lo = value - hi (the 3xTF32 split b2s_conv2d_tc consumes). */
-int b2s_to_bev_tc(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch,
-                  int D, int H, int W, float *out_hi, float *out_lo, void *stream);
+/* BEV map for the tensor-core RPN: NHWC with a one-pixel zero halo, [B, H+2, W+2, C*D], as two fp16 planes
+ * hi = fp16(x), lo = fp16(x - hi) (the 3xF16 split b2s_conv2d_tc consumes).  Rows come as fp32 `feat` [rows, C]
+ * (feat_hi/lo NULL) or already split as feat_hi/feat_lo rows of feat_stride halves (feat NULL). */
+int b2s_to_bev_tc(const float *feat, const b2s_half *feat_hi, const b2s_half *feat_lo, int feat_stride,
+                  const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch, int D, int H, int W,
+                  b2s_half *out_hi, b2s_half *out_lo, void *stream);
 
 /* ---- dense RPN convolution on the tensor pipe (second/pytorch/models/rpn.py:467-497 blocks, :264-299 deblocks,
  *      :386-391 heads): 3x3 stride-1 pad-1 (taps=9) or 1x1 (taps=1) conv + per-channel scale/shift (+ReLU).
- * tcgen05 implicit GEMM, fp32-grade accuracy through the 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi).
- *   in_hi/in_lo  [B, H+2, W+2, Cin]   NHWC + zero halo, hi/lo planes (Cin multiple of 32)
- *   w_hi/w_lo    [taps, n_pad, Cin]   tap = ky*3+kx, w[tap][co][ci] = W_torch[co][ci][ky][kx]; rows >= Cout zero;
- *                                     n_pad in {32, 64, 128}
+ * tcgen05 implicit GEMM (kind::f16), fp32-grade accuracy through the 3xF16 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi,
+ * fp32 accumulation in TMEM, short chains drained with round-to-nearest adds).
+ *   in_hi/in_lo  [B, H+2, W+2, Cin]   NHWC + zero halo, fp16 hi/lo planes (Cin multiple of 64)
+ *   w_hi/w_lo    [taps, n_pad, Cin]   tap = ky*3+kx, w[tap][co][ci] = W_torch[co][ci][ky][kx] * 2^s (s folded into
+ *                                     `scale`); rows >= Cout zero; n_pad in {32, 64, 128}
  *   out_hi       [B, H+2, W+2, out_stride] interior only (out_padded=1) or [B, H, W, out_stride] (out_padded=0);
- *   out_lo       same shape or NULL (then out_hi holds the full fp32 value, e.g. for the heads). */
-int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int batch, int H, int W, int Cin, const float *w_hi,
-                  const float *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
-                  int relu, float *out_hi, float *out_lo, int out_padded, int out_stride, void *stream);
+ *   out_lo       same shape, or NULL: then out_hi is FLOAT and holds the full fp32 value (the heads).
+ *   status_dev   may be NULL; B2S_STATUS_F16_RANGE is raised when an output activation exceeds the fp16 range. */
+int b2s_conv2d_tc(const b2s_half *in_hi, const b2s_half *in_lo, int batch, int H, int W, int Cin, const b2s_half *w_hi,
+                  const b2s_half *w_lo, int taps, int Cout, int n_pad, const float *scale, const float *shift,
+                  int relu, void *out_hi, b2s_half *out_lo, int out_padded, int out_stride, unsigned *status_dev,
+                  void *stream);
 
 /* general form, for the multi-stage RPNs (rpn.py:469-497: stride-2 first conv of a block after ZeroPad2d(1);
  * :264-299 deblocks: ConvTranspose2d(k = s, stride s) for upsample_stride >= 1, Conv2d(k = s, stride s) below 1;
@@ -178,10 +200,11 @@ int b2s_conv2d_tc(const float *in_hi, const float *in_lo, int batch, int H, int 
  *   [kh*kw, n_pad, Cin], and is written to pixel (h*out_mul + off_h, w*out_mul + off_w) of an Hout x Wout map with
  *   out_stride channels per pixel (pass out pointers already advanced to the first output channel).
  *   ConvTranspose2d k = s: s*s calls with kh = kw = 1, Hg = Hin, out_mul = s, (off_h, off_w) = (a, c), W[:, :, a, c]. */
-int b2s_conv2d_tc_ex(const float *in_hi, const float *in_lo, int batch, int Hin, int Win, int Cin, const float *w_hi,
-                     const float *w_lo, int kh, int kw, int stride, int pad, int Cout, int n_pad, const float *scale,
-                     const float *shift, int relu, int Hg, int Wg, float *out_hi, float *out_lo, int Hout, int Wout,
-                     int out_padded, int out_stride, int out_mul, int off_h, int off_w, void *stream);
+int b2s_conv2d_tc_ex(const b2s_half *in_hi, const b2s_half *in_lo, int batch, int Hin, int Win, int Cin,
+                     const b2s_half *w_hi, const b2s_half *w_lo, int kh, int kw, int stride, int pad, int Cout,
+                     int n_pad, const float *scale, const float *shift, int relu, int Hg, int Wg, void *out_hi,
+                     b2s_half *out_lo, int Hout, int Wout, int out_padded, int out_stride, int out_mul, int off_h,
+                     int off_w, unsigned *status_dev, void *stream);
 
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,
@@ -219,22 +242,42 @@ size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max);
  * rotated == 0: stand-up boxes of the rotated boxes, IoU with +1 on width/height, suppress when > thresh.
  * Descending score order, ties -> lower anchor index.  Kept boxes (<= post_max per frame), after the
  * direction fix-up and post_center_range test (range_host NULL = no test), are written to
- *   det [B, post_max, code+2] = (box[code], score, label) and det_count_dev [B]. */
+ *   det: frame b's record starts at det + b*det_frame_stride floats and holds post_max rows of
+ *        (box[code], score, label); det_frame_stride 0 means post_max*(code+2) (dense [B, post_max, code+2]).
+ *        With det_frame_stride > post_max*(code+2) the kept count is ALSO stored as a float in the record's last
+ *        element -- the record is then exactly the multi-GPU all-gather payload, no packing step;
+ *   det_count_dev [B]. */
 int b2s_nms(const float *cand_box, const float *cand_score, const int *cand_label, const int *cand_dir,
             const int *cand_anchor, const int *cand_count_dev, int batch, int cand_cap, int code,
             int rotated, int pre_max, int post_max, float iou_thresh, int use_dir, float dir_offset,
             float dir_limit_offset, int num_dir_bins, const float *range_host /*host[6] or NULL*/,
-            float *det, int *det_count_dev, void *workspace, size_t workspace_bytes, void *stream);
+            float *det, int det_frame_stride, int *det_count_dev, void *workspace, size_t workspace_bytes,
+            void *stream);
 
 /* numpy-facing spconv.utils signatures: HOST arrays in/out, internal H2D/D2H + sync (like upstream's
  * non_max_suppression, which takes a device_id and does its own copies). */
 /* eps=1, inclusive=0: spconv.utils.non_max_suppression ("+1" IoU, suppress if IoU > thresh);
  * eps given, inclusive=1: spconv.utils.non_max_suppression_cpu (suppress if IoU >= thresh). */
+/* device_id < 0: run on the caller's current device.  The caller's current device is restored on return. */
 int b2s_nms_aligned_host(const float *sorted_dets /*host [N,5]*/, int n, float thresh, float eps,
                          int inclusive, int *keep_out /*host [N]*/, int device_id);
 int b2s_nms_rotated_host(const float *corners /*host [N,4,2]*/, const int *order /*host [N]*/,
                          const float *standup_iou /*host [N,N]*/, int n, float thresh,
                          int *keep_out /*host [N]*/, int device_id);
+
+
+/* ---- rotated overlap matrices (eval / target assignment: SURVEY.md §8(f)2) ------------------------ */
+/* criterion -1: IoU, 0: inter/area(box), 1: inter/area(query), 2: intersection area
+ * (devRotateIoUEval, second/core/non_max_suppression/nms_gpu.py:553-566). */
+/* rotate_iou_gpu_eval replacement (nms_gpu.py:569-607), device resident: boxes [N,5], query_boxes [K,5] as
+ * (x, y, w, l, r); out [N,K]; workspace (N+K)*8 floats. */
+int b2s_rotate_iou_eval(const float *boxes, int N, const float *query_boxes, int K, int criterion, float *out,
+                        float *workspace, void *stream);
+/* spconv.utils.rbbox_iou (criterion -1) / rbbox_intersection (criterion 2; interchangeable with
+ * rotate_iou_gpu_eval(..., 2) in second/utils/eval.py:174-175) -- HOST arrays: corners [N,4,2], qcorners [K,4,2],
+ * standup_iou [N,K]; pairs with standup_iou <= standup_thresh give 0 (second/core/box_np_ops.py:10-34). */
+int b2s_rbbox_overlap_host(const float *corners, const float *qcorners, const float *standup_iou, int N, int K,
+                           float standup_thresh, int criterion, float *out /*host [N,K]*/, int device_id);
 
 #ifdef __cplusplus
 }

@@ -259,7 +259,9 @@ int orc_rotate_nms(const float *corners /*[N,4,2]*/, const int *order,
 }
 
 /* spconv.utils.rbbox_iou / rbbox_intersection(corners[N,4,2], qcorners[K,4,2],
- * standup_iou[N,K], standup_thresh) -> [N,K].  mode 0: IoU, mode 1: inter/area(q) */
+ * standup_iou[N,K], standup_thresh) -> [N,K].  mode 0: IoU, mode 1: intersection AREA.
+ * In-tree anchor for mode 1: second/utils/eval.py:174-175 uses rinter_cc (box_np_ops.py:23-34) interchangeably with
+ * rotate_iou_gpu_eval(..., criterion=2), whose device function returns area_inter (nms_gpu.py:553-566). */
 void orc_rbbox_iou(const float *corners, const float *qcorners,
                    const float *standup_iou, int N, int K, float standup_thresh,
                    int mode, float *out)
@@ -272,7 +274,7 @@ void orc_rbbox_iou(const float *corners, const float *qcorners,
                 double inter = orc_quad_intersection(corners + 8 * n,
                                                      qcorners + 8 * k, &sa, &sb);
                 if (mode == 0) r = (float)(inter / (sa + sb - inter));
-                else r = (float)(inter / sb);
+                else r = (float)inter;
             }
             out[(size_t)n * K + k] = r;
         }

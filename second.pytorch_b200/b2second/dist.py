@@ -46,6 +46,20 @@ class DetectionGatherer:
         self.send = torch.zeros(batch_per_rank, width, dtype=torch.float32, device=device)
         self.recv = torch.zeros(self.world * batch_per_rank, width, dtype=torch.float32, device=device)
 
+    def gather_records(self, records):
+        """records [B, post_max*S + 1]: the engine's ``det_record`` buffer (the NMS epilogue writes the detections AND
+        the count straight into it, so there is no packing step) -> same return value as ``gather``.  The buffer is
+        the collective's send buffer itself."""
+        assert records.shape == self.send.shape and records.is_contiguous()
+        if self.world == 1:
+            self.recv.copy_(records)
+        elif hasattr(dist, "all_gather_into_tensor") and records.is_cuda:
+            dist.all_gather_into_tensor(self.recv, records, group=self.group)
+        else:
+            parts = list(self.recv.view(self.world, self.B, -1).unbind(0))
+            dist.all_gather(parts, records, group=self.group)
+        return unpack_records(self.recv, self.post_max, self.stride)
+
     def gather(self, det, count):
         """-> (det_all [W*B, post_max, S], count_all [W*B]) in global frame order, on every rank."""
         self.send.copy_(pack_records(det, count))

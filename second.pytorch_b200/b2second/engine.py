@@ -1,32 +1,38 @@
 """Fused device pipeline for ``VoxelNet`` inference: points in HBM -> detections in HBM, no host sync.
 
-This is the fast path behind the ``VoxelNet.forward(example)`` contract ("a fast path may
-additionally accept example['points']").  Where the module-by-module path (``models.VoxelNet`` on the
-``spconv`` drop-in) mirrors the reference call by call -- one rulebook sync per strided conv, a
-D2H -> CPU NMS -> H2D round trip per frame (second/pytorch/core/box_torch_ops.py:503,512) -- the engine
-keeps every data-dependent count in device memory and runs a fixed launch sequence over
-capacity-sized buffers, so the whole frame batch is ONE CUDA graph:
+This is the fast path behind the ``VoxelNet.forward(example)`` contract (reached through
+``b2second.fastpath.accelerate(net)`` for a reference-built network and through ``models.VoxelNet.forward`` for
+the mirror).  Where the module-by-module path mirrors the reference call by call -- one rulebook sync per
+strided conv, a D2H -> CPU NMS -> H2D round trip per frame (second/pytorch/core/box_torch_ops.py:503,512) -- the
+engine keeps every data-dependent count in device memory and runs a fixed launch sequence over capacity-sized
+buffers, so the whole frame batch is ONE CUDA graph:
 
   b2s_voxelize (+ fused SimpleVoxel mean)                     voxelnet.py:325-328, preprocess.py:303-315
-  per sparse layer: b2s_rulebook_{subm,conv} (cached per indice_key) + b2s_sparse_conv_tc (tcgen05, hi/lo
+     or, for an example that arrives already voxelised (the reference's own dict):
+     b2s_hash_build + b2s_vfe_mean over the caller's voxels   voxel_encoder.py:220-225,246-255
+  per sparse layer: b2s_rulebook_{subm,conv} (cached per indice_key) + b2s_sparse_conv_tc (tcgen05, fp16 hi/lo
       planes flow from layer to layer) with BatchNorm1d/ReLU folded into the epilogue      middle.py:145-192
   b2s_pfn (PointPillars)                                       pointpillars.py:203-237
-  b2s_to_bev_tc (NHWC + halo, hi/lo)                           middle.py:206-209 / pointpillars.py:444-476
+  b2s_to_bev_tc (NHWC + halo, fp16 hi/lo)                      middle.py:206-209 / pointpillars.py:444-476
   RPN as a program of b2s_conv2d_tc_ex launches (tc.plan_rpn)  rpn.py:314-331,393-420,467-497
       (rpn_impl="cudnn" keeps the torch modules as a cross-check: fp32, TF32 off)
   b2s_decode_filter_strided + b2s_nms (+ direction/range epilogue)   voxelnet.py:377-645
 
+The network is read through ``b2second.spec.spec_from_module`` (attribute names of the reference), never through
+``b2second.models`` classes or a ``ModelConfig``.
+
 Output per batch: ``det [B, post_max, code+2]`` (box, score, label) + ``det_count [B]`` -- the fixed-stride
-record the multi-GPU path all-gathers.
+record the multi-GPU path all-gathers; ``det`` and ``det_count`` live in ONE buffer
+(``det_record [B, post_max*(code+2) + 1]``) so the all-gather needs no packing step.
 """
 import ctypes
 import os
 
 import numpy as np
 import torch
-from torch import nn
 
-from . import models
+from . import spec as _spec
+from . import tc as _tc
 
 
 def _pow2_at_least(n):
@@ -34,12 +40,6 @@ def _pow2_at_least(n):
     while c < n:
         c <<= 1
     return c
-
-
-def _fold_bn(bn):
-    scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float().contiguous()
-    shift = (bn.bias - bn.running_mean * scale).detach().float().contiguous()
-    return scale, shift
 
 
 def ctypes_ptr(addr):
@@ -53,52 +53,55 @@ class _Level:
 
 class InferenceEngine:
     def __init__(self, net, batch_size=1, max_points=None, max_voxels=None, row_cap_factor=2.0,
-                 cand_cap=None, use_cuda_graph=True, rpn_impl="auto", sparse_impl="tc"):
+                 cand_cap=None, use_cuda_graph=True, rpn_impl="auto", sparse_impl="tc", device=None):
         import spconv as sp                      # the CUDA drop-in: fails loudly if the library is missing
         assert not getattr(sp, "__oracle__", False), "the engine is the product path; it never runs on the oracle"
         self.sp = sp
         self.lib = sp._lib.load()
         self._L = sp._lib
-        self.net = net.eval()
-        self.cfg = cfg = net.cfg
+        self.spec = s = net if isinstance(net, _spec.NetSpec) else _spec.spec_from_module(net, max_voxels)
+        if max_voxels:
+            s.max_voxels = int(max_voxels)
+        if s.multiclass_nms:
+            raise _spec.UnsupportedNetwork("per-class NMS branch (voxelnet.py:458-547) is not on the fused path yet")
         self.B = int(batch_size)
-        dev = next(net.parameters()).device
+        dev = torch.device(device) if device is not None else s.device
         assert dev.type == "cuda", "InferenceEngine needs the network on a CUDA device"
         self.dev = dev
         # parity bar is fp32: keep cuDNN/cuBLAS off TF32 (torch allows TF32 convs by default)
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.benchmark = True
-        self.F = cfg.num_point_features
-        self.T = cfg.max_points_per_voxel
-        self.max_voxels = int(max_voxels or cfg.max_voxels)
+        self.F = s.num_point_features
+        self.T = s.max_points_per_voxel
+        self.max_voxels = s.max_voxels
         self.P_cap = int(max_points or 40000) * self.B
-        self.grid = cfg.grid_size
-        self.code = cfg.box_code_size
+        self.grid = s.grid_size
+        self.code = s.box_code_size
         self.use_graph = use_cuda_graph
-        self._graph = None
-        # RPN: "tc" = hand-written tcgen05 implicit GEMM (csrc/conv_tc.cu, 3xTF32), "cudnn" = torch/cuDNN fp32.
-        from . import tc as _tc
+        self._graphs = {}
+        # RPN: "tc" = hand-written tcgen05 implicit GEMM (csrc/conv_tc.cu, 3xF16), "cudnn" = torch/cuDNN fp32.
         if rpn_impl == "auto":
-            rpn_impl = "tc" if _tc.supported(net.rpn) else "cudnn"
+            rpn_impl = "tc" if _tc.supported(s.rpn) else "cudnn"
         assert rpn_impl in ("tc", "cudnn")
-        if rpn_impl == "tc" and not _tc.supported(net.rpn):
-            raise ValueError("rpn_impl='tc': this RPN has a layer b2s_conv2d_tc_ex does not cover (channels % 32, kernel > 4)")
+        if rpn_impl == "tc" and not _tc.supported(s.rpn):
+            raise ValueError("rpn_impl='tc': this RPN has a layer b2s_conv2d_tc_ex does not cover (channels % 64, kernel > 4)")
         self.rpn_impl = rpn_impl
-        assert sparse_impl in ("tc", "fma")       # sparse-conv inner product: tcgen05 3xTF32 | fp32 FMA tiles
+        assert sparse_impl in ("tc", "fma")       # sparse-conv inner product: tcgen05 3xF16 | fp32 FMA tiles
         self.sparse_impl = sparse_impl
-        self._plan_middle(row_cap_factor)
-        self._alloc_voxel_buffers()
-        if rpn_impl == "tc":
-            self._alloc_tc_rpn(_tc)
-        self._alloc_detect_buffers(cand_cap)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._plan_middle(row_cap_factor)
+            self._alloc_voxel_buffers()
+            if rpn_impl == "tc":
+                self._alloc_tc_rpn()
+            self._alloc_detect_buffers(cand_cap)
 
     # ---------------------------------------------------------------- planning / allocation
     def _new_level(self, cap, shape, with_storage=True):
         lv = _Level()
         lv.cap = int(cap)
-        lv.shape = [int(s) for s in shape]
+        lv.shape = [int(x) for x in shape]
         lv.hcap = _pow2_at_least(2 * lv.cap)
         if with_storage:
             lv.coors = torch.zeros(lv.cap, 4, dtype=torch.int32, device=self.dev)
@@ -107,74 +110,70 @@ class InferenceEngine:
             lv.vals = torch.empty(lv.hcap, dtype=torch.int32, device=self.dev)
         return lv
 
+    def _hilo_rows(self, cap, c):
+        """interleaved fp16 rows [cap][hi c | lo c] -> (buffer, hi view, lo view, row stride in halves)."""
+        buf = torch.zeros(cap, 2, c, dtype=torch.float16, device=self.dev)
+        return buf, buf[:, 0], buf[:, 1], 2 * c
+
     def _plan_middle(self, row_cap_factor):
-        cfg, sp = self.cfg, self.sp
-        mid = self.net.middle_feature_extractor
-        self.is_pillars = isinstance(mid, models.PointPillarsScatter)
+        s, sp, dev = self.spec, self.sp, self.dev
+        self.is_pillars = s.is_pillars
         self.layers = []
         self.rb_ws = None
         cap0 = self.B * self.max_voxels
         if self.is_pillars:
-            self.level0 = self._new_level(cap0, [1, int(self.grid[1]), int(self.grid[0])], with_storage=False)
-            pfn = self.net.voxel_feature_extractor
-            assert len(pfn.pfn_layers) == 1, "engine: single-layer PillarFeatureNet only (all BASELINE configs)"
-            lyr = pfn.pfn_layers[0]
-            self.pfn_w = lyr.linear.weight.detach().float().contiguous()
-            self.pfn_scale, self.pfn_shift = _fold_bn(lyr.norm)
-            self.pfn_cout = lyr.units
-            self.pfn_geom = (float(pfn.vx), float(pfn.vy), float(pfn.x_offset), float(pfn.y_offset))
+            self.level0 = self._new_level(cap0, s.sparse_shape, with_storage=False)
+            p = s.pfn
+            self.pfn_w = p["w"].to(dev)
+            self.pfn_scale, self.pfn_shift = p["scale"].to(dev), p["shift"].to(dev)
+            self.pfn_cout = p["cout"]
+            if p["with_distance"]:
+                raise _spec.UnsupportedNetwork("PillarFeatureNet with_distance (off in every BASELINE config)")
+            self.pfn_geom = (p["vx"], p["vy"], p["x_offset"], p["y_offset"])
             self.feat_final_c = self.pfn_cout
             self.final_level = self.level0
-            self.pfn_out = torch.zeros(cap0, self.pfn_cout, dtype=torch.float32, device=self.dev)
+            self.pfn_out = torch.zeros(cap0, self.pfn_cout, dtype=torch.float32, device=dev)
             return
-        shape0 = [int(s) for s in mid.sparse_shape]
-        self.level0 = self._new_level(cap0, shape0, with_storage=False)   # storage = voxelizer outputs
-        mods = list(mid.middle_conv._modules.values())
+        self.level0 = self._new_level(cap0, s.sparse_shape, with_storage=False)   # storage = voxelizer outputs
         level = self.level0
         rulebooks = {}
-        i = 0
         max_ws = 0
-        while i < len(mods):
-            m = mods[i]
-            assert isinstance(m, sp.SparseConvolution), "engine: expected (conv, BN, ReLU) triples"
-            bn = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm1d) else None
-            relu = bn is not None and i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
-            K = int(np.prod(m.kernel_size))
-            lyr = {"index": len(self.layers), "conv": m, "K": K, "cin": m.in_channels, "cout": m.out_channels, "relu": relu,
-                   "w": m.weight.detach().float().contiguous().view(K, m.in_channels, m.out_channels)}
-            if bn is not None:
-                lyr["scale"], lyr["shift"] = _fold_bn(bn)
-            else:
-                lyr["scale"], lyr["shift"] = None, (m.bias.detach().float().contiguous() if m.bias is not None else None)
-            if m.subm:
-                key = ("subm", m.indice_key, id(level)) if m.indice_key is not None else ("subm", id(m))
+        thin_ok = os.environ.get("B2S_THIN_TC", "1") != "0"      # A/B switch: thin layers on the FMA core
+        for j, ls in enumerate(s.layers):
+            K = ls["K"]
+            lyr = dict(ls)
+            lyr["index"] = j
+            lyr["w"] = ls["w"].to(dev)
+            lyr["scale"] = None if ls["scale"] is None else ls["scale"].to(dev)
+            lyr["shift"] = None if ls["shift"] is None else ls["shift"].to(dev)
+            if ls["subm"]:
+                key = ("subm", ls["indice_key"], id(level)) if ls["indice_key"] is not None else ("subm", j)
                 if key not in rulebooks:
-                    rulebooks[key] = {"nbr": torch.empty(level.cap, K, dtype=torch.int32, device=self.dev),
-                                      "build": ("subm", level, m)}
+                    rulebooks[key] = {"nbr": torch.empty(level.cap, K, dtype=torch.int32, device=dev)}
                     lyr["build_rb"] = True
                 else:
                     lyr["build_rb"] = False
                 lyr["rb"] = rulebooks[key]
                 lyr["in_level"], lyr["out_level"] = level, level
             else:
-                out_shape = sp.ops.get_conv_output_size(level.shape, m.kernel_size, m.stride, m.padding, m.dilation)
+                out_shape = sp.ops.get_conv_output_size(level.shape, ls["kernel_size"], ls["stride"], ls["padding"],
+                                                        ls["dilation"])
                 cells = int(np.prod(out_shape))
-                fan = int(np.prod([-(-k // s) for k, s in zip(m.kernel_size, m.stride)]))
+                fan = int(np.prod([-(-k // st) for k, st in zip(ls["kernel_size"], ls["stride"])]))
                 per_frame = min(cells, int(self.max_voxels * row_cap_factor), level.cap // self.B * fan)
                 new = self._new_level(self.B * per_frame, out_shape)
-                rb = {"nbr": torch.empty(new.cap, K, dtype=torch.int32, device=self.dev), "build": ("conv", level, m)}
-                lyr["rb"], lyr["build_rb"] = rb, True
+                lyr["rb"] = {"nbr": torch.empty(new.cap, K, dtype=torch.int32, device=dev)}
+                lyr["build_rb"] = True
                 lyr["in_level"], lyr["out_level"] = level, new
                 max_ws = max(max_ws, self.lib.b2s_rulebook_conv_workspace_bytes(self.B, self._L.i3(out_shape)))
                 level = new
-            lyr["out"] = torch.zeros(lyr["out_level"].cap, m.out_channels, dtype=torch.float32, device=self.dev)
-            # tensor-pipe core (csrc/sparse_conv_tc.cu); thin layers (Cin 4/16) pack 8/2 kernel offsets per K block.
-            # Other widths (e.g. 3 input features) stay on the fp32 FMA core.
-            thin_ok = os.environ.get("B2S_THIN_TC", "1") != "0"      # A/B switch: thin layers on the FMA core
-            lyr["tc"] = (self.sparse_impl == "tc" and m.in_channels in ((4, 16, 32, 64) if thin_ok else (32, 64))
-                         and m.out_channels in (16, 32, 64) and K <= 27)
+            # tensor-pipe core (csrc/sparse_conv_tc.cu): the library says which (Cin, Cout) it was built for;
+            # 3-/4-feature input layers are zero-padded to 8 channels.  Everything else: fp32 FMA core.
+            cin_tc = _tc.sparse_tc_cin(ls["cin"])
+            lyr["cin_tc"] = cin_tc
+            lyr["tc"] = bool(self.sparse_impl == "tc" and cin_tc is not None and (thin_ok or cin_tc >= 32) and
+                             self.lib.b2s_sparse_conv_tc_supported(cin_tc, ls["cout"]))
             self.layers.append(lyr)
-            i += 1 + (1 if bn is not None else 0) + (1 if relu else 0)
         # once a layer runs on the tensor pipe all later ones must too (hi/lo planes flow forward)
         seen_tc = False
         for lyr in self.layers:
@@ -183,26 +182,28 @@ class InferenceEngine:
                     l2["tc"] = False
                 break
             seen_tc = seen_tc or lyr["tc"]
-        from . import tc as _tc
         for j, lyr in enumerate(self.layers):
+            cap = lyr["out_level"].cap
             if lyr["tc"]:
-                lyr["w_hi"], lyr["w_lo"] = _tc.split_tf32(_tc.pack_sparse_weights(lyr["w"]))
-                lyr["out_lo"] = torch.zeros_like(lyr["out"])
+                wp = _tc.pack_sparse_weights(lyr["w"])
+                ws = _tc.pow2_scale(wp)
+                lyr["w_hi"], lyr["w_lo"] = _tc.split_f16(wp, ws)
+                base = lyr["scale"] if lyr["scale"] is not None else torch.ones(lyr["cout"], device=dev)
+                lyr["scale_tc"] = (base.float() / ws).contiguous()
+                lyr["out_buf"], lyr["out_hi"], lyr["out_lo"], lyr["out_stride"] = self._hilo_rows(cap, lyr["cout"])
                 if j == 0 or not self.layers[j - 1]["tc"]:
-                    # first tensor-pipe layer: its fp32 input rows are split into hi/lo planes first
-                    lyr["in_split"] = (torch.zeros(lyr["in_level"].cap, lyr["cin"], dtype=torch.float32, device=self.dev),
-                                       torch.zeros(lyr["in_level"].cap, lyr["cin"], dtype=torch.float32, device=self.dev))
+                    # first tensor-pipe layer: its fp32 input rows are split into fp16 hi/lo planes first
+                    lyr["in_split"] = self._hilo_rows(lyr["in_level"].cap, lyr["cin_tc"])
+            else:
+                lyr["out"] = torch.zeros(cap, lyr["cout"], dtype=torch.float32, device=dev)
         self.any_sparse_tc = any(l["tc"] for l in self.layers)
-        if self.any_sparse_tc:
-            last = self.layers[-1]
-            self.merged_out = torch.zeros_like(last["out"])
-        self.rb_ws = torch.empty(max(max_ws, 1), dtype=torch.uint8, device=self.dev)
+        self.rb_ws = torch.empty(max(max_ws, 1), dtype=torch.uint8, device=dev)
         self.rb_ws_bytes = max_ws
         self.final_level = level
         self.feat_final_c = self.layers[-1]["cout"]
 
     def _alloc_voxel_buffers(self):
-        lib, dev = self.lib, self.dev
+        lib, dev, s = self.lib, self.dev, self.spec
         cap = self.B * self.max_voxels
         self.points = torch.zeros(self.P_cap, self.F, dtype=torch.float32, device=dev)
         self.offsets = torch.zeros(self.B + 1, dtype=torch.int32, device=dev)
@@ -215,11 +216,10 @@ class InferenceEngine:
         self.vox_vals = torch.empty(self.vox_hcap, dtype=torch.int32, device=dev)
         self.vox_ws_bytes = lib.b2s_voxelize_workspace_bytes(self.P_cap, self.B, self.max_voxels, self.T)
         self.vox_ws = torch.empty(max(self.vox_ws_bytes, 1), dtype=torch.uint8, device=dev)
-        vfe = self.net.voxel_feature_extractor
-        if isinstance(vfe, models.SimpleVoxel):
-            self.vfe_mode, self.vfe_nf, c = 1, vfe.num_input_features, vfe.num_input_features
-        elif isinstance(vfe, models.SimpleVoxelRadius):
-            self.vfe_mode, self.vfe_nf, c = 2, vfe.num_input_features, vfe.num_input_features - 1
+        if s.vfe_kind == "mean":
+            self.vfe_mode, self.vfe_nf, c = 1, s.vfe_num_features, s.vfe_num_features
+        elif s.vfe_kind == "mean_radius":
+            self.vfe_mode, self.vfe_nf, c = 2, s.vfe_num_features, s.vfe_num_features - 1
         else:
             self.vfe_mode, self.vfe_nf, c = 0, self.F, 0
         self.vfe_out = torch.zeros(cap, c, dtype=torch.float32, device=dev) if c else None
@@ -229,41 +229,77 @@ class InferenceEngine:
                                                          self.vox_vals, self.vox_hcap)
         C = self.feat_final_c
         D, H, W = self.final_level.shape
-        self.bev = torch.zeros(self.B, C * D, H, W, dtype=torch.float32, device=dev)
+        self.bev_cd = C * D
+        if self.spec.bev_channels is None:
+            self.spec.bev_channels = C * D
+        if self.rpn_impl == "cudnn":
+            self.bev = torch.zeros(self.B, C * D, H, W, dtype=torch.float32, device=dev)
+        # pre-voxelised entry (the reference's own example dict): the caller's voxels land here
+        self.in_voxels = None
 
-    def _alloc_tc_rpn(self, _tc):
-        """buffers of the tensor-core RPN: NHWC halo-padded hi/lo planes (halo zero-filled once, never written)."""
+    def _alloc_tc_rpn(self):
+        """buffers of the tensor-core RPN: NHWC halo-padded fp16 hi/lo planes (halo zero-filled once, never written)."""
         dev, B = self.dev, self.B
         D, H, W = self.final_level.shape
         C = self.feat_final_c * D
-        plan = _tc.plan_rpn(self.net.rpn, H, W)
+        rpn = self.spec.rpn
+        if next(rpn.parameters()).device != dev:
+            raise ValueError("the RPN's parameters must live on the engine's device")
+        plan = _tc.plan_rpn(rpn, H, W)
         self.tc_prog = plan
         self.tc_plan = plan["ops"]
         assert plan["in_channels"] == C, "BEV channels %d != RPN input %d" % (C, plan["in_channels"])
 
         def plane(h, w, c):
-            return (torch.zeros(B, h + 2, w + 2, c, dtype=torch.float32, device=dev),
-                    torch.zeros(B, h + 2, w + 2, c, dtype=torch.float32, device=dev))
+            return (torch.zeros(B, h + 2, w + 2, c, dtype=torch.float16, device=dev),
+                    torch.zeros(B, h + 2, w + 2, c, dtype=torch.float16, device=dev))
         self.tc_bev = plane(H, W, C)
         self.tc_bufs = {"in": self.tc_bev}
         for name, (h, w, c) in plan["buffers"].items():
             self.tc_bufs[name] = plane(h, w, c)
         hd = plan["heads"]
         self.tc_head_stride = hd["stride"]
-        _, fH, fW = self.cfg.feature_map_size
-        assert (hd["H"], hd["W"]) == (fH, fW), "RPN output %dx%d != anchor grid %dx%d" % (hd["H"], hd["W"], fH, fW)
         self.tc_heads = torch.zeros(B, hd["H"], hd["W"], self.tc_head_stride, dtype=torch.float32, device=dev)
         self.tc_bufs["heads"] = (self.tc_heads, None)
         self.tc_hw = (H, W)
 
+    def _feature_hw(self):
+        if self.rpn_impl == "tc":
+            return self.tc_prog["heads"]["H"], self.tc_prog["heads"]["W"]
+        D, H, W = self.final_level.shape
+        with torch.no_grad():
+            y = self.spec.rpn.conv_box(self._rpn_backbone(torch.zeros(1, self.bev_cd, H, W, device=self.dev)))
+        return int(y.shape[2]), int(y.shape[3])
+
+    def _rpn_backbone(self, x):
+        """RPNNoHeadBase.forward (rpn.py:314-331) on the torch modules: cuDNN cross-check path only."""
+        rpn = self.spec.rpn
+        ups = []
+        for i in range(len(rpn.blocks)):
+            x = rpn.blocks[i](x)
+            if i - rpn._upsample_start_idx >= 0:
+                ups.append(rpn.deblocks[i - rpn._upsample_start_idx](x))
+        if len(ups) > 0:
+            x = torch.cat(ups, dim=1)
+        return x
+
     def _alloc_detect_buffers(self, cand_cap):
-        cfg, dev = self.cfg, self.dev
-        anchors = torch.from_numpy(self.net.anchors()).to(dev)
-        self.anchors = anchors.contiguous()
-        self.A = anchors.shape[0]
-        self.a_loc = cfg.num_anchors_per_loc
-        _, self.fH, self.fW = cfg.feature_map_size
-        assert self.a_loc * self.fH * self.fW == self.A
+        s, dev = self.spec, self.dev
+        self.fH, self.fW = self._feature_hw()
+        self.a_loc = s.num_anchors_per_loc
+        self.A = self.a_loc * self.fH * self.fW
+        self.anchors = torch.zeros(self.A, self.code, dtype=torch.float32, device=dev)
+        self._anchors_key = None
+        try:
+            a = _spec.anchors_for(s, (self.fH, self.fW))
+        except Exception:
+            a = None                                  # anchors then come with the first example (set_anchors)
+        if a is not None:
+            assert a.shape[0] == self.A, "anchor count %d != RPN output %d" % (a.shape[0], self.A)
+            self.anchors.copy_(torch.from_numpy(a))
+            self._anchors_key = "generated"
+        self.anchors_mask = None                      # [B, A] uint8, allocated on first use
+        self.use_mask = False
         self.cand_cap = int(cand_cap or min(self.A, 32768))
         B, cc, code = self.B, self.cand_cap, self.code
         self.cand_box = torch.zeros(B, cc, code, dtype=torch.float32, device=dev)
@@ -272,117 +308,140 @@ class InferenceEngine:
         self.cand_dir = torch.zeros(B, cc, dtype=torch.int32, device=dev)
         self.cand_anchor = torch.zeros(B, cc, dtype=torch.int32, device=dev)
         self.cand_count = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.pre_max, self.post_max = cfg.nms_pre_max_size, cfg.nms_post_max_size
+        self.score_thresh = float(s.nms_score_thresholds[0])
+        self.pre_max, self.post_max = int(s.nms_pre_max_sizes[0]), int(s.nms_post_max_sizes[0])
+        self.iou_thresh = float(s.nms_iou_thresholds[0])
         self.nms_ws_bytes = self.lib.b2s_nms_workspace_bytes(B, cc, self.pre_max)
         self.nms_ws = torch.empty(max(self.nms_ws_bytes, 1), dtype=torch.uint8, device=dev)
-        self.det = torch.zeros(B, self.post_max, code + 2, dtype=torch.float32, device=dev)
+        # one record per frame: post_max*(code+2) detection floats followed by the count (as a float: < 2^24) --
+        # exactly the all-gather payload (b2second/dist.py), written in place by the NMS epilogue
+        self.rec_width = self.post_max * (code + 2) + 1
+        self.det_record = torch.zeros(B, self.rec_width, dtype=torch.float32, device=dev)
         self.det_count = torch.zeros(B, dtype=torch.int32, device=dev)
-        rng = cfg.post_center_limit_range
+        rng = s.post_center_range
         self.range_host = self._L.f6(rng) if len(rng) == 6 else None
 
+    @property
+    def det(self):
+        """[B, post_max, code+2] view of the detection records."""
+        return self.det_record[:, :self.rec_width - 1].view(self.B, self.post_max, self.code + 2)
+
     # ---------------------------------------------------------------- the launch sequence
-    def _launch(self):
-        L, lib, cfg = self._L, self.lib, self.cfg
+    def _launch(self, mode="points"):
+        L, lib, s = self._L, self.lib, self.spec
         st = L.stream()
         self.status.zero_()
-        self._mark("voxelize")
-        L.check(lib.b2s_voxelize(
-            L.ptr(self.points), L.ptr(self.offsets), self.P_cap_used, self.F, self.B,
-            L.f3(cfg.point_cloud_range[:3]), L.f3(cfg.voxel_size), L.i3(self.grid), self.T, self.max_voxels,
-            L.ptr(self.vox_coors), L.ptr(self.vox_num), L.ptr(self.vox_slots), None, self.vfe_mode, self.vfe_nf,
-            L.ptr(self.vfe_out), L.ptr(self.num_voxels), L.ptr(self.vox_keys), L.ptr(self.vox_vals), self.vox_hcap,
-            int(self.level0.shape[0]),       # hash keys in the middle encoder's shape (grid_z + 1, middle.py:139)
-            L.ptr(self.vox_ws), self.vox_ws_bytes, L.ptr(self.status), st), "b2s_voxelize")
+        if mode == "points":
+            self._mark("voxelize")
+            L.check(lib.b2s_voxelize(
+                L.ptr(self.points), L.ptr(self.offsets), self.P_cap, self.F, self.B,
+                L.f3(s.point_cloud_range[:3]), L.f3(s.voxel_size), L.i3(self.grid), self.T, self.max_voxels,
+                L.ptr(self.vox_coors), L.ptr(self.vox_num), L.ptr(self.vox_slots), None, self.vfe_mode, self.vfe_nf,
+                L.ptr(self.vfe_out), L.ptr(self.num_voxels), L.ptr(self.vox_keys), L.ptr(self.vox_vals), self.vox_hcap,
+                int(self.level0.shape[0]),       # hash keys in the middle encoder's shape (grid_z + 1, middle.py:139)
+                L.ptr(self.vox_ws), self.vox_ws_bytes, L.ptr(self.status), st), "b2s_voxelize")
+            pfn_points, pfn_slots = self.points, self.vox_slots
+        else:
+            # the caller's voxels / num_points / coordinates are already in in_voxels / vox_num / vox_coors and
+            # num_voxels[0] holds their count: build level 0's locator and the voxel features from them
+            self._mark("voxelize")
+            lv = self.level0
+            if not self.is_pillars:
+                L.check(lib.b2s_hash_build(L.ptr(lv.coors), L.ptr(lv.n_dev), lv.cap, L.i3(lv.shape), L.ptr(lv.keys),
+                                           L.ptr(lv.vals), lv.hcap, L.ptr(self.status), st), "b2s_hash_build")
+                L.check(lib.b2s_vfe_mean(L.ptr(self.in_voxels), L.ptr(self.vox_num), L.ptr(lv.n_dev), lv.cap, self.T,
+                                         self.F, self.vfe_mode, self.vfe_nf, L.ptr(self.vfe_out), st), "b2s_vfe_mean")
+            pfn_points, pfn_slots = self.in_voxels, self.in_slots
         if self.is_pillars:
             vx, vy, xo, yo = self.pfn_geom
             self._mark("pfn")
-            L.check(lib.b2s_pfn(L.ptr(self.points), self.F, L.ptr(self.vox_slots), L.ptr(self.vox_num),
+            L.check(lib.b2s_pfn(L.ptr(pfn_points), self.F, L.ptr(pfn_slots), L.ptr(self.vox_num),
                                 L.ptr(self.vox_coors), L.ptr(self.num_voxels), self.level0.cap, self.T,
                                 L.ptr(self.pfn_w), L.ptr(self.pfn_scale), L.ptr(self.pfn_shift), self.pfn_cout,
                                 vx, vy, xo, yo, L.ptr(self.pfn_out), st), "b2s_pfn")
-            feats = self.pfn_out
+            feats, hilo = self.pfn_out, None
         else:
-            feats, feats_lo = self.vfe_out, None
+            feats, hilo = self.vfe_out, None          # hilo = (hi, lo, stride) once on the tensor pipe
             for lyr in self.layers:
-                m, lin, lout = lyr["conv"], lyr["in_level"], lyr["out_level"]
+                lin, lout = lyr["in_level"], lyr["out_level"]
                 if lyr["build_rb"]:
                     self._mark("rulebook%d" % lyr["index"])
-                    if m.subm:
+                    if lyr["subm"]:
                         L.check(lib.b2s_rulebook_subm(L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, L.i3(lin.shape),
-                                                      L.i3(m.kernel_size), L.i3(m.dilation), L.ptr(lin.keys),
+                                                      L.i3(lyr["kernel_size"]), L.i3(lyr["dilation"]), L.ptr(lin.keys),
                                                       L.ptr(lin.vals), lin.hcap, L.ptr(lyr["rb"]["nbr"]), st),
                                 "b2s_rulebook_subm")
                     else:
                         L.check(lib.b2s_rulebook_conv(
                             L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, self.B, L.i3(lin.shape), L.i3(lout.shape),
-                            L.i3(m.kernel_size), L.i3(m.stride), L.i3(m.padding), L.i3(m.dilation), L.ptr(lin.keys),
-                            L.ptr(lin.vals), lin.hcap, L.ptr(lout.coors), L.ptr(lout.n_dev), lout.cap,
+                            L.i3(lyr["kernel_size"]), L.i3(lyr["stride"]), L.i3(lyr["padding"]), L.i3(lyr["dilation"]),
+                            L.ptr(lin.keys), L.ptr(lin.vals), lin.hcap, L.ptr(lout.coors), L.ptr(lout.n_dev), lout.cap,
                             L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys), L.ptr(lout.vals), lout.hcap,
                             L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
                 self._mark("sparse_conv%d" % lyr["index"])
                 if lyr["tc"]:
                     if "in_split" in lyr:
-                        hi, lo = lyr["in_split"]
-                        L.check(lib.b2s_split_tf32(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
-                                                   lyr["cin"], st), "b2s_split_tf32")
-                        feats, feats_lo = hi, lo
-                    L.check(lib.b2s_sparse_conv_tc(L.ptr(feats), L.ptr(feats_lo), lin.cap, lyr["cin"], L.ptr(lyr["w_hi"]),
-                                                   L.ptr(lyr["w_lo"]), L.ptr(lyr["rb"]["nbr"]), lyr["K"],
-                                                   L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
-                                                   L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
-                                                   L.ptr(lyr["out_lo"]), lyr["cout"], st), "b2s_sparse_conv_tc")
-                    feats, feats_lo = lyr["out"], lyr["out_lo"]
+                        _, hi, lo, stride = lyr["in_split"]
+                        L.check(lib.b2s_split_f16(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
+                                                  lyr["cin"], stride, st), "b2s_split_f16")
+                        hilo = (hi, lo, stride)
+                    L.check(lib.b2s_sparse_conv_tc(
+                        L.ptr(hilo[0]), L.ptr(hilo[1]), hilo[2], lin.cap, lyr["cin_tc"], L.ptr(lyr["w_hi"]),
+                        L.ptr(lyr["w_lo"]), L.ptr(lyr["rb"]["nbr"]), lyr["K"], L.ptr(lout.n_dev), lout.cap,
+                        L.ptr(lyr["scale_tc"]), L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out_hi"]),
+                        L.ptr(lyr["out_lo"]), lyr["out_stride"], lyr["cout"], L.ptr(self.status), st),
+                        "b2s_sparse_conv_tc")
+                    feats, hilo = None, (lyr["out_hi"], lyr["out_lo"], lyr["out_stride"])
                 else:
                     L.check(lib.b2s_sparse_conv(L.ptr(feats), lyr["cin"], L.ptr(lyr["w"]), L.ptr(lyr["rb"]["nbr"]),
                                                 lyr["K"], L.ptr(lout.n_dev), lout.cap, L.ptr(lyr["scale"]),
                                                 L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out"]),
                                                 lyr["cout"], st), "b2s_sparse_conv")
-                    feats, feats_lo = lyr["out"], None
-            if feats_lo is not None:      # back to plain fp32 rows for the BEV scatter (hi + lo is exact)
-                lout = self.layers[-1]["out_level"]
-                L.check(lib.b2s_merge_hilo(L.ptr(feats), L.ptr(feats_lo), L.ptr(self.merged_out), L.ptr(lout.n_dev),
-                                           lout.cap, self.layers[-1]["cout"], st), "b2s_merge_hilo")
-                feats = self.merged_out
+                    feats, hilo = lyr["out"], None
+        if self.rpn_impl == "tc":
+            self._launch_tc_tail(feats, hilo)
+            return
         fl = self.final_level
         D, H, W = fl.shape
-        if self.rpn_impl == "tc":
-            self._launch_tc_tail(feats)
-            return
+        if hilo is not None:          # back to plain fp32 rows for the NCHW scatter (hi + lo is exact)
+            if getattr(self, "merged_out", None) is None:
+                self.merged_out = torch.zeros(fl.cap, self.feat_final_c, dtype=torch.float32, device=self.dev)
+            L.check(lib.b2s_merge_f16(L.ptr(hilo[0]), L.ptr(hilo[1]), L.ptr(self.merged_out), L.ptr(fl.n_dev),
+                                      fl.cap, self.feat_final_c, hilo[2], st), "b2s_merge_f16")
+            feats = self.merged_out
         self._mark("to_bev")
         L.check(lib.b2s_to_bev(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
                                D, H, W, L.ptr(self.bev), 0, st), "b2s_to_bev")
         self._mark("rpn")
-        rpn = self.net.rpn
-        x = rpn.backbone(self.bev)
+        rpn = s.rpn
+        x = self._rpn_backbone(self.bev)
         box = rpn.conv_box(x).contiguous()
         cls = rpn.conv_cls(x).contiguous()
-        dirp = rpn.conv_dir_cls(x).contiguous() if cfg.use_direction_classifier else None
+        dirp = rpn.conv_dir_cls(x).contiguous() if s.use_direction_classifier else None
         self._keep = (x, box, cls, dirp)
         self._mark("decode_filter")
         L.check(lib.b2s_decode_filter(
-            L.ptr(box), L.ptr(cls), L.ptr(dirp), L.ptr(self.anchors), None, self.B, self.a_loc, self.fH, self.fW,
-            self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
-            L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
-            L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter")
-        self._mark("nms")
-        L.check(lib.b2s_nms(
+            L.ptr(box), L.ptr(cls), L.ptr(dirp), L.ptr(self.anchors), L.ptr(self.anchors_mask) if self.use_mask else None,
+            self.B, self.a_loc, self.fH, self.fW, self.code, s.num_class, s.num_direction_bins, self.score_thresh,
             L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
-            L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.B, self.cand_cap, self.code,
-            1 if cfg.use_rotate_nms else 0, self.pre_max, self.post_max, float(cfg.nms_iou_threshold),
-            1 if cfg.use_direction_classifier else 0, float(cfg.direction_offset),
-            float(cfg.direction_limit_offset), cfg.num_direction_bins, self.range_host, L.ptr(self.det),
-            L.ptr(self.det_count), L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
-        self._mark("end")
+            L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter")
+        self._launch_nms(st)
 
-    def _launch_tc_tail(self, feats):
-        """BEV (NHWC, halo, hi/lo) -> tcgen05 RPN layers -> packed heads -> decode/filter -> NMS."""
-        L, lib, cfg = self._L, self.lib, self.cfg
+    def _launch_tc_tail(self, feats, hilo):
+        """BEV (NHWC, halo, fp16 hi/lo) -> tcgen05 RPN layers -> packed heads -> decode/filter -> NMS."""
+        L, lib, s = self._L, self.lib, self.spec
         st = L.stream()
         fl = self.final_level
         D, H, W = fl.shape
         self._mark("to_bev")
-        L.check(lib.b2s_to_bev_tc(L.ptr(feats), L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap, self.feat_final_c, self.B,
-                                  D, H, W, L.ptr(self.tc_bev[0]), L.ptr(self.tc_bev[1]), st), "b2s_to_bev_tc")
+        if hilo is not None:
+            L.check(lib.b2s_to_bev_tc(None, L.ptr(hilo[0]), L.ptr(hilo[1]), hilo[2], L.ptr(fl.coors), L.ptr(fl.n_dev),
+                                      fl.cap, self.feat_final_c, self.B, D, H, W, L.ptr(self.tc_bev[0]),
+                                      L.ptr(self.tc_bev[1]), st), "b2s_to_bev_tc")
+        else:
+            L.check(lib.b2s_to_bev_tc(L.ptr(feats), None, None, 0, L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap,
+                                      self.feat_final_c, self.B, D, H, W, L.ptr(self.tc_bev[0]), L.ptr(self.tc_bev[1]),
+                                      st), "b2s_to_bev_tc")
         self._mark("rpn")
         marked_tail = False
         for op in self.tc_plan:
@@ -391,15 +450,16 @@ class InferenceEngine:
                 marked_tail = True
             src, dst = self.tc_bufs[op["src"]], self.tc_bufs[op["dst"]]
             cdst = dst[0].shape[-1]                                   # channels per pixel of the destination map
-            o_hi = ctypes_ptr(dst[0].data_ptr() + 4 * op["dst_coff"])
-            o_lo = ctypes_ptr(dst[1].data_ptr() + 4 * op["dst_coff"]) if op["planes"] == 2 else None
+            esz = dst[0].element_size()
+            o_hi = ctypes_ptr(dst[0].data_ptr() + esz * op["dst_coff"])
+            o_lo = ctypes_ptr(dst[1].data_ptr() + esz * op["dst_coff"]) if op["planes"] == 2 else None
             L.check(lib.b2s_conv2d_tc_ex(
                 L.ptr(src[0]), L.ptr(src[1]), self.B, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]),
                 L.ptr(op["w_lo"]), op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
-                L.ptr(op["scale"]) if op["scale"] is not None else None,
-                L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"],
-                o_hi, o_lo, op["Hout"], op["Wout"], 1 if op["padded"] else 0, cdst, op["out_mul"], op["off_h"],
-                op["off_w"], st), "b2s_conv2d_tc_ex(%s)" % op["kind"])
+                L.ptr(op["scale"]), L.ptr(op["shift"]) if op["shift"] is not None else None,
+                1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi, o_lo, op["Hout"], op["Wout"],
+                1 if op["padded"] else 0, cdst, op["out_mul"], op["off_h"], op["off_w"], L.ptr(self.status), st),
+                "b2s_conv2d_tc_ex(%s)" % op["kind"])
         if not marked_tail:
             self._mark("rpn_1x1")
         S = self.tc_head_stride
@@ -409,25 +469,26 @@ class InferenceEngine:
         esz = heads.element_size()
         box_p = ctypes_ptr(heads.data_ptr() + offs[0] * esz)
         cls_p = ctypes_ptr(heads.data_ptr() + offs[1] * esz)
-        dir_p = ctypes_ptr(heads.data_ptr() + offs[2] * esz) if cfg.use_direction_classifier else None
+        dir_p = ctypes_ptr(heads.data_ptr() + offs[2] * esz) if s.use_direction_classifier else None
         bs = self.fH * self.fW * S
         L.check(lib.b2s_decode_filter_strided(
-            box_p, cls_p, dir_p, bs, bs, bs, 1, S, L.ptr(self.anchors), None, self.B, self.a_loc, self.fH, self.fW,
-            self.code, cfg.num_class, cfg.num_direction_bins, float(cfg.nms_score_threshold), L.ptr(self.cand_box),
+            box_p, cls_p, dir_p, bs, bs, bs, 1, S, L.ptr(self.anchors),
+            L.ptr(self.anchors_mask) if self.use_mask else None, self.B, self.a_loc, self.fH, self.fW,
+            self.code, s.num_class, s.num_direction_bins, self.score_thresh, L.ptr(self.cand_box),
             L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
             L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter_strided")
         self._launch_nms(st)
 
     def _launch_nms(self, st):
-        L, lib, cfg = self._L, self.lib, self.cfg
+        L, lib, s = self._L, self.lib, self.spec
         self._mark("nms")
         L.check(lib.b2s_nms(
             L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
             L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.B, self.cand_cap, self.code,
-            1 if cfg.use_rotate_nms else 0, self.pre_max, self.post_max, float(cfg.nms_iou_threshold),
-            1 if cfg.use_direction_classifier else 0, float(cfg.direction_offset),
-            float(cfg.direction_limit_offset), cfg.num_direction_bins, self.range_host, L.ptr(self.det),
-            L.ptr(self.det_count), L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
+            1 if s.use_rotate_nms else 0, self.pre_max, self.post_max, self.iou_thresh,
+            1 if s.use_direction_classifier else 0, float(s.direction_offset),
+            float(s.direction_limit_offset), s.num_direction_bins, self.range_host, L.ptr(self.det_record),
+            self.rec_width, L.ptr(self.det_count), L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
         self._mark("end")
 
     # ---------------------------------------------------------------- instrumentation
@@ -439,15 +500,14 @@ class InferenceEngine:
             ev.record()
             self._marks.append((name, ev))
 
-    def run_timed(self, iters=5):
+    def run_timed(self, iters=5, mode="points"):
         """eager (no graph) replay with a CUDA event before every stage; returns {stage: mean ms}."""
-        self.P_cap_used = self.P_cap
         acc = {}
-        with torch.no_grad():
-            self._launch()     # warm
+        with torch.no_grad(), torch.cuda.device(self.dev):
+            self._launch(mode)     # warm
             for _ in range(iters):
                 self._marks = []
-                self._launch()
+                self._launch(mode)
                 torch.cuda.synchronize()
                 for (name, ev), (_, nxt) in zip(self._marks[:-1], self._marks[1:]):
                     acc[name] = acc.get(name, 0.0) + ev.elapsed_time(nxt)
@@ -461,14 +521,14 @@ class InferenceEngine:
             n += 1                               # b2s_pfn
         for lyr in self.layers:
             if lyr["build_rb"]:
-                n += 1 if lyr["conv"].subm else 6   # subm_nbr | mark, popc_scan, scan_sums, emit, hash_build, conv_nbr
+                n += 1 if lyr["subm"] else 6     # subm_nbr | mark, popc_scan, scan_sums, emit, hash_build, conv_nbr
             n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc
             if lyr.get("in_split") is not None:
-                n += 1                           # b2s_split_tf32
-        if getattr(self, "any_sparse_tc", False):
-            n += 1                               # b2s_merge_hilo
+                n += 1                           # b2s_split_f16
         if self.rpn_impl == "tc":
             n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
+        elif getattr(self, "any_sparse_tc", False):
+            n += 1                               # b2s_merge_f16
         return n + 1 + 1 + 3                     # to_bev, decode_filter, nms: select_sort + iou_mask + reduce
 
     def sparse_layer_stats(self):
@@ -479,15 +539,16 @@ class InferenceEngine:
             n_in = int(lyr["in_level"].n_dev[0].item())
             pairs = int((lyr["rb"]["nbr"][:n_out] >= 0).sum().item())
             cin, cout, K = lyr["cin"], lyr["cout"], lyr["K"]
-            out.append({"index": lyr["index"], "subm": bool(lyr["conv"].subm), "cin": cin, "cout": cout, "K": K,
+            out.append({"index": lyr["index"], "subm": bool(lyr["subm"]), "cin": cin, "cout": cout, "K": K,
                         "n_in": n_in, "n_out": n_out, "pairs": pairs,
+                        "useful_mma_frac": pairs / max(1, K * n_out),
                         "bytes": 4 * (n_in * cin + n_out * cout) + 8 * pairs + 4 * K * cin * cout,
                         "flops": 2 * pairs * cin * cout})
         return out
 
     def rpn_layer_stats(self):
-        """per tcgen05 RPN layer: algorithmic fp32 flops (2*pixels*taps*cin*cout; the 3xTF32 split issues 3x that on
-        the tensor pipe) and algorithmic bytes (hi/lo planes in and out + weights)."""
+        """per tcgen05 RPN layer: algorithmic fp32 flops (2*pixels*taps*cin*cout; the 3xF16 split issues 3x that on
+        the tensor pipe) and bytes moved (fp16 hi/lo planes in and out + weights)."""
         if self.rpn_impl != "tc":
             return []
         out = []
@@ -495,12 +556,40 @@ class InferenceEngine:
             cin, cout, taps = op["cin"], op["cout"], op["taps"]
             px = self.B * op["Hg"] * op["Wg"]
             px_in = self.B * op["Hin"] * op["Win"]
+            out_b = 2 * 2 * px * cout if op["planes"] == 2 else 4 * px * cout
             out.append({"index": i, "kind": op["kind"], "v2": op["v2"], "cin": cin, "cout": cout, "taps": taps,
                         "pixels": px, "flops": 2 * px * taps * cin * cout,
-                        "bytes": 4 * (2 * px_in * cin + op["planes"] * px * cout + 2 * taps * cin * op["n_pad"])})
+                        "bytes": 2 * 2 * px_in * cin + out_b + 2 * 2 * taps * cin * op["n_pad"],
+                        "bytes_fp32_algorithmic": 4 * (px_in * cin + px * cout + taps * cin * cout)})
         return out
 
     # ---------------------------------------------------------------- public API
+    def set_anchors(self, anchors):
+        """anchors [A, code] or [B', A, code] (the example's ``anchors``; every frame shares one grid)."""
+        a = anchors[0] if anchors.dim() == 3 else anchors
+        key = (a.data_ptr(), tuple(a.shape), a._version, str(a.device))
+        if key == self._anchors_key:
+            return
+        a = a.reshape(-1, a.shape[-1])
+        assert a.shape[0] == self.A and a.shape[1] == self.code, \
+            "num_anchors=%d, but num_output=%d. please check size" % (a.shape[0], self.A)
+        self.anchors.copy_(a, non_blocking=True)
+        self._anchors_key = key
+
+    def set_anchors_mask(self, mask):
+        """anchors_mask [B, A] (bool/uint8) or None (voxelnet.py:397-400,432-439)."""
+        if mask is None:
+            if self.use_mask:
+                self.use_mask = False
+                self._graphs.clear()
+            return
+        if self.anchors_mask is None:
+            self.anchors_mask = torch.zeros(self.B, self.A, dtype=torch.uint8, device=self.dev)
+        if not self.use_mask:
+            self.use_mask = True
+            self._graphs.clear()               # the launch arguments change (NULL -> buffer)
+        self.anchors_mask.copy_(mask.reshape(self.B, self.A).to(torch.uint8), non_blocking=True)
+
     def load_points(self, frames):
         """frames: list of B CUDA (or pinned/CPU) float32 [P_i, F] tensors -> static input buffers."""
         assert len(frames) == self.B
@@ -513,36 +602,62 @@ class InferenceEngine:
                 self.points[off:off + n].copy_(f, non_blocking=True)
             off += n
         offs = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32)
-        self.offsets.copy_(offs.pin_memory() if offs.device.type == "cpu" else offs, non_blocking=True)
+        self.offsets.copy_(offs.pin_memory(), non_blocking=True)
         return total
 
-    def run(self):
-        """launch the pipeline on the points currently in the static buffers (async)."""
+    def load_voxels(self, voxels, num_points, coordinates):
+        """the reference's example tensors (voxels [N,T,F], num_points [N], coordinates [N,4] (b,z,y,x)), on any
+        device, -> static buffers.  N is known on the host (a tensor shape): no sync."""
+        n = int(voxels.shape[0])
+        cap = self.level0.cap
+        assert n <= cap, "more voxels (%d) than the engine's capacity (%d)" % (n, cap)
+        assert tuple(voxels.shape[1:]) == (self.T, self.F), "voxels must be [N, %d, %d]" % (self.T, self.F)
+        if self.in_voxels is None:
+            self.in_voxels = torch.zeros(cap, self.T, self.F, dtype=torch.float32, device=self.dev)
+            # PFN reads points through per-voxel slot indices: voxel v, slot t -> row v*T + t of in_voxels
+            self.in_slots = torch.arange(cap * self.T, dtype=torch.int32, device=self.dev).view(cap, self.T)
+            self._nvox_host = torch.zeros(1 + self.B, dtype=torch.int32).pin_memory()
+        self.in_voxels[:n].copy_(voxels, non_blocking=True)
+        self.vox_num[:n].copy_(num_points.to(torch.int32) if num_points.dtype != torch.int32 else num_points,
+                               non_blocking=True)
+        self.vox_coors[:n].copy_(coordinates.to(torch.int32) if coordinates.dtype != torch.int32 else coordinates,
+                                 non_blocking=True)
+        self._nvox_host[0] = n
+        self.num_voxels.copy_(self._nvox_host, non_blocking=True)
+        return n
+
+    def run(self, mode="points"):
+        """launch the pipeline on the data currently in the static buffers (async)."""
         # the grid sizes of the per-point kernels are fixed at capacity so one graph serves any frame mix
-        self.P_cap_used = self.P_cap
-        if not self.use_graph:
-            with torch.no_grad():
-                self._launch()
-            return self.det, self.det_count
-        if self._graph is None:
-            with torch.no_grad():
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    for _ in range(3):          # warm-up: cuDNN autotune, lazy module init, func attributes
-                        self._launch()
-                torch.cuda.current_stream().wait_stream(s)
-                torch.cuda.synchronize()
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._launch()
-                self._graph = g
-        self._graph.replay()
+        with torch.cuda.device(self.dev):
+            if not self.use_graph:
+                with torch.no_grad():
+                    self._launch(mode)
+                return self.det, self.det_count
+            g = self._graphs.get(mode)
+            if g is None:
+                with torch.no_grad():
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        for _ in range(3):          # warm-up: cuDNN autotune, lazy module init, func attributes
+                            self._launch(mode)
+                    torch.cuda.current_stream().wait_stream(side)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._launch(mode)
+                    self._graphs[mode] = g
+            g.replay()
         return self.det, self.det_count
 
     def infer(self, frames):
         self.load_points(frames)
-        return self.run()
+        return self.run("points")
+
+    def infer_voxels(self, voxels, num_points, coordinates):
+        self.load_voxels(voxels, num_points, coordinates)
+        return self.run("voxels")
 
     def check_status(self):
         """sync + raise on data-dependent overflow (call when results are read back)."""
@@ -551,14 +666,38 @@ class InferenceEngine:
             raise RuntimeError("b2second engine: " + self._L.status_message(st))
         return st
 
-    def detections(self):
-        """sync and convert to the reference's list-of-dicts (voxelnet.py:616-645)."""
-        det = self.det.cpu()
-        cnt = self.det_count.cpu().tolist()
-        self.check_status()
+    def detections(self, metadata=None, output="host"):
+        """sync and convert to the reference's list-of-dicts (voxelnet.py:616-645).
+
+        output="host": ONE pinned D2H copy of the detection records (counts ride in the records' last element) +
+        one stream sync, sliced on the host into CPU tensors.  output="device": the tensors stay on the GPU like the
+        reference's (one snapshot clone, per-frame views)."""
+        code, B = self.code, self.B
+        meta = metadata if metadata is not None and len(metadata) > 0 else [None] * B
+        if getattr(self, "_rec_host", None) is None:
+            self._rec_host = torch.empty(B, self.rec_width, dtype=torch.float32).pin_memory()
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(self.dev):
+            self._rec_host.copy_(self.det_record, non_blocking=True)
+            self._status_host.copy_(self.status, non_blocking=True)
+            if output == "device":
+                snap = self.det.clone()
+                labels = snap[..., code + 1].long()
+            torch.cuda.current_stream().synchronize()          # the one sync of the step
+        st = int(self._status_host[0])
+        if st & ~1:   # bit 1 (voxel overflow) is the reference's own drop-extra-voxels behaviour
+            raise RuntimeError("b2second engine: " + self._L.status_message(st))
+        cnt = self._rec_host[:, -1].round().to(torch.int64).tolist()
         out = []
-        for b in range(self.B):
-            d = det[b, :cnt[b]]
-            out.append({"box3d_lidar": d[:, :self.code].clone(), "scores": d[:, self.code].clone(),
-                        "label_preds": d[:, self.code + 1].long(), "metadata": None})
+        if output == "device":
+            for b in range(B):
+                n = cnt[b]
+                out.append({"box3d_lidar": snap[b, :n, :code], "scores": snap[b, :n, code],
+                            "label_preds": labels[b, :n], "metadata": meta[b]})
+            return out
+        host = self._rec_host[:, :-1].view(B, self.post_max, code + 2).clone()
+        for b in range(B):
+            d = host[b, :cnt[b]]
+            out.append({"box3d_lidar": d[:, :code], "scores": d[:, code], "label_preds": d[:, code + 1].long(),
+                        "metadata": meta[b]})
         return out

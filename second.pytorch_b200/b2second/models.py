@@ -295,6 +295,26 @@ class VoxelNet(nn.Module):
             num_direction_bins=cfg.num_direction_bins)
         self.register_buffer("global_step", torch.LongTensor(1).zero_())
         self._anchors_np = None
+        # the reference's own attribute names (voxelnet.py:104-143): b2second.spec reads a network through these,
+        # so the fused engine plans identically from this mirror and from the reference-built VoxelNet
+        self._num_class = cfg.num_class
+        self._num_input_features = cfg.num_point_features
+        self._use_rotate_nms = cfg.use_rotate_nms
+        self._multiclass_nms = cfg.use_multi_class_nms
+        self._nms_class_agnostic = cfg.nms_class_agnostic
+        nrep = cfg.num_class          # second_builder.py:47-62 passes one entry per class (equal unless multi-class NMS)
+        self._nms_score_thresholds = [cfg.nms_score_threshold] * nrep
+        self._nms_pre_max_sizes = [cfg.nms_pre_max_size] * nrep
+        self._nms_post_max_sizes = [cfg.nms_post_max_size] * nrep
+        self._nms_iou_thresholds = [cfg.nms_iou_threshold] * nrep
+        self._use_sigmoid_score = cfg.use_sigmoid_score
+        self._encode_background_as_zeros = cfg.encode_background_as_zeros
+        self._use_direction_classifier = cfg.use_direction_classifier
+        self._num_direction_bins = cfg.num_direction_bins
+        self._post_center_range = list(cfg.post_center_limit_range)
+        self._dir_offset = cfg.direction_offset
+        self._dir_limit_offset = cfg.direction_limit_offset
+        self._fast = None            # b2second.fastpath.FastPath once accelerate() has been called
 
     # -- helpers --------------------------------------------------------------------------
     def anchors(self):
@@ -317,6 +337,11 @@ class VoxelNet(nn.Module):
         return self.rpn(spatial_features)
 
     def forward(self, example):
+        if "points" in example and not self.training:
+            # raw clouds instead of voxels: only the fused engine takes those (b2second.fastpath); bind it once
+            from . import fastpath
+            fastpath.accelerate(self)
+            return self.forward(example)
         voxels = example["voxels"]
         num_points = example["num_points"]
         coors = example["coordinates"]

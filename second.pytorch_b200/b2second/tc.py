@@ -1,8 +1,9 @@
-"""Host side of the tensor-core RPN (csrc/conv_tc.cu, b2s_conv2d_tc): weight preparation and the layer plan.
+"""Host side of the tensor-core kernels (csrc/conv_tc.cu, conv_tc2.cu, sparse_conv_tc.cu): 3xF16 weight
+preparation and the RPN layer plan.
 
 RPNV2 for the sparse-conv configs (second/pytorch/models/rpn.py:467-497 with layer_strides [1], upsample
 strides [1]) is: 6 x [Conv3x3 pad1 + BN + ReLU] -> deblock ConvTranspose2d(k=1,s=1) + BN + ReLU -> three 1x1
-heads.  Each becomes one b2s_conv2d_tc launch on NHWC halo-padded hi/lo planes; the three heads are one launch
+heads.  Each becomes one b2s_conv2d_tc launch on NHWC halo-padded fp16 hi/lo planes; the three heads are one launch
 writing a packed 32-float record per pixel (box | cls | dir | pad) that b2s_decode_filter_strided reads.
 """
 import numpy as np
@@ -10,38 +11,60 @@ import torch
 from torch import nn
 
 
-def split_tf32(t):
-    """fp32 tensor -> (hi, lo): hi = value rounded to tf32 (10-bit mantissa, round half away), lo = t - hi (exact)."""
-    t = t.detach().float().contiguous()
+def pow2_scale(w):
+    """power of two s with max|w| * s in (2^12, 2^13]: fp16 keeps 11 significant bits down to 2^-14, so after this
+    scaling the lo plane of every weight above 2^-17 of the largest one is a NORMAL fp16 (full 22-bit split);
+    2^13 leaves three binades of head-room below the fp16 maximum.  The kernels multiply by 1/s in the epilogue."""
+    m = float(w.detach().abs().max()) if w.numel() else 0.0
+    if not np.isfinite(m) or m <= 0.0:
+        return 1.0
+    return float(2.0 ** (13 - int(np.ceil(np.log2(m)))))
 
-    def rn(x):
-        r = ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
-        return torch.where(torch.isfinite(r), r, x)
 
-    hi = rn(t)
-    # lo is ALSO rounded to tf32: the tensor core then sees exactly representable operands, so no hardware
-    # truncation (a biased error that accumulates ~K instead of ~sqrt(K)) can occur; |t - hi - lo| <= 2^-23 |t|.
-    lo = rn(t - hi)
+def split_f16(t, scale=1.0):
+    """fp32 tensor -> (hi, lo) torch.float16 planes of t*scale: hi = fp16(t*scale), lo = fp16(t*scale - hi)
+    (3xF16 split, csrc/tc_common.cuh; the device-side counterpart is b2s_split_f16)."""
+    t = t.detach().float().contiguous() * float(scale)
+    hi = t.clamp(-65504.0, 65504.0).half()
+    lo = (t - hi.float()).clamp(-65504.0, 65504.0).half()
     return hi.contiguous(), lo.contiguous()
 
 
-SPARSE_TC_CIN = (4, 16, 32, 64)
+def merge_f16(hi, lo):
+    return hi.float() + lo.float()
+
+
+SPARSE_TC_CIN = (8, 16, 32, 64)      # 3 or 4 input features are zero-padded to 8 (one 16-byte row chunk)
 SPARSE_TC_COUT = (16, 32, 64)
+SPARSE_BLOCK_K = 64                  # fp16 channels per 128-byte K block
+
+
+def sparse_tc_cin(cin):
+    """channel count the tensor-core sparse kernel sees for a layer with `cin` inputs (None: not covered)."""
+    if cin in SPARSE_TC_CIN:
+        return cin
+    if cin < 8:
+        return 8
+    return None
 
 
 def pack_sparse_weights(w):
-    """spconv weight [K, Cin, Cout] -> the K-major B operand b2s_sparse_conv_tc expects.
-    Cin >= 32: [K, Cout, Cin].  Cin < 32 (4 or 16): PACK = 32/Cin kernel offsets share one 128-byte K block, so the
-    rows are packed [ceil(K/PACK), Cout, 32] with column (offset-in-pack * Cin + cin) and zero columns past K."""
-    K, cin, cout = w.shape
-    wt = w.detach().float().transpose(1, 2).contiguous()            # [K, Cout, Cin]
-    if cin >= 32:
-        return wt
-    pack = 32 // cin
+    """spconv weight [K, Cin, Cout] -> the K-major B operand b2s_sparse_conv_tc expects (fp32, before the split).
+    Cin is zero-padded to sparse_tc_cin(Cin).  Cin = 64: [K, Cout, 64].  Cin < 64: PACK = 64/Cin kernel offsets
+    share one 128-byte K block, rows packed [ceil(K/PACK), Cout, 64] with column (offset-in-pack * Cin + cin) and
+    zero columns past K."""
+    K, cin0, cout = w.shape
+    cin = sparse_tc_cin(cin0)
+    assert cin is not None, "Cin %d is not covered by the tensor-core sparse kernel" % cin0
+    wt = torch.zeros(K, cout, cin, dtype=torch.float32, device=w.device)
+    wt[:, :, :cin0] = w.detach().float().transpose(1, 2)               # [K, Cout, Cin]
+    if cin >= SPARSE_BLOCK_K:
+        return wt.contiguous()
+    pack = SPARSE_BLOCK_K // cin
     nkb = (K + pack - 1) // pack
     out = torch.zeros(nkb * pack, cout, cin, dtype=wt.dtype, device=wt.device)
     out[:K] = wt
-    return out.view(nkb, pack, cout, cin).permute(0, 2, 1, 3).reshape(nkb, cout, 32).contiguous()
+    return out.view(nkb, pack, cout, cin).permute(0, 2, 1, 3).reshape(nkb, cout, SPARSE_BLOCK_K).contiguous()
 
 
 def _fold_bn2d(bn):
@@ -68,7 +91,7 @@ def _n_pad(cout):
 
 
 def supported(rpn):
-    """True when every layer of this RPNV2 maps onto b2s_conv2d_tc_ex (channels % 32 == 0, kernels <= 4x4)."""
+    """True when every layer of this RPNV2 maps onto b2s_conv2d_tc_ex (channels % 64 == 0, kernels <= 4x4)."""
     try:
         plan_rpn(rpn, 64, 64, dry=True)
         return True
@@ -92,7 +115,7 @@ def plan_rpn(rpn, H, W, dry=False):
     def emit(kind, src, dst, w_t_co_ci, kh, kw, stride, pad, scale, shift, relu, hin, win, hg, wg, hout, wout,
              out_mul=1, off=(0, 0), dst_coff=0, planes=2, padded=True):
         taps, cout, cin = w_t_co_ci.shape
-        assert taps == kh * kw and cin % 32 == 0, "channels must be multiples of 32"
+        assert taps == kh * kw and cin % 64 == 0, "input channels must be multiples of 64"
         for c0 in range(0, cout, 128):
             c1 = min(cout, c0 + 128)
             n_pad = _n_pad(c1 - c0)
@@ -100,22 +123,28 @@ def plan_rpn(rpn, H, W, dry=False):
                  "cin": cin, "cout": c1 - c0, "n_pad": n_pad, "relu": relu, "Hin": hin, "Win": win, "Hg": hg, "Wg": wg,
                  "Hout": hout, "Wout": wout, "out_mul": out_mul, "off_h": off[0], "off_w": off[1],
                  "dst_coff": dst_coff + c0, "planes": planes, "padded": padded,
-                 "scale": None if scale is None else scale[c0:c1].contiguous(),
-                 "shift": None if shift is None else shift[c0:c1].contiguous(),
+                 "shift": None if shift is None else shift[c0:c1].float().contiguous(),
                  # the weights-stationary N=256 kernel takes this op (conv_tc.cu dispatch)
                  "v2": (kh == 3 and kw == 3 and stride == 1 and pad == 1 and n_pad == 128 and planes == 2 and padded
                         and out_mul == 1)}
             if not dry:
-                d["w_hi"], d["w_lo"] = split_tf32(_pad_rows(w_t_co_ci[:, c0:c1].float(), n_pad))
+                # weights pre-scaled by a power of two (exact), undone by the epilogue scale
+                wp = _pad_rows(w_t_co_ci[:, c0:c1].float(), n_pad)
+                ws = pow2_scale(wp)
+                d["w_hi"], d["w_lo"] = split_f16(wp, ws)
+                d["w_scale"] = ws
+                base = torch.ones(c1 - c0, dtype=torch.float32, device=wp.device) if scale is None \
+                    else scale[c0:c1].float()
+                d["scale"] = (base / ws).contiguous()
             ops.append(d)
 
     cur, h, w = "in", H, W
     ups = []                                   # (buffer, channels) of each deblock output, in order
     up_start = rpn._upsample_start_idx
     cat_hw = None
-    up_filters = [list(db)[0].out_channels for db in rpn.deblocks]
+    up_filters = [list(db.children())[0].out_channels for db in rpn.deblocks]
     for bi, block in enumerate(rpn.blocks):
-        mods = list(block)
+        mods = list(block.children())
         i, li = 0, 0
         while i < len(mods):
             m = mods[i]
@@ -143,7 +172,7 @@ def plan_rpn(rpn, H, W, dry=False):
             li += 1
         j = bi - up_start
         if j >= 0:
-            up, bn, relu = list(rpn.deblocks[j])
+            up, bn, relu = list(rpn.deblocks[j].children())
             assert up.bias is None and isinstance(bn, nn.BatchNorm2d)
             sc, sh = _fold_bn2d(bn)
             coff = sum(up_filters[:j])

@@ -1,7 +1,9 @@
 // bev.cu -- sparse rows -> dense BEV map (b2s_to_bev) and the PointPillars feature net (b2s_pfn).
 // See include/b2second.h.  Pure HBM-bound data movement: zero-fill the dense map once, then one
 // scattered write per (row, channel).
-#include "common.cuh"
+#include <cuda_fp16.h>
+
+#include "tc_common.cuh"
 
 namespace {
 
@@ -38,10 +40,12 @@ __global__ void k_to_bev(const float *__restrict__ feat, const int *__restrict__
     }
 }
 
-// tensor-core RPN input: NHWC + one-pixel zero halo, hi/lo (3xTF32) planes
-__global__ void k_to_bev_tc(const float *__restrict__ feat, const int *__restrict__ coors,
+// tensor-core RPN input: NHWC + one-pixel zero halo, fp16 hi/lo planes (3xF16 split).  The rows come either as fp32
+// (PointPillars: the PFN output) or already split (the last sparse layer's hi/lo planes, row stride feat_stride halves).
+__global__ void k_to_bev_tc(const float *__restrict__ feat, const __half *__restrict__ feat_hi,
+                            const __half *__restrict__ feat_lo, int feat_stride, const int *__restrict__ coors,
                             const int *__restrict__ n_dev, int cap_rows, int C, int batch, int D, int H, int W,
-                            float *__restrict__ out_hi, float *__restrict__ out_lo)
+                            __half *__restrict__ out_hi, __half *__restrict__ out_lo)
 {
     const int n = min(*n_dev, cap_rows);
     const long long total = (long long)n * C;
@@ -52,16 +56,16 @@ __global__ void k_to_bev_tc(const float *__restrict__ feat, const int *__restric
         if ((unsigned)q.x >= (unsigned)batch || (unsigned)q.y >= (unsigned)D || (unsigned)q.z >= (unsigned)H ||
             (unsigned)q.w >= (unsigned)W)
             continue;
-        float v = __ldg(&feat[gid]);
-        unsigned u;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-        float hi = __uint_as_float(u);
         size_t CD = (size_t)C * D;
         size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
-        out_hi[idx] = hi;
-        unsigned ul;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(ul) : "f"(v - hi));
-        out_lo[idx] = __uint_as_float(ul);
+        if (feat) {
+            const uint32_t pk = b2s_tc::split_f16(__ldg(&feat[gid]));
+            out_hi[idx] = __ushort_as_half((unsigned short)(pk & 0xFFFFu));
+            out_lo[idx] = __ushort_as_half((unsigned short)(pk >> 16));
+        } else {
+            out_hi[idx] = feat_hi[(size_t)row * feat_stride + c];
+            out_lo[idx] = feat_lo[(size_t)row * feat_stride + c];
+        }
     }
 }
 
@@ -153,17 +157,22 @@ extern "C" int b2s_to_bev(const float *feat, const int *coors, const int *num_ro
     return 0;
 }
 
-extern "C" int b2s_to_bev_tc(const float *feat, const int *coors, const int *num_rows_dev, int cap_rows, int C,
-                             int batch, int D, int H, int W, float *out_hi, float *out_lo, void *stream_)
+extern "C" int b2s_to_bev_tc(const float *feat, const b2s_half *feat_hi, const b2s_half *feat_lo, int feat_stride,
+                             const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch, int D, int H,
+                             int W, b2s_half *out_hi, b2s_half *out_lo, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE(C >= 1 && batch >= 1 && D >= 1 && H >= 1 && W >= 1, "b2s_to_bev_tc: bad sizes");
+    B2S_REQUIRE((feat != nullptr) != (feat_hi != nullptr && feat_lo != nullptr),
+                "b2s_to_bev_tc: pass either fp32 rows or hi/lo fp16 rows");
     size_t total = (size_t)batch * (H + 2) * (W + 2) * C * D;
-    B2S_CUDA_OK(cudaMemsetAsync(out_hi, 0, sizeof(float) * total, stream));
-    B2S_CUDA_OK(cudaMemsetAsync(out_lo, 0, sizeof(float) * total, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(out_hi, 0, sizeof(__half) * total, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(out_lo, 0, sizeof(__half) * total, stream));
     if (cap_rows > 0) {
         k_to_bev_tc<<<bounded_grid((long long)cap_rows * C), kThreads, 0, stream>>>(
-            feat, coors, num_rows_dev, cap_rows, C, batch, D, H, W, out_hi, out_lo);
+            feat, reinterpret_cast<const __half *>(feat_hi), reinterpret_cast<const __half *>(feat_lo), feat_stride, coors,
+            num_rows_dev, cap_rows, C, batch, D, H, W, reinterpret_cast<__half *>(out_hi),
+            reinterpret_cast<__half *>(out_lo));
         B2S_LAUNCH_OK();
     }
     return 0;

@@ -8,23 +8,29 @@
 //
 // This kernel removes shared-memory traffic per tensor cycle two ways:
 //   1. orientation swap, N = 256:  D^T[Cout = 128 (M, TMEM lanes), 256 pixels (N, TMEM columns)]
-//          += W[tap][Cout, 32 ch] (A)  *  X[256 pixels, 32 ch]^T (B)
-//      a 128x256x8 MMA reads 4 + 8 KB in 128 tensor cycles = 96 B/clk;
-//   2. vertical reuse: the activation stage is an 18-row x 16-col pixel tile (one 32-channel chunk, one
+//          += W[tap][Cout, 64 ch] (A)  *  X[256 pixels, 64 ch]^T (B)
+//      a 128x256x16 f16 MMA reads 4 + 8 KB in 128 tensor cycles = 96 B/clk;
+//   2. vertical reuse: the activation stage is an 18-row x 16-col pixel tile (one 64-channel chunk, one
 //      horizontal tap offset dx).  The three vertical taps dy = 0,1,2 are the SAME stage viewed 16 pixel rows
 //      (= 2048 B = two whole 1024-byte swizzle atoms) further down, so the UMMA descriptor just starts 2048*dy
 //      bytes later -- no swizzle-phase tricks.  Activation bytes written to shared memory drop 2.7x.
-// Per (dx, chunk) group: 72 KB activations + 3 x 32 KB weights written, 36 MMAs (4608 tensor cycles).
+// Per (dx, chunk) group: 72 KB activations + 3 x 32 KB weights written, 36 MMAs (4608 tensor cycles) -- the same
+// bytes and cycles as the 3xTF32 kernel of round 1, but a group now covers 64 channels instead of 32 (3xF16 split,
+// tc_common.cuh), so a 128-channel layer is 6 groups per tile instead of 12.
 //
 // Accumulation chains stay short (the tensor core's fp32 accumulate truncates: measured rms error grows linearly
 // with chain length, tools/bench_conv_tc.py): one chain = one (dx, chunk) group = 36 MMAs, drained by the
 // epilogue warps into fp32 registers with round-to-nearest adds; two 256-column TMEM accumulators ping-pong.
 //
 // Epilogue without staging: a TMEM lane is an output CHANNEL here, so lane l of a warp holds channel 32q+l of
-// one pixel -- a plain 4-byte store per lane writes 128 contiguous bytes of the NHWC row.
+// one pixel.  Lanes 2j / 2j+1 swap one value of a pixel pair (one shuffle of the packed hi|lo word), after which
+// every lane owns two adjacent channels of one pixel and stores a half2 per plane: a warp store writes
+// 2 pixels x 64 contiguous bytes.
 //
 // Warp roles (12 warps): 0 activation TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 weight TMA producer,
 // 4-11 epilogue (lane quarter = warp % 4, pixel half = (warp - 4) / 4).
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -34,15 +40,15 @@ constexpr int T2_H = 16, T2_W = 16;                 // 256 output pixels per til
 constexpr int HALO_H = T2_H + 2;                    // rows of the activation stage
 constexpr int N_PIX = T2_H * T2_W;                  // UMMA N
 constexpr int kThreads2 = 384;
-constexpr uint32_t X_PLANE_BYTES = HALO_H * T2_W * BLOCK_K * 4;   // 36 KB (hi or lo)
+constexpr uint32_t X_PLANE_BYTES = HALO_H * T2_W * BLOCK_K * ELEM_BYTES;   // 36 KB (hi or lo)
 constexpr uint32_t X_STAGE_BYTES = 2 * X_PLANE_BYTES;             // 72 KB
-constexpr uint32_t W_PLANE_BYTES = 128 * BLOCK_K * 4;             // 16 KB
+constexpr uint32_t W_PLANE_BYTES = 128 * BLOCK_K * ELEM_BYTES;             // 16 KB
 // Weight ring: 5 slots of ONE plane each (hi and lo alternate).  A K block issues its 8 W_hi MMAs first and frees
 // the hi slot, then its 4 W_lo MMAs -- so a slot is refilled two full K blocks (~3000 tensor cycles) before it is
 // needed.  (First version: 2 slots of hi+lo = one K block of lead -> the MMA issuer waited on weight loads,
 // 0.371 ms/layer; measured round 1.)
 constexpr int X_STAGES = 2, W_STAGES = 5, ACC2 = 2;
-constexpr uint32_t DY_BYTES = T2_W * BLOCK_K * 4;                 // one pixel row of the tile = 2048 B
+constexpr uint32_t DY_BYTES = T2_W * BLOCK_K * ELEM_BYTES;                 // one pixel row of the tile = 2048 B
 
 struct Conv2Params {
     int B, H, W, Cin, Cout, relu;
@@ -52,7 +58,8 @@ struct Conv2Params {
     int dbg;                         // B2S_CONV2_DBG diagnostics (results wrong): 1 no activation loads, 2 no weight
                                      // loads, 4 no TMEM drain, 8 no global stores
     const float *scale, *shift;
-    float *out_hi, *out_lo;          // [B, H+2, W+2, out_stride] halo-padded planes (interior written)
+    __half *out_hi, *out_lo;         // [B, H+2, W+2, out_stride] halo-padded fp16 planes (interior written)
+    int *status;                     // bit B2S_STATUS_F16_RANGE raised when an activation exceeds the fp16 range
 };
 
 __global__ void __launch_bounds__(kThreads2, 1)
@@ -145,7 +152,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         // ===================== MMA issuer =====================
         // The whole warp walks the loops (all values warp-uniform -> uniform registers); one elected lane issues
         // the tcgen05 instructions.  See tc_common.cuh: an `if (lane == 0)` issuer costs ~190 cycles per MMA.
-        constexpr uint32_t idesc = make_idesc_tf32(N_PIX);
+        constexpr uint32_t idesc = make_idesc_f16(N_PIX);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t sx0 = smem_u32(smem_x), sw0 = smem_u32(smem_w);
         // Software-pipelined issue: the barrier of the NEXT burst's operands is waited for while the current burst
@@ -170,9 +177,9 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     const uint64_t w_hi = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // +32 B per K step
-                        umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
-                        umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM_BYTES) >> 4);   // +32 B per K step
+                        umma_f16_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, (dy | k) != 0);
+                        umma_f16_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
                     }
                     // look ahead: the W_lo plane of this K block
                     int wsn = ws + 1;
@@ -181,17 +188,17 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     mbar_wait(&bar_wfull[wsn], wphn);
                     tc_fence_after();
                     {
-                        const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
-                        umma_tf32_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, 1);
-                        umma_tf32_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
+                        const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
+                        umma_f16_afill(tmem_d, w_hi + koff, x_lo + koff, idesc, 1);
+                        umma_f16_alast(tmem_d, w_hi + koff, x_hi + koff, idesc, 1);
                     }
                     umma_commit(&bar_wempty[ws]);
                     ws = wsn; wph = wphn;
                     const uint64_t w_lo = make_desc_sw128(sw0 + (uint32_t)ws * W_PLANE_BYTES);
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                        umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM_BYTES) >> 4);
+                        umma_f16(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
                     }
                     // look ahead: the next K block's W_hi plane, and at a group boundary the next accumulator and
                     // activation stage
@@ -209,8 +216,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                     }
 #pragma unroll
                     for (int k = 2; k < 4; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                        umma_tf32(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM_BYTES) >> 4);
+                        umma_f16(tmem_d, w_lo + koff, x_hi + koff, idesc, 1);
                     }
                     umma_commit(&bar_wempty[ws]);
                     if (dy == 2) {
@@ -258,33 +265,39 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);
                 if (++acc == ACC2) { acc = 0; aph ^= 1; }
             }
-            // BN scale/shift + ReLU + hi/lo split; lane = channel, so each store instruction writes one pixel's
-            // 32 consecutive channels = one 128-byte line
+            // BN scale/shift + ReLU + hi/lo fp16 split.  lane = channel; lanes 2j and 2j+1 exchange one packed (hi|lo)
+            // word per pixel pair so that each lane ends up with channels (2j, 2j+1) of ONE pixel: even lanes keep
+            // pixel cw, odd lanes pixel cw+1.  One half2 store per plane and lane = 2 x 64 contiguous bytes per warp.
             const int hbase = th * T2_H + half * 8, wbase = tw * T2_W;
+            const int odd = lane & 1;
+            const int cpair = c & ~1;                                   // first channel of this lane's pair
+            const bool pair_ok = cpair < p.Cout;                         // Cout is even (host check)
+            bool range_bad = false;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int h = hbase + r;
                 if (h >= p.H) break;
                 const size_t rowpix = ((size_t)b * (p.H + 2) + (h + 1)) * (p.W + 2) + (wbase + 1);
-                float *oh = p.out_hi + rowpix * p.out_stride + c;
-                float *ol = p.out_lo + rowpix * p.out_stride + c;
+                __half *oh = p.out_hi + rowpix * p.out_stride + cpair;
+                __half *ol = p.out_lo + rowpix * p.out_stride + cpair;
 #pragma unroll
-                for (int cw = 0; cw < T2_W; ++cw) {
-                    float x = fmaf(sum[r * 16 + cw], sc, sh);
-                    if (p.relu) x = fmaxf(x, 0.f);
-                    const float hi = to_tf32_rn(x);
-                    const float lo = to_tf32_rn(x - hi);
-                    if (c_ok && wbase + cw < p.W && !(p.dbg & 8)) {
-                        if (p.dbg & 16) {            // experiment: streaming (evict-first) stores
-                            __stcs(&oh[(size_t)cw * p.out_stride], hi);
-                            __stcs(&ol[(size_t)cw * p.out_stride], lo);
-                        } else {
-                            oh[(size_t)cw * p.out_stride] = hi;
-                            ol[(size_t)cw * p.out_stride] = lo;
-                        }
+                for (int cw = 0; cw < T2_W; cw += 2) {
+                    float x0 = fmaf(sum[r * 16 + cw], sc, sh), x1 = fmaf(sum[r * 16 + cw + 1], sc, sh);
+                    if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                    range_bad |= (fabsf(x0) > 65504.f) | (fabsf(x1) > 65504.f);
+                    const uint32_t p0 = split_f16(x0), p1 = split_f16(x1);
+                    const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? p0 : p1, 1);
+                    // even lane: (own p0 = ch c, recv = ch c+1) of pixel cw; odd lane: (recv = ch c-1, own p1 = ch c) of cw+1
+                    const uint32_t a = odd ? recv : p0, bq = odd ? p1 : recv;
+                    const uint32_t hi2 = __byte_perm(a, bq, 0x5410), lo2 = __byte_perm(a, bq, 0x7632);
+                    const int col = cw + odd;
+                    if (pair_ok && wbase + col < p.W && !(p.dbg & 8)) {
+                        *reinterpret_cast<uint32_t *>(oh + (size_t)col * p.out_stride) = hi2;
+                        *reinterpret_cast<uint32_t *>(ol + (size_t)col * p.out_stride) = lo2;
                     }
                 }
             }
+            if (range_bad && c_ok && p.status) atomicOr(p.status, B2S_STATUS_F16_RANGE);
         }
     }
     tc_fence_before();
@@ -298,21 +311,22 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
 }  // namespace
 
 // called by b2s_conv2d_tc (conv_tc.cu) for taps == 9, n_pad == 128, halo-padded hi/lo output
-int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W, int Cin, const float *w_hi,
-                    const float *w_lo, int Cout, const float *scale, const float *shift, int relu, float *out_hi,
-                    float *out_lo, int out_stride, int num_sms, cudaStream_t stream)
+int b2s_conv3x3_tc2(const __half *in_hi, const __half *in_lo, int B, int H, int W, int Cin, const __half *w_hi,
+                    const __half *w_lo, int Cout, const float *scale, const float *shift, int relu, __half *out_hi,
+                    __half *out_lo, int out_stride, int *status, int num_sms, cudaStream_t stream)
 {
     using namespace b2s_tc;
     CUtensorMap x_hi, x_lo, m_w_hi, m_w_lo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(W + 2), (cuuint64_t)(H + 2), (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)(W + 2) * Cin * 4, (cuuint64_t)(H + 2) * (W + 2) * Cin * 4};
+        cuuint64_t str[3] = {(cuuint64_t)Cin * ELEM_BYTES, (cuuint64_t)(W + 2) * Cin * ELEM_BYTES,
+                             (cuuint64_t)(H + 2) * (W + 2) * Cin * ELEM_BYTES};
         cuuint32_t box[4] = {BLOCK_K, T2_W, HALO_H, 1};
         if (make_map(&x_hi, in_hi, 4, dims, str, box) || make_map(&x_lo, in_lo, 4, dims, str, box)) return -1;
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)Cin, 128, 9};
-        cuuint64_t str[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)128 * Cin * 4};
+        cuuint64_t str[2] = {(cuuint64_t)Cin * ELEM_BYTES, (cuuint64_t)128 * Cin * ELEM_BYTES};
         cuuint32_t box[3] = {BLOCK_K, 128, 1};
         if (make_map(&m_w_hi, w_hi, 3, dims, str, box) || make_map(&m_w_lo, w_lo, 3, dims, str, box)) return -1;
     }
@@ -326,16 +340,16 @@ int b2s_conv3x3_tc2(const float *in_hi, const float *in_lo, int B, int H, int W,
         static int dbg = -1, deph = -1;
         if (dbg < 0) { const char *e = getenv("B2S_CONV2_DBG"); dbg = e ? atoi(e) : 0; }
         if (deph < 0) { const char *e = getenv("B2S_CONV2_DEPHASE"); deph = e ? atoi(e) : 0; }
-        p.dbg = dbg;
+#ifdef B2S_DIAG
+        p.dbg = dbg;            // diagnostics that corrupt results exist only in `make DIAG=1` builds
+#else
+        p.dbg = 0;
+#endif
         p.dephase = deph;
     }
-    p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
+    p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo; p.status = status;
     const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;
-    static bool attr = false;
-    if (!attr) {
-        B2S_CUDA_OK(cudaFuncSetAttribute(k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    B2S_SMEM_OPT_IN(k_conv3x3_tc2, smem);
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
     k_conv3x3_tc2<<<grid, kThreads2, smem, stream>>>(x_hi, x_lo, m_w_hi, m_w_lo, p);
     B2S_LAUNCH_OK();

@@ -390,7 +390,7 @@ k_reduce_epilogue(const unsigned long long *__restrict__ mask, const int *__rest
                   const int *__restrict__ cand_dir, int cand_cap, int code, int pre_max, int words,
                   int post_max, int use_dir, float dir_offset, float dir_limit_offset, int num_dir_bins,
                   int has_range, float r0, float r1, float r2, float r3, float r4, float r5, float *det,
-                  int *det_count)
+                  int det_frame_stride, int *det_count)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned long long *s_mask = reinterpret_cast<unsigned long long *>(sm);  // [n][words]
@@ -459,6 +459,8 @@ k_reduce_epilogue(const unsigned long long *__restrict__ mask, const int *__rest
             out += f;
         }
         det_count[b] = out;
+        // record layout for the all-gather: the count rides in the record's last element
+        if (det_frame_stride > post_max * stride) det[(size_t)b * det_frame_stride + det_frame_stride - 1] = (float)out;
     }
     __syncthreads();
     for (int q = tid; q < nk; q += 256) {
@@ -477,7 +479,7 @@ k_reduce_epilogue(const unsigned long long *__restrict__ mask, const int *__rest
             float dir_rot = __fsub_rn(val, __fmul_rn(fl, period));
             v[6] = __fadd_rn(__fadd_rn(dir_rot, dir_offset), __fmul_rn(period, (float)cand_dir[cs]));
         }
-        float *d = det + ((size_t)b * post_max + pos) * stride;
+        float *d = det + (size_t)b * det_frame_stride + (size_t)pos * stride;
         for (int c = 0; c < code; ++c) d[c] = v[c];
         d[code] = cand_score[cs];
         d[code + 1] = (float)cand_label[cs];
@@ -580,23 +582,28 @@ extern "C" int b2s_nms(const float *cand_box, const float *cand_score, const int
                        const int *cand_dir, const int *cand_anchor, const int *cand_count_dev, int batch,
                        int cand_cap, int code, int rotated, int pre_max, int post_max, float iou_thresh,
                        int use_dir, float dir_offset, float dir_limit_offset, int num_dir_bins,
-                       const float *range_host, float *det, int *det_count_dev, void *workspace,
-                       size_t workspace_bytes, void *stream_)
+                       const float *range_host, float *det, int det_frame_stride, int *det_count_dev,
+                       void *workspace, size_t workspace_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE(pre_max >= 1 && pre_max <= 2048, "b2s_nms: pre_max must be 1..2048");
     B2S_REQUIRE(post_max >= 1 && post_max <= 1024, "b2s_nms: post_max must be 1..1024");
     B2S_REQUIRE(code >= 7 && code <= kMaxCode, "b2s_nms: bad code size");
+    if (det_frame_stride == 0) det_frame_stride = post_max * (code + 2);
+    B2S_REQUIRE(det_frame_stride >= post_max * (code + 2), "b2s_nms: det_frame_stride smaller than a frame's rows");
     NmsWorkspace w;
     size_t need = carve(&w, (char *)workspace, batch, pre_max);
     B2S_REQUIRE(workspace_bytes >= need, "b2s_nms: workspace too small (%zu < %zu)", workspace_bytes, need);
-    static bool attr_set = false;
+    static bool attr_set[64] = {false};      // per device: the attribute belongs to the current device
+    int cur_dev = 0;
+    B2S_CUDA_OK(cudaGetDevice(&cur_dev));
+    cur_dev &= 63;
     size_t smem_sel = (size_t)kSortCap * (sizeof(unsigned long long) + sizeof(int));
     size_t smem_red = sizeof(unsigned long long) * (size_t)pre_max * w.words;
-    if (!attr_set) {
+    if (!attr_set[cur_dev]) {
         B2S_CUDA_OK(cudaFuncSetAttribute(k_select_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         B2S_CUDA_OK(cudaFuncSetAttribute(k_reduce_epilogue, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[cur_dev] = true;
     }
     B2S_REQUIRE(smem_red <= 200 * 1024, "b2s_nms: pre_max too large for the shared-memory reduce");
     k_select_sort<<<batch, kSelThreads, smem_sel, stream>>>(cand_box, cand_score, cand_anchor, cand_count_dev,
@@ -610,7 +617,7 @@ extern "C" int b2s_nms(const float *cand_box, const float *cand_score, const int
                                                        cand_label, cand_dir, cand_cap, code, pre_max, w.words,
                                                        post_max, use_dir, dir_offset, dir_limit_offset,
                                                        num_dir_bins, range_host != nullptr, r[0], r[1], r[2],
-                                                       r[3], r[4], r[5], det, det_count_dev);
+                                                       r[3], r[4], r[5], det, det_frame_stride, det_count_dev);
     B2S_LAUNCH_OK();
     return 0;
 }
@@ -664,27 +671,103 @@ __global__ void k_reduce_simple(const unsigned long long *__restrict__ mask, int
     if (threadIdx.x == 0) *nkeep = nk;
 }
 
+// RAII for the numpy-facing wrappers: temporaries are freed and the caller's current device is restored on EVERY
+// exit path (upstream's *_cpu functions never touch CUDA state, so ours must not leave a different device current)
+struct DeviceScope {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceScope(int device_id)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; ok = false; return; }
+        if (device_id >= 0 && device_id != prev) ok = cudaSetDevice(device_id) == cudaSuccess;
+    }
+    ~DeviceScope()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+struct DevBuf {
+    void *p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
 int host_nms_common(float *d_geo, int n, int rotated, float thresh, float eps, int inclusive, int *keep_out_host,
                     cudaStream_t stream)
 {
     int words = (n + 63) / 64;
-    unsigned long long *d_mask = nullptr;
-    int *d_keep = nullptr, *d_nkeep = nullptr;
-    B2S_CUDA_OK(cudaMalloc(&d_mask, sizeof(unsigned long long) * (size_t)n * words));
-    B2S_CUDA_OK(cudaMalloc(&d_keep, sizeof(int) * (size_t)n));
-    B2S_CUDA_OK(cudaMalloc(&d_nkeep, sizeof(int)));
-    B2S_CUDA_OK(cudaMemsetAsync(d_mask, 0, sizeof(unsigned long long) * (size_t)n * words, stream));
+    DevBuf mask, keep, nkeep;
+    B2S_CUDA_OK(mask.alloc(sizeof(unsigned long long) * (size_t)n * words));
+    B2S_CUDA_OK(keep.alloc(sizeof(int) * (size_t)n));
+    B2S_CUDA_OK(nkeep.alloc(sizeof(int)));
+    B2S_CUDA_OK(cudaMemsetAsync(mask.p, 0, sizeof(unsigned long long) * (size_t)n * words, stream));
     dim3 grid(words, words, 1);
-    k_iou_mask<<<grid, 256, 0, stream>>>(d_geo, nullptr, n, words, rotated, thresh, eps, inclusive, d_mask);
-    k_reduce_simple<<<1, 32, sizeof(unsigned long long) * words, stream>>>(d_mask, n, words, d_keep, d_nkeep);
+    k_iou_mask<<<grid, 256, 0, stream>>>(d_geo, nullptr, n, words, rotated, thresh, eps, inclusive,
+                                         mask.as<unsigned long long>());
+    B2S_LAUNCH_OK();
+    k_reduce_simple<<<1, 32, sizeof(unsigned long long) * words, stream>>>(mask.as<unsigned long long>(), n, words,
+                                                                           keep.as<int>(), nkeep.as<int>());
+    B2S_LAUNCH_OK();
     int nk = 0;
-    cudaError_t e = cudaMemcpyAsync(&nk, d_nkeep, sizeof(int), cudaMemcpyDeviceToHost, stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    if (e == cudaSuccess && nk > 0)
-        e = cudaMemcpy(keep_out_host, d_keep, sizeof(int) * (size_t)nk, cudaMemcpyDeviceToHost);
-    cudaFree(d_mask); cudaFree(d_keep); cudaFree(d_nkeep);
-    if (e != cudaSuccess) { b2s_set_error("host nms: %s", cudaGetErrorString(e)); return -1; }
+    B2S_CUDA_OK(cudaMemcpyAsync(&nk, nkeep.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B2S_CUDA_OK(cudaStreamSynchronize(stream));
+    if (nk > 0) B2S_CUDA_OK(cudaMemcpy(keep_out_host, keep.p, sizeof(int) * (size_t)nk, cudaMemcpyDeviceToHost));
     return nk;
+}
+
+// rotated overlap of every (box n, query k) pair: one thread per pair (N x K is small: eval / target assignment)
+//   criterion -1: IoU, 0: inter/area(box), 1: inter/area(query), 2: intersection area
+//   (second/core/non_max_suppression/nms_gpu.py:553-566 devRotateIoUEval)
+__device__ __forceinline__ float overlap_of(float inter, float area_b, float area_q, int criterion)
+{
+    if (criterion == -1) return inter / (area_b + area_q - inter);
+    if (criterion == 0) return inter / area_b;
+    if (criterion == 1) return inter / area_q;
+    return inter;
+}
+
+__global__ void k_rbbox_pairs(const float *__restrict__ corners, const float *__restrict__ qcorners,
+                              const float *__restrict__ standup_iou, int N, int K, float standup_thresh, int criterion,
+                              float *__restrict__ out)
+{
+    const long long total = (long long)N * K;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(g / K), k = (int)(g % K);
+        float r = 0.f;
+        bool gate;
+        float a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a[i] = corners[(size_t)n * 8 + i]; b[i] = qcorners[(size_t)k * 8 + i]; }
+        if (standup_iou) {
+            gate = standup_iou[g] > standup_thresh;
+        } else {                      // gate = stand-up boxes overlap (iou_jit(eps=0) > 0)
+            float sa[4], sb[4];
+            standup_of(a, sa);
+            standup_of(b, sb);
+            gate = fminf(sa[2], sb[2]) - fmaxf(sa[0], sb[0]) > 0.f && fminf(sa[3], sb[3]) - fmaxf(sa[1], sb[1]) > 0.f;
+        }
+        if (gate) {
+            float area_a, area_b;
+            const float inter = quad_intersection(a, b, &area_a, &area_b);
+            r = overlap_of(inter, area_a, area_b, criterion);
+        }
+        out[g] = r;
+    }
+}
+
+__global__ void k_corners_from_rboxes(const float *__restrict__ boxes /*[n,5] x,y,w,l,r*/, int n, float *corners)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *b = boxes + (size_t)i * 5;
+    float c[8];
+    bev_corners(b[0], b[1], b[2], b[3], b[4], c);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) corners[(size_t)i * 8 + q] = c[q];
 }
 
 }  // namespace
@@ -693,15 +776,15 @@ extern "C" int b2s_nms_aligned_host(const float *sorted_dets, int n, float thres
                                     int *keep_out, int device_id)
 {
     if (n <= 0) return 0;
-    B2S_CUDA_OK(cudaSetDevice(device_id));
-    float *d_dets = nullptr, *d_geo = nullptr;
-    B2S_CUDA_OK(cudaMalloc(&d_dets, sizeof(float) * (size_t)n * 5));
-    B2S_CUDA_OK(cudaMalloc(&d_geo, sizeof(float) * (size_t)n * 12));
-    B2S_CUDA_OK(cudaMemcpy(d_dets, sorted_dets, sizeof(float) * (size_t)n * 5, cudaMemcpyHostToDevice));
-    k_geo_from_dets<<<b2s_cdiv(n, 256), 256>>>(d_dets, n, d_geo);
-    int nk = host_nms_common(d_geo, n, 0, thresh, eps, inclusive, keep_out, 0);
-    cudaFree(d_dets); cudaFree(d_geo);
-    return nk;
+    DeviceScope scope(device_id);
+    B2S_REQUIRE(scope.ok, "b2s_nms_aligned_host: cannot select device %d", device_id);
+    DevBuf dets, geo;
+    B2S_CUDA_OK(dets.alloc(sizeof(float) * (size_t)n * 5));
+    B2S_CUDA_OK(geo.alloc(sizeof(float) * (size_t)n * 12));
+    B2S_CUDA_OK(cudaMemcpy(dets.p, sorted_dets, sizeof(float) * (size_t)n * 5, cudaMemcpyHostToDevice));
+    k_geo_from_dets<<<b2s_cdiv(n, 256), 256>>>(dets.as<float>(), n, geo.as<float>());
+    B2S_LAUNCH_OK();
+    return host_nms_common(geo.as<float>(), n, 0, thresh, eps, inclusive, keep_out, 0);
 }
 
 extern "C" int b2s_nms_rotated_host(const float *corners, const int *order, const float *standup_iou, int n,
@@ -709,19 +792,68 @@ extern "C" int b2s_nms_rotated_host(const float *corners, const int *order, cons
 {
     (void)standup_iou;  // gate recomputed on the device from the corners (same predicate)
     if (n <= 0) return 0;
-    B2S_CUDA_OK(cudaSetDevice(device_id));
-    float *d_c = nullptr, *d_geo = nullptr;
-    int *d_order = nullptr;
-    B2S_CUDA_OK(cudaMalloc(&d_c, sizeof(float) * (size_t)n * 8));
-    B2S_CUDA_OK(cudaMalloc(&d_geo, sizeof(float) * (size_t)n * 12));
-    B2S_CUDA_OK(cudaMalloc(&d_order, sizeof(int) * (size_t)n));
-    B2S_CUDA_OK(cudaMemcpy(d_c, corners, sizeof(float) * (size_t)n * 8, cudaMemcpyHostToDevice));
-    B2S_CUDA_OK(cudaMemcpy(d_order, order, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
-    k_geo_from_corners<<<b2s_cdiv(n, 256), 256>>>(d_c, d_order, n, d_geo);
+    DeviceScope scope(device_id);
+    B2S_REQUIRE(scope.ok, "b2s_nms_rotated_host: cannot select device %d", device_id);
+    DevBuf c, geo, ord;
+    B2S_CUDA_OK(c.alloc(sizeof(float) * (size_t)n * 8));
+    B2S_CUDA_OK(geo.alloc(sizeof(float) * (size_t)n * 12));
+    B2S_CUDA_OK(ord.alloc(sizeof(int) * (size_t)n));
+    B2S_CUDA_OK(cudaMemcpy(c.p, corners, sizeof(float) * (size_t)n * 8, cudaMemcpyHostToDevice));
+    B2S_CUDA_OK(cudaMemcpy(ord.p, order, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice));
+    k_geo_from_corners<<<b2s_cdiv(n, 256), 256>>>(c.as<float>(), ord.as<int>(), n, geo.as<float>());
+    B2S_LAUNCH_OK();
     int *keep_sorted = (int *)malloc(sizeof(int) * (size_t)n);
-    int nk = host_nms_common(d_geo, n, 1, thresh, 0.f, 1, keep_sorted, 0);
+    if (!keep_sorted) { b2s_set_error("b2s_nms_rotated_host: out of host memory"); return -1; }
+    int nk = host_nms_common(geo.as<float>(), n, 1, thresh, 0.f, 1, keep_sorted, 0);
     for (int i = 0; i < nk; ++i) keep_out[i] = order[keep_sorted[i]];  // positions in `order` -> box ids
     free(keep_sorted);
-    cudaFree(d_c); cudaFree(d_geo); cudaFree(d_order);
     return nk;
+}
+
+// Device-resident rotated overlap matrix (the rotate_iou_gpu_eval replacement, nms_gpu.py:569-607): boxes [N,5],
+// query_boxes [K,5] as (x, y, w, l, r); out [N,K].  workspace: (N + K) * 8 floats.
+extern "C" int b2s_rotate_iou_eval(const float *boxes, int N, const float *query_boxes, int K, int criterion, float *out,
+                                   float *workspace, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(N >= 0 && K >= 0 && criterion >= -1 && criterion <= 2, "b2s_rotate_iou_eval: bad arguments");
+    if (N == 0 || K == 0) return 0;
+    float *c = workspace, *qc = workspace + (size_t)N * 8;
+    k_corners_from_rboxes<<<b2s_cdiv(N, 256), 256, 0, stream>>>(boxes, N, c);
+    B2S_LAUNCH_OK();
+    k_corners_from_rboxes<<<b2s_cdiv(K, 256), 256, 0, stream>>>(query_boxes, K, qc);
+    B2S_LAUNCH_OK();
+    long long total = (long long)N * K;
+    int blocks = b2s_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_rbbox_pairs<<<blocks, 256, 0, stream>>>(c, qc, nullptr, N, K, 0.f, criterion, out);
+    B2S_LAUNCH_OK();
+    return 0;
+}
+
+// spconv.utils.rbbox_iou (criterion -1) / rbbox_intersection (criterion 2) with the numpy-facing contract: HOST
+// arrays in and out (second/core/box_np_ops.py:10-34).
+extern "C" int b2s_rbbox_overlap_host(const float *corners, const float *qcorners, const float *standup_iou, int N, int K,
+                                      float standup_thresh, int criterion, float *out, int device_id)
+{
+    if (N <= 0 || K <= 0) return 0;
+    B2S_REQUIRE(criterion >= -1 && criterion <= 2 && standup_iou != nullptr, "b2s_rbbox_overlap_host: bad arguments");
+    DeviceScope scope(device_id);
+    B2S_REQUIRE(scope.ok, "b2s_rbbox_overlap_host: cannot select device %d", device_id);
+    DevBuf c, qc, si, o;
+    B2S_CUDA_OK(c.alloc(sizeof(float) * (size_t)N * 8));
+    B2S_CUDA_OK(qc.alloc(sizeof(float) * (size_t)K * 8));
+    B2S_CUDA_OK(si.alloc(sizeof(float) * (size_t)N * K));
+    B2S_CUDA_OK(o.alloc(sizeof(float) * (size_t)N * K));
+    B2S_CUDA_OK(cudaMemcpy(c.p, corners, sizeof(float) * (size_t)N * 8, cudaMemcpyHostToDevice));
+    B2S_CUDA_OK(cudaMemcpy(qc.p, qcorners, sizeof(float) * (size_t)K * 8, cudaMemcpyHostToDevice));
+    B2S_CUDA_OK(cudaMemcpy(si.p, standup_iou, sizeof(float) * (size_t)N * K, cudaMemcpyHostToDevice));
+    long long total = (long long)N * K;
+    int blocks = b2s_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_rbbox_pairs<<<blocks, 256>>>(c.as<float>(), qc.as<float>(), si.as<float>(), N, K, standup_thresh, criterion,
+                                   o.as<float>());
+    B2S_LAUNCH_OK();
+    B2S_CUDA_OK(cudaMemcpy(out, o.p, sizeof(float) * (size_t)N * K, cudaMemcpyDeviceToHost));
+    return 0;
 }

@@ -371,6 +371,11 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
+    // the input-side scatter enumerates at most ceil(k/s) <= 4 candidate outputs per dimension, which is only
+    // right for dilation 1 (a dilated strided conv can reach more); SECOND never builds one (middle.py:146-189)
+    B2S_REQUIRE(dilation == nullptr || (dilation[0] == 1 && dilation[1] == 1 && dilation[2] == 1) ||
+                    (stride[0] == 1 && stride[1] == 1 && stride[2] == 1),
+                "b2s_rulebook_conv: dilation > 1 combined with stride > 1 is not supported");
     B2S_REQUIRE(fill_geom(&g, in_shape, out_shape, ksize, stride, padding, dilation) == 0,
                 "b2s_rulebook_conv: bad geometry");
     for (int j = 0; j < 3; ++j) {

@@ -2,14 +2,15 @@
 //
 // Same output-stationary formulation as sparse_conv.cu (one CTA owns 128 output rows and walks the K kernel
 // offsets; nbr[o][k] names the input row feeding output row o through offset k), but the per-offset product
-//     D[128 rows, Cout] += A[128 gathered rows, 32 channels] * W[k][Cout, 32 channels]^T
-// is a tcgen05.mma (kind::tf32) on the 3xTF32 hi/lo split (see conv_tc.cu), accumulating in TMEM.
+//     D[128 rows, Cout] += A[128 gathered rows, 64 channels] * W[k][Cout, 64 channels]^T
+// is a tcgen05.mma (kind::f16) on the 3xF16 hi/lo split (tc_common.cuh), accumulating in TMEM.
 //
-// K block = one 128-byte-wide slice of the reduction:
-//   Cin >= 32 : (kernel offset k, 32-channel chunk ch)                      -- K * Cin/32 K blocks per tile
-//   Cin <  32 : PACK = 32/Cin consecutive kernel offsets side by side        -- ceil(K / PACK) K blocks per tile
-//               (Cin = 16: 2 offsets x 16 channels, Cin = 4: 8 offsets x 4 channels; the weights arrive
-//               pre-packed as [K block][Cout][32], see b2second/tc.py: pack_sparse_weights)
+// K block = one 128-byte-wide slice of the reduction (64 fp16 channels):
+//   Cin >= 64 : (kernel offset k, 64-channel chunk ch)                      -- K * Cin/64 K blocks per tile
+//   Cin <  64 : PACK = 64/Cin consecutive kernel offsets side by side        -- ceil(K / PACK) K blocks per tile
+//               (Cin = 32: 2 offsets, 16: 4 offsets, 8: 8 offsets per K block; the weights arrive pre-packed as
+//               [K block][Cout][64], see b2second/tc.py: pack_sparse_weights.  A 3- or 4-feature input layer is
+//               zero-padded to 8 channels = one 16-byte cp.async per row and plane.)
 //
 // Warp roles (16 warps):
 //   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
@@ -29,6 +30,8 @@
 // ~1340 cycles per K block for them although the copies themselves cost 4 %; hoisting everything that is constant
 // per kernel offset, unrolling the channel chunks and doubling the gather warps brought the K block to ~760
 // cycles (tensor pipe 448 of them, tests/cuda/mma_probe2.cu).
+#include <cuda_fp16.h>
+
 #include "tc_common.cuh"
 
 namespace {
@@ -50,29 +53,32 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
 }
 
 struct SpParams {
-    const float *in_hi, *in_lo;
+    const __half *in_hi, *in_lo;
+    int in_stride, out_stride;   // halves between consecutive rows of the input / output planes
+    int *status;
     const int *nbr;
     const int *n_out_dev;
     int cap_out, K, relu;
     int flags;               // B2S_SP_ZSKIP: bit 0 zero-slot skip (default on); diagnostics (wrong results): 2 no gather
                              // copies, 4 no weight loads, 8 no neighbour-table staging; 16 print the issuer's wait times
     const float *scale, *shift;
-    float *out_hi, *out_lo;
+    void *out_hi;                // fp16 hi plane, or (out_lo == NULL) fp32 rows [cap_out, COUT]
+    __half *out_lo;
 };
 
-// CIN in {4, 16, 32, 64}; COUT (= UMMA N) in {16, 32, 64}
+// CIN in {8, 16, 32, 64}; COUT (= UMMA N) in {16, 32, 64}
 template <int CIN, int COUT, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SpParams p)
 {
     constexpr int N = COUT;
-    constexpr bool PACKED = CIN < 32;
-    constexpr int PACK = PACKED ? 32 / CIN : 1;               // kernel offsets per K block
-    constexpr int KCH = PACKED ? 1 : CIN / BLOCK_K;           // 32-channel chunks per offset
+    constexpr bool PACKED = CIN < BLOCK_K;
+    constexpr int PACK = PACKED ? BLOCK_K / CIN : 1;          // kernel offsets per K block
+    constexpr int KCH = PACKED ? 1 : CIN / BLOCK_K;           // 64-channel chunks per offset
     constexpr int CPO = 8 / PACK;                             // 16-byte chunks per offset inside a 128-byte row
     constexpr int CHAIN_KB = PACKED ? 2 : GROUP * KCH;        // K blocks per accumulation chain (short chains)
-    constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * 4;
+    constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * ELEM_BYTES;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     // B-operand concatenation: the stage holds W_hi (N rows) directly followed by W_lo (N rows), so ONE MMA with
     // UMMA N = 2N computes A_hi*W_hi (accumulator columns [0,N)) and A_hi*W_lo (columns [N,2N)); a second MMA
@@ -89,7 +95,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
     __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
-    __shared__ __align__(16) float s_stage[4][32 * 36];      // per epilogue warp: 32 rows x <=32 ch transpose tile
+    __shared__ __align__(16) uint32_t s_stage[4][32 * 36];   // per epilogue warp: 32 rows x 32 words transpose tile
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
@@ -142,7 +148,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         // Software-pipelined single-lane issue: the barriers of the NEXT K block (and, at a chain end, of the next
         // accumulator) are waited for before the current K block's last two MMAs are issued, so the tensor queue
         // does not drain between the short 8-MMA bursts.
-        constexpr uint32_t idesc = make_idesc_tf32(N), idesc2 = make_idesc_tf32(2 * N);
+        constexpr uint32_t idesc = make_idesc_f16(N), idesc2 = make_idesc_f16(2 * N);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t smem0 = smem_u32(smem);
         const int num_tiles_u = __shfl_sync(0xffffffffu, num_tiles, 0);
@@ -171,9 +177,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                         const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
 #pragma unroll
                         for (int kk = 0; kk < 3; ++kk) {
-                            const uint64_t koff = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                            umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
-                            umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
+                            const uint64_t koff = (uint64_t)((kk * UMMA_K * ELEM_BYTES) >> 4);
+                            umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
+                            umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
                         }
                         // look ahead
                         int stn = stage + 1;
@@ -190,9 +196,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                             if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; ++n_kb; }
                         }
                         {
-                            const uint64_t koff = (uint64_t)((3 * UMMA_K * 4) >> 4);
-                            umma_tf32(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
-                            umma_tf32(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
+                            const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
+                            umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
+                            umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
                         }
                         umma_commit(&bar_empty[stage]);
                         if (chain_end) umma_commit(&bar_tfull[acc]);
@@ -287,17 +293,17 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     for (int i = 0; i < RI; ++i) {
                         const int src = s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k];
                         valid |= (src >= 0 ? 1u : 0u) << i;
-                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 4);
+                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * p.in_stride + chunk * 8);
                         g_lo[i] = g_hi[i] + lo_delta;
                     }
 #pragma unroll
-                    for (int ch = 0; ch < KCH; ++ch) copy_block(valid, g_hi, g_lo, ch * (BLOCK_K * 4));
+                    for (int ch = 0; ch < KCH; ++ch) copy_block(valid, g_hi, g_lo, ch * (BLOCK_K * ELEM_BYTES));
                 }
             } else {
                 // PACK offsets side by side: this lane's chunk belongs to offset kb*PACK + chunk/CPO and carries
-                // channels (chunk % CPO)*4 .. +3 of that neighbour's row
+                // channels (chunk % CPO)*8 .. +7 of that neighbour's row
                 const int ko = (int)chunk / CPO;
-                const int cofs = ((int)chunk % CPO) * 4;
+                const int cofs = ((int)chunk % CPO) * 8;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const int k = kb * PACK + ko;
                     const char *g_hi[RI], *g_lo[RI];
@@ -306,7 +312,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     for (int i = 0; i < RI; ++i) {
                         const int src = k < K ? s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k] : -1;
                         valid |= (src >= 0 ? 1u : 0u) << i;
-                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * CIN + cofs);
+                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * p.in_stride + cofs);
                         g_lo[i] = g_hi[i] + lo_delta;
                     }
                     copy_block(valid, g_hi, g_lo, 0);
@@ -345,41 +351,79 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
             }
             // coalesced stores: transpose 32 rows x CW channels through a padded shared tile so every store
-            // instruction writes whole contiguous row segments (a lane-per-row store is 16 B at a row stride)
+            // instruction writes whole contiguous row segments (a lane-per-row store is 16 B at a row stride).
+            // fp16 planes: a staged row = WP words of hi pairs, then (at word 16) WP words of lo pairs; the first CP
+            // lanes of a row group write the hi segment, the next CP lanes the lo segment.
             constexpr int CW = N < 32 ? N : 32;                // channels per pass
-            constexpr int CH4 = CW / 4;                        // 16-byte chunks per row segment
-            constexpr int RPI = 32 / CH4;                      // rows per store instruction
-            float *stg = s_stage[ew];
-            const int sp = lane / CH4, sq = lane % CH4;
+            uint32_t *stg = s_stage[ew];
             const int row_w0 = tile * BLOCK_M + ew * 32;       // first row of this warp
-            const int planes = p.out_lo ? 2 : 1;
-            for (int pl_i = 0; pl_i < planes; ++pl_i) {
-                float *outp = pl_i ? p.out_lo : p.out_hi;
+            bool range_bad = false;
+            if (p.out_lo) {
+                constexpr int WP = CW / 2;                     // words per plane and row
+                constexpr int CP = WP / 4;                     // 16-byte chunks per plane and row
+                constexpr int LPR = 2 * CP;                    // lanes per row
+                constexpr int RPI = 32 / LPR;                  // rows per store instruction
+                const int sp = lane / LPR, sq = lane % LPR;
+                __half *outp = (sq < CP) ? reinterpret_cast<__half *>(p.out_hi) : p.out_lo;
+                const int coff = (sq % CP) * 8;                // first of this lane's 8 channels inside the pass
 #pragma unroll
                 for (int cc = 0; cc < N; cc += CW) {
                     __syncwarp();
 #pragma unroll
-                    for (int c0 = 0; c0 < CW; c0 += 4) {
-                        float v[4];
+                    for (int c0 = 0; c0 < CW; c0 += 8) {
+                        uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            float x = fmaf(sum[cc + c0 + j], s_scale[cc + c0 + j], s_shift[cc + c0 + j]);
-                            if (p.relu) x = fmaxf(x, 0.f);
-                            if (p.out_lo) { float hi = to_tf32_rn(x); x = pl_i ? to_tf32_rn(x - hi) : hi; }
-                            v[j] = x;
+                            float x0 = fmaf(sum[cc + c0 + 2 * j], s_scale[cc + c0 + 2 * j], s_shift[cc + c0 + 2 * j]);
+                            float x1 = fmaf(sum[cc + c0 + 2 * j + 1], s_scale[cc + c0 + 2 * j + 1], s_shift[cc + c0 + 2 * j + 1]);
+                            if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                            range_bad |= (fabsf(x0) > 65504.f) | (fabsf(x1) > 65504.f);
+                            const uint32_t p0 = split_f16(x0), p1 = split_f16(x1);
+                            hw[j] = __byte_perm(p0, p1, 0x5410);
+                            lw[j] = __byte_perm(p0, p1, 0x7632);
                         }
-                        *reinterpret_cast<float4 *>(stg + lane * 36 + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<uint4 *>(stg + lane * 36 + c0 / 2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(stg + lane * 36 + 16 + c0 / 2) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
                     __syncwarp();
 #pragma unroll
                     for (int it = 0; it < 32 / RPI; ++it) {
                         const int rr = row_w0 + it * RPI + sp;
                         if (rr < n_out)
-                            *reinterpret_cast<float4 *>(outp + (size_t)rr * N + cc + sq * 4) =
-                                *reinterpret_cast<const float4 *>(stg + (it * RPI + sp) * 36 + sq * 4);
+                            *reinterpret_cast<uint4 *>(outp + (size_t)rr * p.out_stride + cc + coff) =
+                                *reinterpret_cast<const uint4 *>(stg + (it * RPI + sp) * 36 + (sq < CP ? 0 : 16) + (sq % CP) * 4);
+                    }
+                }
+            } else {
+                constexpr int CH4 = CW / 4;                        // 16-byte chunks per row segment
+                constexpr int RPI = 32 / CH4;                      // rows per store instruction
+                const int sp = lane / CH4, sq = lane % CH4;
+                float *outp = reinterpret_cast<float *>(p.out_hi);
+#pragma unroll
+                for (int cc = 0; cc < N; cc += CW) {
+                    __syncwarp();
+#pragma unroll
+                    for (int c0 = 0; c0 < CW; c0 += 4) {
+                        uint32_t v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x = fmaf(sum[cc + c0 + j], s_scale[cc + c0 + j], s_shift[cc + c0 + j]);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            v[j] = __float_as_uint(x);
+                        }
+                        *reinterpret_cast<uint4 *>(stg + lane * 36 + c0) = make_uint4(v[0], v[1], v[2], v[3]);
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int it = 0; it < 32 / RPI; ++it) {
+                        const int rr = row_w0 + it * RPI + sp;
+                        if (rr < n_out)
+                            *reinterpret_cast<uint4 *>(outp + (size_t)rr * N + cc + sq * 4) =
+                                *reinterpret_cast<const uint4 *>(stg + (it * RPI + sp) * 36 + sq * 4);
                     }
                 }
             }
+            if (__any_sync(0xffffffffu, range_bad) && lane == 0 && p.status) atomicOr(p.status, B2S_STATUS_F16_RANGE);
         }
     }
     tc_fence_before();
@@ -393,14 +437,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
 template <int CIN, int COUT, int STAGES>
 int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
-    constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * 4;
+    constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * ELEM_BYTES;
     size_t smem = stage * STAGES + 1024;
-    static bool attr = false;
-    if (!attr) {
-        B2S_CUDA_OK(cudaFuncSetAttribute(k_sparse_conv_tc<CIN, COUT, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, STAGES>), smem);
     int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles_cap < num_sms ? tiles_cap : num_sms;
     k_sparse_conv_tc<CIN, COUT, STAGES><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
@@ -410,46 +449,58 @@ int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, 
 
 }  // namespace
 
-// Weight layout: Cin >= 32: [K][Cout][Cin]; Cin < 32 (4 or 16): packed [ceil(K / (32/Cin))][Cout][32] with column
+extern "C" int b2s_sparse_conv_tc_supported(int cin, int cout)
+{
+    return (cin == 8 || cin == 16 || cin == 32 || cin == 64) && (cout == 16 || cout == 32 || cout == 64);
+}
+
+// Weight layout: Cin = 64: [K][Cout][64]; Cin < 64 (8, 16, 32): packed [ceil(K / (64/Cin))][Cout][64] with column
 // (offset-in-pack * Cin + cin) and zero columns for offsets >= K (b2second/tc.py: pack_sparse_weights).
-extern "C" int b2s_sparse_conv_tc(const float *feat_hi, const float *feat_lo, int rows_in, int cin, const float *w_hi,
-                                  const float *w_lo, const int *nbr, int K, const int *num_out_dev, int cap_out,
-                                  const float *scale, const float *shift, int relu, float *out_hi, float *out_lo,
-                                  int cout, void *stream_)
+extern "C" int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,
+                                  const b2s_half *w_hi, const b2s_half *w_lo, const int *nbr, int K,
+                                  const int *num_out_dev, int cap_out, const float *scale, const float *shift, int relu,
+                                  void *out_hi, b2s_half *out_lo, int out_stride, int cout, unsigned *status_dev,
+                                  void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B2S_REQUIRE((cin == 4 || cin == 16 || cin == 32 || cin == 64) && (cout == 16 || cout == 32 || cout == 64),
-                "b2s_sparse_conv_tc: built for Cin in {4, 16, 32, 64}, Cout in {16, 32, 64} (others: b2s_sparse_conv)");
+    B2S_REQUIRE(b2s_sparse_conv_tc_supported(cin, cout),
+                "b2s_sparse_conv_tc: built for Cin in {8, 16, 32, 64}, Cout in {16, 32, 64} (others: b2s_sparse_conv)");
     B2S_REQUIRE(K >= 1 && K <= 27 && cap_out >= 0 && rows_in >= 0, "b2s_sparse_conv_tc: K must be 1..27");
+    B2S_REQUIRE(in_stride >= cin && in_stride % 8 == 0 && ((uintptr_t)feat_hi & 15) == 0 && ((uintptr_t)feat_lo & 15) == 0,
+                "b2s_sparse_conv_tc: input rows must be 16-byte aligned (in_stride multiple of 8 halves)");
+    B2S_REQUIRE(out_lo == nullptr || (out_stride >= cout && out_stride % 8 == 0 && ((uintptr_t)out_hi & 15) == 0 &&
+                                      ((uintptr_t)out_lo & 15) == 0),
+                "b2s_sparse_conv_tc: output rows must be 16-byte aligned (out_stride multiple of 8 halves)");
     if (cap_out == 0) return 0;
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        B2S_CUDA_OK(cudaGetDevice(&dev));
-        B2S_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int num_sms = num_sms_current();
     CUtensorMap m_hi, m_lo;
     {
-        const bool packed = cin < 32;
-        const int pack = packed ? 32 / cin : 1;
-        cuuint64_t row = packed ? 32 : (cuuint64_t)cin;          // floats per weight row
+        const bool packed = cin < BLOCK_K;
+        const int pack = packed ? BLOCK_K / cin : 1;
+        cuuint64_t row = packed ? BLOCK_K : (cuuint64_t)cin;     // halves per weight row
         cuuint64_t nkb = packed ? (cuuint64_t)((K + pack - 1) / pack) : (cuuint64_t)K;
         cuuint64_t dims[3] = {row, (cuuint64_t)cout, nkb};
-        cuuint64_t str[2] = {row * 4, (cuuint64_t)cout * row * 4};
+        cuuint64_t str[2] = {row * ELEM_BYTES, (cuuint64_t)cout * row * ELEM_BYTES};
         cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
         if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
     }
     SpParams p;
-    p.in_hi = feat_hi; p.in_lo = feat_lo; p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
+    p.in_hi = reinterpret_cast<const __half *>(feat_hi); p.in_lo = reinterpret_cast<const __half *>(feat_lo);
+    p.in_stride = in_stride; p.out_stride = out_stride; p.status = (int *)status_dev;
+    p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
     {
         static int fl = -1;
         if (fl < 0) { const char *e = getenv("B2S_SP_ZSKIP"); fl = e ? atoi(e) : 1; }
-        p.flags = fl;
+#ifdef B2S_DIAG
+        p.flags = fl;           // bits 2/4/8 corrupt results: only in `make DIAG=1` builds
+#else
+        p.flags = fl & (1 | 16);
+#endif
     }
-    p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo;
+    p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = reinterpret_cast<__half *>(out_lo);
 #define B2S_TC_CASE(CI, CO) if (cin == CI && cout == CO) return launch<CI, CO, 4>(m_hi, m_lo, p, num_sms, stream);
-    B2S_TC_CASE(64, 64) B2S_TC_CASE(32, 64) B2S_TC_CASE(32, 32) B2S_TC_CASE(64, 32) B2S_TC_CASE(16, 16)
-    B2S_TC_CASE(16, 32) B2S_TC_CASE(4, 16) B2S_TC_CASE(16, 64) B2S_TC_CASE(4, 32)
+    B2S_TC_CASE(64, 64) B2S_TC_CASE(64, 32) B2S_TC_CASE(64, 16) B2S_TC_CASE(32, 64) B2S_TC_CASE(32, 32) B2S_TC_CASE(32, 16)
+    B2S_TC_CASE(16, 64) B2S_TC_CASE(16, 32) B2S_TC_CASE(16, 16) B2S_TC_CASE(8, 64) B2S_TC_CASE(8, 32) B2S_TC_CASE(8, 16)
 #undef B2S_TC_CASE
     b2s_set_error("b2s_sparse_conv_tc: Cin=%d Cout=%d not built", cin, cout);
     return -2;

@@ -6,10 +6,18 @@
 
 namespace b2s_tc {
 
+// Operand format ("3xF16"): every fp32 operand x is carried as two fp16 planes, hi = fp16_rn(x) and
+// lo = fp16_rn(x - hi): 22 significand bits while lo is a normal fp16, 2^-25 absolute otherwise (fp16 subnormals are
+// exact operands for the tensor core).  Each K step issues A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in
+// TMEM (the dropped lo*lo term is ~2^-22 relative) -- the same three products as the 3xTF32 split of round 1, but
+// kind::f16 runs at twice the tf32 rate and the planes are half the bytes.  Weights are pre-scaled by a power of two
+// per layer (folded into the epilogue scale) so that their lo plane stays in the normal range
+// (b2second/tc.py: split_f16); activations are stored unscaled (|x| <= 65504, saturating conversion).
 constexpr int BLOCK_M = 128;   // accumulator rows (TMEM lanes)
-constexpr int BLOCK_K = 32;    // 32 fp32 = 128 B = one SWIZZLE_128B row
-constexpr int UMMA_K = 8;      // tf32: 32 bytes per MMA K step
-constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr int BLOCK_K = 64;    // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;     // f16: 32 bytes per MMA K step
+constexpr int ELEM_BYTES = 2;
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * ELEM_BYTES;   // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -92,39 +100,39 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr)
     return d;
 }
 
-// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int n)
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=f16 (format code 0 in bits 7-9 / 10-12), both K-major, M=128, N
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n)
 {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // Two consecutive MMAs that share the A operand: the first keeps A in the tensor core's collector buffer
 // (SASS UTCHMMA ...A_KEEP), the second reads it from there (A_REUSE) instead of fetching it from shared memory again.
-__device__ __forceinline__ void umma_tf32_afill(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_afill(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                 uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_tf32_alast(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_alast(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                 uint32_t accumulate)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+        "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
@@ -145,13 +153,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float to_tf32_rn(float v)
+// fp32 -> (hi, lo) fp16 pair packed in one register: hi in bits 0-15, lo in bits 16-31.  Saturating conversions
+// (a value beyond +-65504 clamps instead of turning into inf and poisoning the accumulators).
+__device__ __forceinline__ uint32_t split_f16(float v)
 {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return __uint_as_float(u);
+    uint16_t h, l;
+    float hf;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    asm("cvt.f32.f16 %0, %1;" : "=f"(hf) : "h"(h));
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l) : "f"(v - hf));
+    return (uint32_t)h | ((uint32_t)l << 16);
+}
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h)
+{
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
 }
 
+
+// ---- host side: per-device caches (a process may drive several GPUs: SM count and the opt-in dynamic shared memory
+// attribute belong to the CURRENT device, so they are cached per device index, not in a process-wide static) ----
+constexpr int kMaxDevices = 64;
+inline int current_device()
+{
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (kMaxDevices - 1);
+}
+inline int num_sms_current()
+{
+    static int sms[kMaxDevices] = {0};
+    const int d = current_device();
+    if (!sms[d]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v <= 0) v = 148;
+        sms[d] = v;
+    }
+    return sms[d];
+}
+// opt a kernel into `bytes` of dynamic shared memory on the current device (once per device and kernel instance)
+#define B2S_SMEM_OPT_IN(kernel, bytes)                                                                           \
+    do {                                                                                                         \
+        static bool _done[b2s_tc::kMaxDevices] = {false};                                                        \
+        const int _d = b2s_tc::current_device();                                                                 \
+        if (!_done[_d]) {                                                                                        \
+            B2S_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+            _done[_d] = true;                                                                                    \
+        }                                                                                                        \
+    } while (0)
 
 // ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -172,7 +222,7 @@ inline PFN_encodeTiled get_encode()
 }
 
 // elem_strides (optional): traversal stride per dimension -- {1, s, s, 1} fetches every s-th pixel (strided conv)
-inline int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_t *dims,
+inline int make_map(CUtensorMap *m, const void *base, int rank, const cuuint64_t *dims,
                     const cuuint64_t *strides_bytes, const cuuint32_t *box, const cuuint32_t *elem_strides = nullptr)
 {
     PFN_encodeTiled enc = get_encode();
@@ -180,7 +230,7 @@ inline int make_map(CUtensorMap *m, const float *base, int rank, const cuuint64_
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (elem_strides)
         for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void *)base, dims, strides_bytes, box, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, (void *)base, dims, strides_bytes, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { b2s_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }

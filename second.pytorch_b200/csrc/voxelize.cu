@@ -255,6 +255,42 @@ __global__ void k_finish(const float *__restrict__ pts, int F, int T, const int 
     }
 }
 
+// SimpleVoxel / SimpleVoxelRadius over voxels that arrive already gathered ([rows, T, F], zero padded): the same
+// sequential fp32 sum in slot order and true division as k_finish
+__global__ void k_vfe_mean(const float *__restrict__ voxels, const int *__restrict__ num, const int *__restrict__ n_dev,
+                           int cap_rows, int T, int F, int vfe_mode, int vfe_nf, float *vfe_out)
+{
+    const int n_rows = min(*n_dev, cap_rows);
+    for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+        const int n = min(num[row], T);
+        float acc[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+        const float *v = voxels + (size_t)row * T * F;
+        for (int t = 0; t < n; ++t) {
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < vfe_nf) acc[f] = __fadd_rn(acc[f], __ldg(&v[(size_t)t * F + f]));
+        }
+        const float fn = (float)n;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < vfe_nf) acc[f] = __fdiv_rn(acc[f], fn);
+        if (vfe_mode == B2S_VFE_MEAN) {
+            float *o = vfe_out + (size_t)row * vfe_nf;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < vfe_nf) o[f] = acc[f];
+        } else {
+            float *o = vfe_out + (size_t)row * (vfe_nf - 1);
+            o[0] = sqrtf(__fadd_rn(__fmul_rn(acc[0], acc[0]), __fmul_rn(acc[1], acc[1])));
+#pragma unroll
+            for (int f = 2; f < 8; ++f)
+                if (f < vfe_nf) o[f - 1] = acc[f];
+        }
+    }
+}
+
 struct VoxWorkspace {
     int *pslot, *first, *rank_local, *block_sums, *frame_rank_start, *frame_row_base;
 };
@@ -355,5 +391,21 @@ extern "C" int b2s_voxelize(const float *points, const int *frame_offsets_dev, i
                                                                         vfe_num_features, vfe_out);
         B2S_LAUNCH_OK();
     }
+    return 0;
+}
+
+extern "C" int b2s_vfe_mean(const float *voxels, const int *num_points_per_voxel, const int *num_rows_dev, int cap_rows,
+                            int T, int F, int vfe_mode, int vfe_num_features, float *vfe_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(vfe_mode == B2S_VFE_MEAN || vfe_mode == B2S_VFE_MEAN_RADIUS, "b2s_vfe_mean: vfe_mode must be 1 or 2");
+    B2S_REQUIRE(T >= 1 && F >= 1 && vfe_num_features >= (vfe_mode == B2S_VFE_MEAN_RADIUS ? 2 : 1) &&
+                vfe_num_features <= 8 && vfe_num_features <= F, "b2s_vfe_mean: bad feature counts");
+    if (cap_rows <= 0) return 0;
+    int blocks = b2s_cdiv(cap_rows, kThreads);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_vfe_mean<<<blocks, kThreads, 0, stream>>>(voxels, num_points_per_voxel, num_rows_dev, cap_rows, T, F, vfe_mode,
+                                                vfe_num_features, vfe_out);
+    B2S_LAUNCH_OK();
     return 0;
 }

@@ -14,6 +14,7 @@ All arithmetic happens in libb2second.so (include/b2second.h).  No CPU fallback:
 CUDA tensors and the library must be built, otherwise calls raise.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -24,6 +25,10 @@ from . import ops  # noqa: F401
 from . import utils  # noqa: F401
 
 __version__ = "1.2.1+b2second"
+
+# sparse convolutions run on the tensor pipe (b2s_sparse_conv_tc, fp32-grade 3xF16 split) where the library covers the
+# channel counts; False / env B2S_SPCONV_TC=0 forces the fp32 FMA kernel (b2s_sparse_conv) everywhere
+USE_TENSOR_CORES = os.environ.get("B2S_SPCONV_TC", "1") != "0"
 
 
 def _pow2_at_least(n):
@@ -37,13 +42,35 @@ class SparseConvTensor:
     """features [N,C] fp32 (CUDA), indices [N,4] int32 (b,z,y,x), spatial_shape (D,H,W), batch_size."""
 
     def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
-        self.features = features
+        self._features = features
+        self._hilo = None   # (hi, lo, row stride in halves): fp16 hi/lo planes of the rows (tensor-core layers)
         self.indices = indices if indices.dtype == torch.int32 else indices.int()
         self.spatial_shape = [int(s) for s in spatial_shape]
         self.batch_size = int(batch_size)
         self.indice_dict = {}
         self.grid = grid
         self._hash = None   # (keys u64-as-int64 [cap], vals int32 [cap], cap)
+
+    # ``features`` is read AND assigned by the reference (resnet.py:54-64).  Layers that run on the tensor pipe keep
+    # their output as fp16 hi/lo planes (the next sparse layer consumes those directly); the fp32 rows are
+    # materialised (hi + lo, exact) only when somebody actually reads ``.features``.
+    @property
+    def features(self):
+        if self._features is None and self._hilo is not None:
+            hi, lo, stride = self._hilo
+            n, c = hi.shape
+            out = torch.empty(n, c, dtype=torch.float32, device=hi.device)
+            if n > 0:
+                lib = _lib.load()
+                _lib.check(lib.b2s_merge_f16(_lib.ptr(hi), _lib.ptr(lo), _lib.ptr(out), None, n, c, stride,
+                                             _lib.stream()), "b2s_merge_f16")
+            self._features = out
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._features = value
+        self._hilo = None
 
     @property
     def spatial_size(self):
@@ -74,9 +101,10 @@ class SparseConvTensor:
         return self._hash
 
     def dense(self, channels_first=True):
-        _lib.require_cuda(self.features, "SparseConvTensor.features")
+        feats = self.features
+        _lib.require_cuda(feats, "SparseConvTensor.features")
         lib = _lib.load()
-        feats = self.features.contiguous().float()
+        feats = feats.contiguous().float()
         idx = self.indices.contiguous()
         n, C = feats.shape
         D, H, W = self.spatial_shape
@@ -111,11 +139,18 @@ def is_spconv_module(module):
 
 
 def _fold_bn(bn):
-    """eval-mode BatchNorm1d -> per-channel (scale, shift)."""
-    w = bn.weight if bn.weight is not None else torch.ones_like(bn.running_mean)
-    b = bn.bias if bn.bias is not None else torch.zeros_like(bn.running_mean)
-    scale = (w / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
-    shift = (b - bn.running_mean * scale).float().contiguous()
+    """eval-mode BatchNorm1d -> per-channel (scale, shift); cached on the module until a parameter/buffer changes."""
+    ts = [t for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var) if t is not None]
+    key = tuple((t.data_ptr(), t._version) for t in ts)
+    cached = getattr(bn, "_b2s_folded", None)
+    if cached is not None and cached[0] == key:
+        return cached[1], cached[2]
+    with torch.no_grad():
+        w = bn.weight if bn.weight is not None else torch.ones_like(bn.running_mean)
+        b = bn.bias if bn.bias is not None else torch.zeros_like(bn.running_mean)
+        scale = (w / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+        shift = (b - bn.running_mean * scale).float().contiguous()
+    bn._b2s_folded = (key, scale, shift)
     return scale, shift
 
 
@@ -224,12 +259,35 @@ class SparseConvolution(SparseModule):
             bound = 1 / math.sqrt(fan_in)
             nn.init.uniform_(self.bias, -bound, bound)
 
+    def _tc_weights(self, cin_tc):
+        """fp16 hi/lo planes of the (power-of-two scaled) weight in the tensor-core kernel's layout; cached until the
+        parameter changes."""
+        from b2second import tc as _tc
+        w = self.weight
+        key = (w.data_ptr(), w._version, str(w.device))
+        cached = getattr(self, "_b2s_tc_w", None)
+        if cached is None or cached[0] != key:
+            K = int(np.prod(self.kernel_size))
+            with torch.no_grad():
+                wp = _tc.pack_sparse_weights(w.detach().float().contiguous().view(K, self.in_channels,
+                                                                                 self.out_channels))
+                ws = _tc.pow2_scale(wp)
+                hi, lo = _tc.split_f16(wp, ws)
+                inv = torch.full((self.out_channels,), 1.0 / ws, dtype=torch.float32, device=w.device)
+            cached = (key, hi, lo, ws, inv)
+            self._b2s_tc_w = cached
+        return cached[1:]
+
     def forward(self, input, _epilogue=None):
         assert isinstance(input, SparseConvTensor)
-        _lib.require_cuda(input.features, "SparseConvTensor.features")
+        if self.training:
+            # upstream implements indice_conv_backward; this drop-in covers the inference path only (SURVEY.md §8(f)4).
+            # Failing here beats silently returning zero gradients for the middle extractor.  (eval() with autograd
+            # enabled is the reference's own inference mode -- voxelnet.py:368-374 -- and runs; the outputs simply
+            # carry no grad_fn.)
+            raise NotImplementedError("b2second spconv: training / autograd through sparse convolutions is not "
+                                      "implemented (inference drop-in); call net.eval() and run under torch.no_grad()")
         lib = _lib.load()
-        feats = input.features.contiguous().float()
-        dev = feats.device
         K = int(np.prod(self.kernel_size))
         # a 1x1x1 stride-1 conv keeps the active set (upstream short-circuits it to a plain mm)
         subm = self.subm or (self.conv1x1 and all(s == 1 for s in self.stride) and all(p == 0 for p in self.padding))
@@ -245,21 +303,60 @@ class SparseConvolution(SparseModule):
             rb = ops.build_rulebook(input, self.kernel_size, self.stride, self.padding, self.dilation, subm)
             input.indice_dict[self.indice_key] = rb
         n_out = rb.num_out
-        out_feats = torch.empty(n_out, self.out_channels, dtype=torch.float32, device=dev)
+        dev = input.indices.device
         if _epilogue is not None:
             scale, shift, relu = _epilogue
         else:
-            scale, shift, relu = None, (self.bias.float().contiguous() if self.bias is not None else None), False
+            scale, shift, relu = None, (self.bias.detach().float().contiguous() if self.bias is not None else None), False
+        out = SparseConvTensor(None, rb.out_indices, out_shape, input.batch_size)
+        out._hash = rb.out_hash
+        out.indice_dict = input.indice_dict
+        out.grid = input.grid
+        from b2second import tc as _tc
+        cin_tc = _tc.sparse_tc_cin(self.in_channels)
+        use_tc = (USE_TENSOR_CORES and cin_tc is not None
+                  and bool(lib.b2s_sparse_conv_tc_supported(cin_tc, self.out_channels)))
+        if use_tc:
+            # tensor pipe (tcgen05, 3xF16 split): fp16 hi/lo rows in, fp16 hi/lo rows out
+            if input._hilo is not None and input._hilo[0].shape[1] == cin_tc:
+                hi, lo, stride = input._hilo
+            else:
+                feats = input.features
+                _lib.require_cuda(feats, "SparseConvTensor.features")
+                feats = feats.contiguous().float()
+                n_in = feats.shape[0]
+                buf = torch.empty(max(n_in, 1), 2, cin_tc, dtype=torch.float16, device=dev)
+                hi, lo, stride = buf[:, 0], buf[:, 1], 2 * cin_tc
+                if n_in > 0:
+                    _lib.check(lib.b2s_split_f16(_lib.ptr(feats), _lib.ptr(hi), _lib.ptr(lo), None, n_in,
+                                                 self.in_channels, stride, _lib.stream()), "b2s_split_f16")
+                input._hilo = (hi[:n_in], lo[:n_in], stride)
+            w_hi, w_lo, ws, inv = self._tc_weights(cin_tc)
+            scale_tc = inv if scale is None else (scale / ws).contiguous()
+            obuf = torch.empty(max(n_out, 1), 2, self.out_channels, dtype=torch.float16, device=dev)
+            o_hi, o_lo = obuf[:, 0], obuf[:, 1]
+            if n_out > 0:
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                _lib.check(lib.b2s_sparse_conv_tc(
+                    _lib.ptr(hi), _lib.ptr(lo), stride, hi.shape[0], cin_tc, _lib.ptr(w_hi), _lib.ptr(w_lo),
+                    _lib.ptr(rb.nbr), K, _lib.ptr(rb.num_out_dev), n_out, _lib.ptr(scale_tc), _lib.ptr(shift),
+                    1 if relu else 0, _lib.ptr(o_hi), _lib.ptr(o_lo), 2 * self.out_channels, self.out_channels,
+                    _lib.ptr(status), _lib.stream()), "b2s_sparse_conv_tc")
+                out._status = status
+            out._hilo = (o_hi[:n_out], o_lo[:n_out], 2 * self.out_channels)
+            out._keep = obuf
+            return out
+        feats = input.features
+        _lib.require_cuda(feats, "SparseConvTensor.features")
+        feats = feats.contiguous().float()
+        out_feats = torch.empty(n_out, self.out_channels, dtype=torch.float32, device=dev)
         w = self.weight.detach().float().contiguous().view(K, self.in_channels, self.out_channels)
         if n_out > 0:
             _lib.check(lib.b2s_sparse_conv(_lib.ptr(feats), self.in_channels, _lib.ptr(w), _lib.ptr(rb.nbr), K,
                                            _lib.ptr(rb.num_out_dev), n_out, _lib.ptr(scale), _lib.ptr(shift),
                                            1 if relu else 0, _lib.ptr(out_feats), self.out_channels,
                                            _lib.stream()), "b2s_sparse_conv")
-        out = SparseConvTensor(out_feats, rb.out_indices, out_shape, input.batch_size)
-        out._hash = rb.out_hash
-        out.indice_dict = input.indice_dict
-        out.grid = input.grid
+        out._features = out_feats
         return out
 
 

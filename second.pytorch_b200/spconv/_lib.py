@@ -44,25 +44,29 @@ SIGNATURES = {
     "b2s_decode_filter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_int, c_void_p, c_void_p]),
-    "b2s_sparse_conv_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                   c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
-    "b2s_split_tf32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "b2s_merge_hilo": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
-    "b2s_to_bev_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                              c_void_p, c_void_p]),
+    "b2s_sparse_conv_tc_supported": (c_int, [c_int, c_int]),
+    "b2s_sparse_conv_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b2s_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2s_merge_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2s_to_bev_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_void_p, c_void_p, c_void_p]),
     "b2s_conv2d_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
-                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+                              c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b2s_conv2d_tc_ex": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b2s_decode_filter_strided": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, ctypes.c_longlong,
                                           ctypes.c_longlong, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                           c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_nms_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b2s_nms": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                        c_int, c_float, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                        c_int, c_float, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                         c_size_t, c_void_p]),
+    "b2s_vfe_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b2s_rotate_iou_eval": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2s_rbbox_overlap_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_int]),
     "b2s_nms_aligned_host": (c_int, [c_void_p, c_int, c_float, c_float, c_int, c_void_p, c_int]),
     "b2s_nms_rotated_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_int]),
 }
@@ -83,7 +87,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b2s_version() < 100:
+    if lib.b2s_version() < 200:
         raise ImportError("libb2second.so is too old")
     _lib = lib
     return lib
@@ -125,7 +129,8 @@ def require_cuda(t, name):
 
 STATUS_BITS = {1: "voxel overflow (more voxels than max_voxels; extra voxels dropped as upstream does)",
                2: "row overflow (strided conv produced more rows than the buffer capacity)",
-               4: "hash table full", 8: "candidate overflow (more score survivors than cand_cap)"}
+               4: "hash table full", 8: "candidate overflow (more score survivors than cand_cap)",
+               16: "an activation left the fp16 range (|x| > 65504) on the tensor-core path"}
 
 
 def status_message(word):

@@ -5,7 +5,8 @@
   non_max_suppression               second/core/non_max_suppression/nms_gpu.py:10-19
   non_max_suppression_cpu           second/core/non_max_suppression/nms_cpu.py:14-17
   rotate_non_max_suppression_cpu    nms_cpu.py:20-31
-  rbbox_iou / rbbox_intersection    second/core/box_np_ops.py:10-34 (training / eval only)
+  rbbox_iou / rbbox_intersection    second/core/box_np_ops.py:10-34 (target assignment / eval)
+  rotate_iou_eval                   device-resident counterpart of nms_gpu.py:569-607 ``rotate_iou_gpu_eval``
 
 The numpy signatures are kept (host arrays in, host arrays out); the work runs on the GPU.  The
 device-resident fast path (points already on the GPU, no host round trip) is ``generate_device``.
@@ -162,7 +163,8 @@ def non_max_suppression_cpu(boxes, order, thresh, eps=0.0):
         return []
     sorted_dets = np.ascontiguousarray(boxes[order])
     keep = np.zeros(n, dtype=np.int32)
-    k = _lib.check(lib.b2s_nms_aligned_host(_as_ptr(sorted_dets), n, float(thresh), float(eps), 1, _as_ptr(keep), 0),
+    # device -1 = the caller's current CUDA device (upstream's *_cpu functions take no device argument)
+    k = _lib.check(lib.b2s_nms_aligned_host(_as_ptr(sorted_dets), n, float(thresh), float(eps), 1, _as_ptr(keep), -1),
                    "b2s_nms_aligned_host")
     return order[keep[:k]].tolist()
 
@@ -179,14 +181,48 @@ def rotate_non_max_suppression_cpu(box_corners, order, standup_iou, thresh):
     ident = np.arange(n, dtype=np.int32)
     siou = np.ascontiguousarray(standup_iou, dtype=np.float32)     # gate is recomputed on the device
     k = _lib.check(lib.b2s_nms_rotated_host(_as_ptr(sorted_corners), _as_ptr(ident), _as_ptr(siou), n, float(thresh),
-                                            _as_ptr(keep), 0), "b2s_nms_rotated_host")
+                                            _as_ptr(keep), -1), "b2s_nms_rotated_host")
     return order[keep[:k]].tolist()
 
 
+def _rbbox(box_corners, qbox_corners, standup_iou, standup_thresh, criterion):
+    lib = _lib.load()
+    box_corners = np.ascontiguousarray(box_corners, dtype=np.float32).reshape(-1, 4, 2)
+    qbox_corners = np.ascontiguousarray(qbox_corners, dtype=np.float32).reshape(-1, 4, 2)
+    n, k = box_corners.shape[0], qbox_corners.shape[0]
+    standup_iou = np.ascontiguousarray(standup_iou, dtype=np.float32).reshape(n, k)
+    out = np.zeros((n, k), dtype=np.float32)
+    if n and k:
+        _lib.check(lib.b2s_rbbox_overlap_host(_as_ptr(box_corners), _as_ptr(qbox_corners), _as_ptr(standup_iou), n, k,
+                                              float(standup_thresh), int(criterion), _as_ptr(out), -1),
+                   "b2s_rbbox_overlap_host")
+    return out
+
+
 def rbbox_iou(box_corners, qbox_corners, standup_iou, standup_thresh):
-    raise NotImplementedError("rbbox_iou is used by training/eval only (box_np_ops.py:10-34): out of the "
-                              "inference hot path (SURVEY.md §8b); importable so the reference imports succeed")
+    """rotated IoU of every (box, query) pair whose stand-up IoU exceeds ``standup_thresh`` (0 elsewhere):
+    second/core/box_np_ops.py:10-20 ``riou_cc`` -> region_similarity.py:70."""
+    return _rbbox(box_corners, qbox_corners, standup_iou, standup_thresh, -1)
 
 
 def rbbox_intersection(box_corners, qbox_corners, standup_iou, standup_thresh):
-    raise NotImplementedError("rbbox_intersection is used by training/eval only: out of the inference hot path")
+    """rotated intersection AREA (box_np_ops.py:23-34 ``rinter_cc``; second/utils/eval.py:174-175 uses it
+    interchangeably with ``rotate_iou_gpu_eval(..., criterion=2)`` = area_inter, nms_gpu.py:553-566)."""
+    return _rbbox(box_corners, qbox_corners, standup_iou, standup_thresh, 2)
+
+
+def rotate_iou_eval(boxes, query_boxes, criterion=-1):
+    """device-resident ``rotate_iou_gpu_eval`` (nms_gpu.py:569-607): CUDA tensors [N,5] / [K,5] (x, y, w, l, r)
+    -> CUDA tensor [N,K]; criterion -1 IoU, 0 inter/area(box), 1 inter/area(query), 2 intersection area."""
+    _lib.require_cuda(boxes, "boxes")
+    _lib.require_cuda(query_boxes, "query_boxes")
+    lib = _lib.load()
+    b = boxes.contiguous().float()
+    q = query_boxes.contiguous().float()
+    n, k = b.shape[0], q.shape[0]
+    out = torch.zeros(n, k, dtype=torch.float32, device=b.device)
+    if n and k:
+        ws = torch.empty((n + k) * 8, dtype=torch.float32, device=b.device)
+        _lib.check(lib.b2s_rotate_iou_eval(_lib.ptr(b), n, _lib.ptr(q), k, int(criterion), _lib.ptr(out), _lib.ptr(ws),
+                                           _lib.stream()), "b2s_rotate_iou_eval")
+    return out

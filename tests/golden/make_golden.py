@@ -18,13 +18,26 @@ sys.path.insert(0, os.path.join(REPO, "second.pytorch_b200"))
 
 from b2second import config, models, refcompat, synth  # noqa: E402
 
-CASES = [  # (config name, cloud kind, seed, num_points)
+CASES = [  # (config name, cloud kind, seed, num_points[, max_voxels override])
     ("car.fhd", "kitti", 0, 20000),
     ("car.fhd", "kitti", 1, 29000),
+    ("car.fhd", "kitti", 2, 24000),
     ("car.lite", "kitti", 0, 20000),
+    ("car.lite", "kitti", 1, 29000),
+    ("car.lite", "kitti", 2, 12000),
     ("all.fhd", "kitti", 0, 20000),
+    ("all.fhd", "kitti", 1, 29000),
+    ("all.fhd", "kitti", 2, 12000),
     ("pointpillars.car.xyres_16", "kitti", 0, 20000),
+    ("pointpillars.car.xyres_16", "kitti", 1, 29000),
+    ("pointpillars.car.xyres_16", "kitti", 2, 12000),
     ("nuscenes.all.pp.largea", "nuscenes", 0, 60000),
+    ("nuscenes.all.pp.largea", "nuscenes", 1, 120000),
+    # BASELINE config 5 size: 10 merged sweeps, ~300 k points per frame
+    ("nuscenes.all.pp.largea", "nuscenes", 2, 300000),
+    # more voxels than max_voxels: the extra voxels are dropped in first-come order (spconv semantics)
+    ("car.fhd", "kitti", 3, 29000, 9000),
+    ("pointpillars.car.xyres_16", "kitti", 3, 20000, 3000),
 ]
 
 
@@ -42,7 +55,13 @@ def main():
     import torch
     refcompat.install(os.path.join(REPO, "oracle", "spconv_cpu"))
     torch.set_num_threads(8)
-    for name, kind, seed, npts in CASES:
+    force = "--force" in sys.argv
+    for case in CASES:
+        name, kind, seed, npts = case[:4]
+        max_voxels = case[4] if len(case) > 4 else None
+        path = os.path.join(HERE, "%s.seed%d.n%d%s.npz" % (name, seed, npts, ".mv%d" % max_voxels if max_voxels else ""))
+        if os.path.exists(path) and not force:
+            continue
         cfgp = refcompat.load_config(config.REFERENCE_FILES[name])
         mcfg = cfgp.model.second
         net = refcompat.build_network(mcfg).eval()
@@ -50,7 +69,7 @@ def main():
         anchors = refcompat.generate_anchors(net, mcfg)
         b = config.get_config(name)
         pts = make_cloud(kind, seed, npts, b.point_cloud_range)
-        res = net.voxel_generator.generate(pts, b.max_voxels)
+        res = net.voxel_generator.generate(pts, max_voxels or b.max_voxels)
         coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
         ex = {"anchors": torch.from_numpy(anchors[None]), "voxels": torch.from_numpy(res["voxels"]),
               "num_points": torch.from_numpy(res["num_points_per_voxel"]), "coordinates": torch.from_numpy(coords)}
@@ -72,6 +91,7 @@ def main():
         sel_nz = nz[np.random.default_rng(1).choice(nz.size, min(256, nz.size), replace=False)]
         fix = {
             "points_sha1": sha(pts), "num_points": pts.shape[0], "voxel_num": res["voxel_num"],
+            "max_voxels": int(max_voxels or b.max_voxels),
             "coords_sha1": sha(res["coordinates"]), "num_points_per_voxel_sha1": sha(res["num_points_per_voxel"]),
             "voxels_sha1": sha(res["voxels"]), "coords_head": res["coordinates"][:64],
             "vfe_sum": float(vf.double().sum()), "vfe_abs": float(vf.double().abs().sum()),
@@ -87,7 +107,6 @@ def main():
             "num_pass_threshold": int((torch.sigmoid(pd["cls_preds"]).reshape(-1, b.num_class).max(1)[0]
                                        >= b.nms_score_threshold).sum()),
         }
-        path = os.path.join(HERE, "%s.seed%d.n%d.npz" % (name, seed, npts))
         np.savez_compressed(path, **fix)
         print(name, seed, npts, "voxels", res["voxel_num"], "pass", fix["num_pass_threshold"], "dets",
               out["box3d_lidar"].shape[0], "->", os.path.basename(path), os.path.getsize(path), "bytes")

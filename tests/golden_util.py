@@ -11,12 +11,18 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def cases():
+    """(config name, seed, num_points, fixture path); fixtures named <config>.seed<S>.n<P>[.mv<max_voxels>].npz"""
+    import re
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
-        base = os.path.basename(p)[:-4]
-        name, seed, n = base.rsplit(".", 2)
-        out.append((name, int(seed[4:]), int(n[1:]), p))
+        m = re.match(r"^(.*)\.seed(\d+)\.n(\d+)(?:\.mv(\d+))?$", os.path.basename(p)[:-4])
+        out.append((m.group(1), int(m.group(2)), int(m.group(3)), p))
     return out
+
+
+def max_voxels_of(fix, name):
+    """the voxel cap the fixture was generated with (older fixtures: the config's own)."""
+    return int(fix["max_voxels"]) if "max_voxels" in fix else config.get_config(name).max_voxels
 
 
 def sha(a):

@@ -46,7 +46,10 @@ def _worker(rank, world, port, B, post_max, stride, q):
         for i in range(gidx + 1):
             det[lb, i, 0] = 100 * gidx + i
     d_all, c_all = g.gather(det, cnt)
+    # the engine's record layout (detections followed by the count as a float) goes out without a packing step
+    d_rec, c_rec = g.gather_records(b2dist.pack_records(det, cnt))
     ok = c_all.tolist() == [i + 1 for i in range(world * B)]
+    ok &= bool(torch.equal(d_rec, d_all)) and bool(torch.equal(c_rec, c_all))
     for gidx in range(world * B):
         for i in range(gidx + 1):
             ok &= float(d_all[gidx, i, 0]) == 100 * gidx + i

@@ -16,7 +16,7 @@ def test_fixtures_present():
     assert {"car.fhd", "car.lite", "all.fhd", "pointpillars.car.xyres_16", "nuscenes.all.pp.largea"} <= names
 
 
-@pytest.mark.parametrize("name,seed,n,path", CASES, ids=[f"{c[0]}-s{c[1]}" for c in CASES])
+@pytest.mark.parametrize("name,seed,n,path", CASES, ids=[f"{c[0]}-s{c[1]}-n{c[2]}" for c in CASES])
 def test_mirror_on_oracle_reproduces_reference_golden(oracle, name, seed, n, path):
     fix = np.load(path)
     cfg = config.get_config(name)
@@ -26,7 +26,7 @@ def test_mirror_on_oracle_reproduces_reference_golden(oracle, name, seed, n, pat
     models.synthetic_weights_(net, name, seed=0)
     anchors = net.anchors()
     assert gu.sha(anchors) == str(fix["anchors_sha1"]) and anchors.shape[0] == int(fix["num_anchors"])
-    res = net.voxel_generator.generate(pts, cfg.max_voxels)
+    res = net.voxel_generator.generate(pts, gu.max_voxels_of(fix, name))
     assert res["voxel_num"] == int(fix["voxel_num"])
     assert gu.sha(res["coordinates"]) == str(fix["coords_sha1"])
     assert gu.sha(res["voxels"]) == str(fix["voxels_sha1"])

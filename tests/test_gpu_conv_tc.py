@@ -1,5 +1,5 @@
-"""GPU parity of the tensor-core RPN convolution (b2s_conv2d_tc, tcgen05 + 3xTF32 split) against torch fp32
-conv2d with TF32 disabled.  Bar: fp32-grade accuracy, |err| <= 2e-5 * max|ref| (plain TF32 would be ~1e-3)."""
+"""GPU parity of the tensor-core RPN convolution (b2s_conv2d_tc, tcgen05 kind::f16 + 3xF16 hi/lo split) against torch
+fp32 conv2d with TF32 disabled.  Bar: fp32-grade accuracy, |err| <= 2e-5 * max|ref| (plain fp16/TF32 would be ~1e-3)."""
 import ctypes
 
 import numpy as np
@@ -20,15 +20,20 @@ def run_tc(product, x, w_tco_ci, taps, cout, n_pad, scale, shift, relu, out_padd
     L = product._lib
     lib = L.load()
     B, C, H, W = x.shape
-    hi, lo = tc.split_tf32(pad_nhwc(x))
-    w_hi, w_lo = tc.split_tf32(tc._pad_rows(w_tco_ci, n_pad))
+    hi, lo = tc.split_f16(pad_nhwc(x))
+    wp = tc._pad_rows(w_tco_ci, n_pad)
+    ws = tc.pow2_scale(wp)                                    # power-of-two weight pre-scale, undone by `scale`
+    w_hi, w_lo = tc.split_f16(wp, ws)
+    scale_k = ((scale if scale is not None else torch.ones(cout, device="cuda")) / ws).contiguous()
     shape = (B, H + 2, W + 2, out_stride) if out_padded else (B, H, W, out_stride)
-    o_hi = torch.zeros(shape, device="cuda")
-    o_lo = torch.zeros(shape, device="cuda") if want_lo else None
+    o_hi = torch.zeros(shape, device="cuda", dtype=torch.float16 if want_lo else torch.float32)
+    o_lo = torch.zeros(shape, device="cuda", dtype=torch.float16) if want_lo else None
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
     L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, C, L.ptr(w_hi), L.ptr(w_lo), taps, cout, n_pad,
-                              L.ptr(scale), L.ptr(shift), 1 if relu else 0, L.ptr(o_hi), L.ptr(o_lo),
-                              1 if out_padded else 0, out_stride, L.stream()), "b2s_conv2d_tc")
+                              L.ptr(scale_k), L.ptr(shift), 1 if relu else 0, L.ptr(o_hi), L.ptr(o_lo),
+                              1 if out_padded else 0, out_stride, L.ptr(status), L.stream()), "b2s_conv2d_tc")
     torch.cuda.synchronize()
+    assert int(status.item()) == 0
     return o_hi, o_lo
 
 
@@ -40,8 +45,8 @@ def _fp32():
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 16, 32, 128), (2, 24, 40, 128, 128), (1, 200, 176, 128, 128),
-                                            (1, 16, 32, 64, 64)])
+@pytest.mark.parametrize("B,H,W,cin,cout", [(1, 8, 16, 64, 128), (2, 24, 40, 128, 128), (1, 200, 176, 128, 128),
+                                            (1, 16, 32, 64, 64), (3, 35, 21, 256, 128), (1, 16, 16, 64, 32)])
 def test_conv3x3_bn_relu(product, B, H, W, cin, cout):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
     x = torch.randn(B, cin, H, W, device="cuda", generator=g)
@@ -50,15 +55,15 @@ def test_conv3x3_bn_relu(product, B, H, W, cin, cout):
     shift = torch.randn(cout, device="cuda", generator=g) * 0.1
     ref = torch.relu(F.conv2d(x, w, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
     wt = w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()
-    n_pad = 128 if cout > 64 else 64
+    n_pad = 128 if cout > 64 else (64 if cout > 32 else 32)
     o_hi, o_lo = run_tc(product, x, wt, 9, cout, n_pad, scale, shift, True, True, cout)
-    got = (o_hi + o_lo)[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
+    got = (o_hi.float() + o_lo.float())[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2)
     err = (got - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item(), "max err %g (ref max %g)" % (err, ref.abs().max().item())
-    # halo untouched (stays zero) and hi is exactly tf32-representable
-    assert float(o_hi[:, 0].abs().sum() + o_hi[:, -1].abs().sum() + o_hi[:, :, 0].abs().sum()
-                 + o_hi[:, :, -1].abs().sum()) == 0.0
-    assert int((o_hi.view(torch.int32) & 0x1FFF).abs().sum()) == 0
+    # halo untouched (stays zero); hi is the fp16 rounding of the value and lo the fp16 rounding of the rest
+    assert float(o_hi[:, 0].float().abs().sum() + o_hi[:, -1].float().abs().sum() + o_hi[:, :, 0].float().abs().sum()
+                 + o_hi[:, :, -1].float().abs().sum()) == 0.0
+    assert torch.equal(got.half().float(), o_hi.float()[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2))
 
 
 @pytest.mark.timeout(120)
@@ -71,6 +76,7 @@ def test_conv1x1_heads_packed(product):
     ref = F.conv2d(x, w, bias)
     wt = w[:, :, 0, 0].unsqueeze(0).contiguous()
     o, _ = run_tc(product, x, wt, 1, cout, 32, None, bias, False, False, 32, want_lo=False)
+    assert o.dtype == torch.float32
     got = o[..., :cout].permute(0, 3, 1, 2)
     err = (got - ref).abs().max().item()
     assert err <= 2e-5 * ref.abs().max().item(), "max err %g" % err
@@ -83,26 +89,30 @@ def run_rpn_plan(product, plan, x_nchw):
     L = product._lib
     lib = L.load()
     B = x_nchw.shape[0]
-    bufs = {"in": tc.split_tf32(pad_nhwc(x_nchw))}
+    bufs = {"in": tc.split_f16(pad_nhwc(x_nchw))}
     for name, (h, w, c) in plan["buffers"].items():
-        bufs[name] = (torch.zeros(B, h + 2, w + 2, c, device="cuda"), torch.zeros(B, h + 2, w + 2, c, device="cuda"))
+        bufs[name] = (torch.zeros(B, h + 2, w + 2, c, device="cuda", dtype=torch.float16),
+                      torch.zeros(B, h + 2, w + 2, c, device="cuda", dtype=torch.float16))
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
     hd = plan["heads"]
     heads = torch.zeros(B, hd["H"], hd["W"], hd["stride"], device="cuda")
     bufs["heads"] = (heads, None)
     keep = []
     for op in plan["ops"]:
         src, dst = bufs[op["src"]], bufs[op["dst"]]
-        o_hi = ctypes.c_void_p(dst[0].data_ptr() + 4 * op["dst_coff"])
-        o_lo = ctypes.c_void_p(dst[1].data_ptr() + 4 * op["dst_coff"]) if op["planes"] == 2 else None
+        esz = dst[0].element_size()
+        o_hi = ctypes.c_void_p(dst[0].data_ptr() + esz * op["dst_coff"])
+        o_lo = ctypes.c_void_p(dst[1].data_ptr() + esz * op["dst_coff"]) if op["planes"] == 2 else None
         keep.append((op["scale"], op["shift"]))
         L.check(lib.b2s_conv2d_tc_ex(
             L.ptr(src[0]), L.ptr(src[1]), B, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]), L.ptr(op["w_lo"]),
             op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
-            L.ptr(op["scale"]) if op["scale"] is not None else None,
+            L.ptr(op["scale"]),
             L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi, o_lo,
             op["Hout"], op["Wout"], 1 if op["padded"] else 0, dst[0].shape[-1], op["out_mul"], op["off_h"], op["off_w"],
-            L.stream()), "b2s_conv2d_tc_ex")
+            L.ptr(status), L.stream()), "b2s_conv2d_tc_ex")
     torch.cuda.synchronize()
+    assert int(status.item()) == 0
     return heads
 
 
@@ -135,3 +145,27 @@ def test_rpn_program_matches_torch(product, name, H, W):
     assert err <= 1e-4 * max(1.0, ref.abs().max().item()), "head tensors differ by %g (bar 1e-4 on the regression outputs)" % err
     offs = plan["heads"]["offsets"]
     assert offs[-1] == n and offs[0] == 0
+
+
+@pytest.mark.timeout(120)
+def test_fp16_range_guard_raises_status(product):
+    """an activation beyond the fp16 range is clamped and reported (B2S_STATUS_F16_RANGE), never turned into inf."""
+    from b2second import tc
+    L = product._lib
+    lib = L.load()
+    B, H, W, cin, cout = 1, 16, 16, 64, 128
+    x = torch.full((B, cin, H, W), 30.0, device="cuda")
+    w = torch.full((cout, cin, 3, 3), 8.0, device="cuda")          # 64 * 9 * 30 * 8 = 138240 > 65504
+    wt = w.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous()
+    hi, lo = tc.split_f16(pad_nhwc(x))
+    ws = tc.pow2_scale(wt)
+    w_hi, w_lo = tc.split_f16(wt, ws)
+    scale = torch.full((cout,), 1.0 / ws, device="cuda")
+    o_hi = torch.zeros(B, H + 2, W + 2, cout, device="cuda", dtype=torch.float16)
+    o_lo = torch.zeros_like(o_hi)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, cin, L.ptr(w_hi), L.ptr(w_lo), 9, cout, 128, L.ptr(scale),
+                              None, 0, L.ptr(o_hi), L.ptr(o_lo), 1, cout, L.ptr(status), L.stream()), "b2s_conv2d_tc")
+    torch.cuda.synchronize()
+    assert int(status.item()) & 16
+    assert bool(torch.isfinite(o_hi.float()).all()) and float(o_hi.float().max()) == 65504.0

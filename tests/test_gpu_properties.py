@@ -110,18 +110,21 @@ def test_sparse_conv_tc_linearity_full_size(product, cin, cout):
     rb = product.ops.build_rulebook(x, [3, 3, 3], [1, 1, 1], [1, 1, 1], [1, 1, 1], True)
     n = rb.num_out
     w = torch.randn(27, cin, cout, device="cuda") * 0.1
-    w_hi, w_lo = tc.split_tf32(tc.pack_sparse_weights(w))
+    wp = tc.pack_sparse_weights(w)
+    ws = tc.pow2_scale(wp)
+    w_hi, w_lo = tc.split_f16(wp, ws)
+    inv = torch.full((cout,), 1.0 / ws, device="cuda")
     nbr = rb.nbr.contiguous()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def conv(f):
-        f_hi, f_lo = tc.split_tf32(f)
-        o_hi = torch.zeros(n, cout, device="cuda")
-        o_lo = torch.zeros_like(o_hi)
-        L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), n, cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr), 27,
-                                       L.ptr(rb.num_out_dev), n, None, None, 0, L.ptr(o_hi), L.ptr(o_lo), cout,
-                                       L.stream()), "b2s_sparse_conv_tc")
+        f_hi, f_lo = tc.split_f16(f)
+        o = torch.zeros(n, cout, device="cuda")            # fp32 output variant (out_lo NULL)
+        L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), cin, n, cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr), 27,
+                                       L.ptr(rb.num_out_dev), n, L.ptr(inv), None, 0, L.ptr(o), None, 0, cout,
+                                       L.ptr(status), L.stream()), "b2s_sparse_conv_tc")
         torch.cuda.synchronize()
-        return o_hi + o_lo
+        return o
 
     a, b = x.features, torch.randn_like(x.features)
     ya, yb, yab = conv(a), conv(b), conv(2.5 * a - b)

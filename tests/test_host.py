@@ -109,12 +109,13 @@ def test_forward_contract_on_oracle(oracle):
 
 
 def test_pack_sparse_weights_layout():
-    """b2second.tc.pack_sparse_weights: the packed K-block GEMM (32 columns = PACK offsets x Cin channels) must equal
-    the per-offset contraction sum_k in[nbr[o,k]] @ W[k] that b2s_sparse_conv_tc's gather assembles for Cin < 32."""
+    """b2second.tc.pack_sparse_weights: the packed K-block GEMM (64 fp16 columns = PACK offsets x Cin channels, Cin 3/4
+    zero-padded to 8) must equal the per-offset contraction sum_k in[nbr[o,k]] @ W[k] that b2s_sparse_conv_tc's gather
+    assembles for Cin < 64."""
     import torch
     from b2second import tc
     g = torch.Generator().manual_seed(0)
-    for cin, cout in ((4, 16), (16, 32), (32, 32)):
+    for cin, cout in ((3, 16), (4, 16), (16, 32), (32, 32), (64, 64)):
         K, n = 27, 50
         w = torch.randn(K, cin, cout, generator=g)
         x = torch.randn(n, cin, generator=g)
@@ -124,20 +125,48 @@ def test_pack_sparse_weights_layout():
             ok = nbr[:, k] >= 0
             ref[ok] += x[nbr[ok, k]] @ w[k]
         p = tc.pack_sparse_weights(w)
-        if cin >= 32:
+        cin_tc = tc.sparse_tc_cin(cin)
+        if cin_tc >= 64:
             assert p.shape == (K, cout, cin) and torch.equal(p, w.transpose(1, 2))
             continue
-        pack = 32 // cin
+        pack = 64 // cin_tc
         nkb = (K + pack - 1) // pack
-        assert p.shape == (nkb, cout, 32)
+        assert p.shape == (nkb, cout, 64)
+        xp = torch.zeros(n, cin_tc)
+        xp[:, :cin] = x                                 # the split kernel zero-pads the rows to cin_tc channels
         got = torch.zeros(n, cout)
         for kb in range(nkb):
-            a = torch.zeros(n, 32)                      # the gathered A tile row: PACK neighbours side by side
+            a = torch.zeros(n, 64)                      # the gathered A tile row: PACK neighbours side by side
             for ko in range(pack):
                 k = kb * pack + ko
                 if k >= K:
                     continue
                 ok = nbr[:, k] >= 0
-                a[ok, ko * cin:(ko + 1) * cin] = x[nbr[ok, k]]
+                a[ok, ko * cin_tc:(ko + 1) * cin_tc] = xp[nbr[ok, k]]
             got += a @ p[kb].t()
         assert float((got - ref).abs().max()) < 1e-4
+
+
+def test_split_f16_is_fp32_grade():
+    """the 3xF16 operand split (csrc/tc_common.cuh): hi + lo reproduces an fp32 value to 2^-22 relative where lo is a
+    normal fp16, and to 2^-25 absolute below; the power-of-two weight pre-scale is exact."""
+    import torch
+    from b2second import tc
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(100000, generator=g) * 3
+    hi, lo = tc.split_f16(x)
+    err = (tc.merge_f16(hi, lo).double() - x.double()).abs()
+    assert float((err / x.abs().clamp(min=2.0 ** -3).double()).max()) <= 2.0 ** -21
+    assert float(err.max()) <= 2.0 ** -21 * float(x.abs().max())
+    small = torch.randn(10000, generator=g) * 1e-3
+    hs, ls = tc.split_f16(small)
+    assert float((tc.merge_f16(hs, ls).double() - small.double()).abs().max()) <= 2.0 ** -25 * 1.0001
+    w = torch.randn(9, 128, 128, generator=g) * 0.03
+    s = tc.pow2_scale(w)
+    assert 2.0 ** 12 < float(w.abs().max()) * s <= 2.0 ** 13 and float(np.log2(s)).is_integer()
+    wh, wl = tc.split_f16(w, s)
+    rel = ((tc.merge_f16(wh, wl).double() / s - w.double()).abs() / w.abs().double().clamp(min=float(w.abs().max()) * 2.0 ** -16))
+    assert float(rel.max()) <= 2.0 ** -21
+    big = torch.tensor([1e6, -1e6, 65504.0])
+    hb, lb = tc.split_f16(big)
+    assert bool(torch.isfinite(hb.float()).all()) and float(hb[0]) == 65504.0      # saturating, never inf

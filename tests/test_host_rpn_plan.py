@@ -22,7 +22,8 @@ def interpret(plan, x):
     for op in plan["ops"]:
         src = bufs[op["src"]]
         assert src.shape[1] == op["cin"] and tuple(src.shape[2:]) == (op["Hin"], op["Win"])
-        w = (op["w_hi"] + op["w_lo"])[:, :op["cout"]]                      # [taps, cout, cin]
+        # fp16 hi/lo planes of the power-of-two pre-scaled weights; op["scale"] carries the inverse scale
+        w = (op["w_hi"].float() + op["w_lo"].float())[:, :op["cout"]]      # [taps, cout, cin]
         w = w.reshape(op["kh"], op["kw"], op["cout"], op["cin"]).permute(2, 3, 0, 1)
         y = F.conv2d(src, w, stride=op["stride"], padding=op["pad"])
         assert tuple(y.shape[2:]) == (op["Hg"], op["Wg"])

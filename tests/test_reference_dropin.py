@@ -78,6 +78,39 @@ def test_mirror_equals_reference_network(ref_env, name):
     assert torch.equal(o_r["label_preds"], o_m["label_preds"])
 
 
+@pytest.mark.parametrize("name", sorted(config.BUILTIN))
+def test_engine_plan_from_reference_network_equals_plan_from_mirror(ref_env, name):
+    """b2second.spec reads a network through the reference's attribute names only, so the fused engine plans the
+    UNMODIFIED reference VoxelNet (second_builder.build) exactly as it plans the mirror: same layer list, folded
+    BN constants, NMS / direction parameters, RPN weights and anchors -- for all five BASELINE configs."""
+    from b2second import spec
+    cfgp = refcompat.load_config(config.REFERENCE_FILES[name])
+    ref = refcompat.build_network(cfgp.model.second).eval()
+    mine = models.build_network(name, ref_env).eval()
+    models.synthetic_weights_(ref, name)
+    models.synthetic_weights_(mine, name)
+    cfg = config.get_config(name)
+    s_ref = spec.spec_from_module(ref, max_voxels=cfg.max_voxels)
+    s_mine = spec.spec_from_module(mine, max_voxels=cfg.max_voxels)
+    a, b = s_ref.signature(), s_mine.signature()
+    assert set(a) == set(b)
+    for k in a:
+        assert a[k] == b[k], "spec field %s differs between the reference network and the mirror" % k
+    fm = cfg.feature_map_size
+    assert np.array_equal(spec.anchors_for(s_ref, (fm[1], fm[2])), spec.anchors_for(s_mine, (fm[1], fm[2])))
+    # the RPN launch program is planned from the module tree, too
+    from b2second import tc
+    D, H, W = 1, 64, 48
+    p_ref, p_mine = tc.plan_rpn(ref.rpn, H, W), tc.plan_rpn(mine.rpn, H, W)
+    assert len(p_ref["ops"]) == len(p_mine["ops"]) and p_ref["buffers"] == p_mine["buffers"]
+    for o1, o2 in zip(p_ref["ops"], p_mine["ops"]):
+        for k in o1:
+            if isinstance(o1[k], torch.Tensor):
+                assert torch.equal(o1[k], o2[k]), k
+            else:
+                assert o1[k] == o2[k], k
+
+
 def test_reference_builds_on_cuda_dropin_in_subprocess():
     """`import spconv` == second.pytorch_b200/spconv; the reference's second_builder constructs VoxelNet on it."""
     code = r"""

@@ -1,5 +1,6 @@
 """micro-benchmark of b2s_conv2d_tc alone (RPN 3x3 128->128 at car.fhd size), CUDA-event timed.
-B2S_CONV_DBG (diagnostic, wrong results): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no TMEM drain."""
+B2S_CONV_DBG (diagnostic, wrong results; `make DIAG=1` builds only): 1 = no lo loads, 2 = hi*hi MMA only, 4 = no
+TMEM drain.  B2S_CONV_B = frames."""
 import os
 import sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,16 +11,19 @@ sp = loader.product_spconv()
 L = sp._lib
 lib = L.load()
 B, H, W, C = 8, 200, 176, 128
+B = int(os.environ.get("B2S_CONV_B", B))
 x = torch.randn(B, H + 2, W + 2, C, device="cuda")
-hi, lo = tc.split_tf32(x)
+hi, lo = tc.split_f16(x)
 w = torch.randn(9, C, C, device="cuda") * 0.03
-w_hi, w_lo = tc.split_tf32(w)
-scale = torch.ones(C, device="cuda"); shift = torch.zeros(C, device="cuda")
+ws = tc.pow2_scale(w)
+w_hi, w_lo = tc.split_f16(w, ws)
+scale = torch.full((C,), 1.0 / ws, device="cuda"); shift = torch.zeros(C, device="cuda")
 o_hi = torch.zeros_like(hi); o_lo = torch.zeros_like(hi)
+status = torch.zeros(1, dtype=torch.int32, device="cuda")
 flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda")
 def run():
     L.check(lib.b2s_conv2d_tc(L.ptr(hi), L.ptr(lo), B, H, W, C, L.ptr(w_hi), L.ptr(w_lo), 9, C, 128, L.ptr(scale),
-                              L.ptr(shift), 1, L.ptr(o_hi), L.ptr(o_lo), 1, C, L.stream()), "conv")
+                              L.ptr(shift), 1, L.ptr(o_hi), L.ptr(o_lo), 1, C, L.ptr(status), L.stream()), "conv")
 for _ in range(3): run()
 torch.cuda.synchronize()
 ts = []
@@ -30,13 +34,13 @@ for i in range(10):
     ts.append(a.elapsed_time(b))
 ms = sorted(ts)[len(ts) // 2]
 flops = 2.0 * B * H * W * C * C * 9
-print("B2S_CONV_DBG=%s B2S_CONV_HALO=%s  median %.3f ms  algorithmic %.1f TFLOP/s (x3 tf32 issued: %.1f)" % (
+print("B2S_CONV_DBG=%s B2S_CONV_HALO=%s  median %.3f ms  algorithmic %.1f TFLOP/s (x3 f16 MMAs issued: %.1f)" % (
     os.environ.get("B2S_CONV_DBG", "0"), os.environ.get("B2S_CONV_HALO", "0"), ms, flops / ms / 1e9, 3 * flops / ms / 1e9))
 # accuracy of the merged hi+lo output against an fp64 cuDNN-free reference (frames 0..1)
 if os.environ.get("B2S_CONV_ACC", "1") == "1":
     nb = 2
     xin = (hi[:nb].double() + lo[:nb].double()).permute(0, 3, 1, 2)            # [nb, C, H+2, W+2] (halo = padding)
-    wt = (w_hi.double() + w_lo.double()).reshape(3, 3, C, C).permute(2, 3, 0, 1)  # [Cout, Cin, 3, 3]
+    wt = ((w_hi.double() + w_lo.double()) / ws).reshape(3, 3, C, C).permute(2, 3, 0, 1)  # [Cout, Cin, 3, 3]
     ref = torch.nn.functional.conv2d(xin, wt).clamp_(min=0).permute(0, 2, 3, 1)  # [nb, H, W, C]
     got = (o_hi[:nb, 1:-1, 1:-1].double() + o_lo[:nb, 1:-1, 1:-1].double())
     err = (got - ref).abs()
