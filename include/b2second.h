@@ -156,11 +156,12 @@ int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_
                        int cout, unsigned *status_dev, void *stream);
 
 /* fp32 rows <-> fp16 hi/lo planes (hi = fp16 round-to-nearest, lo = fp16-rounded remainder; saturating).
- * split: x [rows, row_floats] -> rows of out_stride halves (>= row_floats, multiple of 8, zero padded).
+ * split: x [rows, row_floats] -> out_channels halves per row and plane (>= row_floats, multiple of 8, zero padded), rows
+ *        out_stride halves apart (>= out_channels; 2*out_channels for interleaved [row][hi | lo] storage).
  * merge: rows of in_stride halves -> x [rows, row_floats] = hi + lo (exact in fp32).
  * rows = *num_rows_dev (NULL: cap_rows). */
 int b2s_split_f16(const float *x, b2s_half *hi, b2s_half *lo, const int *num_rows_dev, int cap_rows, int row_floats,
-                  int out_stride, void *stream);
+                  int out_channels, int out_stride, void *stream);
 int b2s_merge_f16(const b2s_half *hi, const b2s_half *lo, float *x, const int *num_rows_dev, int cap_rows,
                   int row_floats, int in_stride, void *stream);
 
@@ -234,6 +235,24 @@ int b2s_decode_filter_strided(const float *box, const float *cls, const float *d
                               int code, int ncls, int nbins, float score_thresh, float *cand_box,
                               float *cand_score, int *cand_label, int *cand_dir, int *cand_anchor,
                               int *cand_count_dev, int cand_cap, unsigned *status_dev, void *stream);
+
+/* multi-class NMS branch (second/pytorch/models/voxelnet.py:458-547): one candidate list per (class, frame),
+ * "virtual frame" v = c*batch + b (class-major): cand_* are [ncls*batch, cand_cap, ...], cand_count_dev [ncls*batch].
+ * An anchor joins class c's list when its class-c score passes score_thresh[c] and (class_lo/hi given) its a_loc
+ * index lies in [class_lo[c], class_hi[c]) (target_assigner.anchors_range); label = c.  class_lo = class_hi = NULL:
+ * nms_class_agnostic.  Head tensors addressed by strides as in b2s_decode_filter_strided.  ncls <= 16.
+ * Follow with b2s_nms(batch = ncls*batch) and b2s_concat_class_detections. */
+int b2s_decode_filter_multiclass(const float *box, const float *cls, const float *dir, long long box_batch_stride,
+                                 long long cls_batch_stride, long long dir_batch_stride, int ch_stride, int pix_stride,
+                                 const float *anchors, int batch, int a_loc, int H, int W, int code, int ncls, int nbins,
+                                 const int *class_lo /*host[ncls] or NULL*/, const int *class_hi /*host[ncls] or NULL*/,
+                                 const float *score_thresh /*host[ncls]*/, float *cand_box, float *cand_score,
+                                 int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev, int cand_cap,
+                                 unsigned *status_dev, void *stream);
+/* det_mc [ncls*batch, post_max, code+2], count_mc [ncls*batch] (class-major b2s_nms outputs) -> per-frame records
+ * of up to ncls*post_max rows in class order (voxelnet.py:528-533); det / det_frame_stride / det_count_dev as b2s_nms. */
+int b2s_concat_class_detections(const float *det_mc, const int *count_mc, int batch, int ncls, int post_max, int code,
+                                float *det, int det_frame_stride, int *det_count_dev, void *stream);
 
 /* ---- top-k + NMS + direction/range epilogue ------------------------------------------------------ */
 size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max);

@@ -150,81 +150,16 @@ int orc_nms_cpu(const float *dets /*[N,5]*/, const int *order, int N,
 /* the 4-corner polygons; for convex quads area(A∩B) is what S-H computes and  */
 /* area(A∪B) = area(A)+area(B)-area(A∩B).                                      */
 /* ------------------------------------------------------------------------- */
-static double poly_area(const double *p, int n)
-{
-    double s = 0.0;
-    for (int i = 0; i < n; ++i) {
-        int j = (i + 1 == n) ? 0 : i + 1;
-        s += p[2 * i] * p[2 * j + 1] - p[2 * j] * p[2 * i + 1];
-    }
-    return 0.5 * s;
-}
-
-/* clip subject polygon (n pts) by the half plane to the left of a->b
- * (polygon orientation normalised by the caller); returns new count. */
-static int clip_edge(const double *in, int n, double ax, double ay, double bx,
-                     double by, double *out)
-{
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
-        int j = (i + 1 == n) ? 0 : i + 1;
-        double px = in[2 * i], py = in[2 * i + 1];
-        double qx = in[2 * j], qy = in[2 * j + 1];
-        double sp = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
-        double sq = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
-        int pin = sp >= 0.0, qin = sq >= 0.0;
-        if (pin) { out[2 * m] = px; out[2 * m + 1] = py; ++m; }
-        if (pin != qin) {
-            double t = sp / (sp - sq);
-            out[2 * m] = px + t * (qx - px);
-            out[2 * m + 1] = py + t * (qy - py);
-            ++m;
-        }
-    }
-    return m;
-}
-
-/* a, b: 4 corners each (x,y) f32, any orientation.  returns intersection area */
-double orc_quad_intersection(const float *a, const float *b, double *area_a,
-                             double *area_b)
-{
-    double A[8], B[8];
-    for (int i = 0; i < 8; ++i) { A[i] = a[i]; B[i] = b[i]; }
-    double sa = poly_area(A, 4), sb = poly_area(B, 4);
-    if (sa < 0) { /* make counter-clockwise */
-        for (int i = 0; i < 2; ++i) {
-            int j = 3 - i;
-            double tx = A[2 * i], ty = A[2 * i + 1];
-            A[2 * i] = A[2 * j]; A[2 * i + 1] = A[2 * j + 1];
-            A[2 * j] = tx; A[2 * j + 1] = ty;
-        }
-        sa = -sa;
-    }
-    if (sb < 0) {
-        for (int i = 0; i < 2; ++i) {
-            int j = 3 - i;
-            double tx = B[2 * i], ty = B[2 * i + 1];
-            B[2 * i] = B[2 * j]; B[2 * i + 1] = B[2 * j + 1];
-            B[2 * j] = tx; B[2 * j + 1] = ty;
-        }
-        sb = -sb;
-    }
-    if (area_a) *area_a = sa;
-    if (area_b) *area_b = sb;
-    double buf0[32], buf1[32];
-    int n = 4;
-    memcpy(buf0, A, sizeof(A));
-    double *cur = buf0, *nxt = buf1;
-    for (int e = 0; e < 4 && n > 0; ++e) {
-        int f = (e + 1) & 3;
-        n = clip_edge(cur, n, B[2 * e], B[2 * e + 1], B[2 * f], B[2 * f + 1],
-                      nxt);
-        double *t = cur; cur = nxt; nxt = t;
-    }
-    if (n < 3) return 0.0;
-    double inter = poly_area(cur, n);
-    return inter > 0.0 ? inter : 0.0;
-}
+#define REAL double
+#define FN(name) name
+#include "quad_clip.inc"
+#undef REAL
+#undef FN
+#define REAL float
+#define FN(name) name##_f32
+#include "quad_clip.inc"
+#undef REAL
+#undef FN
 
 /* spconv.utils.rotate_non_max_suppression_cpu(corners, order, standup_iou, thresh):
  * greedy in `order`; skip pair if standup_iou <= 0; suppress if inter/union >= thresh.
@@ -252,6 +187,34 @@ int orc_rotate_nms(const float *corners /*[N,4,2]*/, const int *order,
             double ov = inter / uni;
             if (iou_out) iou_out[(size_t)i * N + j] = ov;
             if (ov >= (double)thresh) sup[j] = 1;
+        }
+    }
+    free(sup);
+    return nk;
+}
+
+/* the same greedy loop with the polygon clip in fp32 (see quad_clip.inc) */
+int orc_rotate_nms_f32(const float *corners /*[N,4,2]*/, const int *order,
+                       const float *standup_iou /*[N,N]*/, int N, float thresh,
+                       int *keep, double *iou_out)
+{
+    unsigned char *sup = (unsigned char *)calloc((size_t)N + 1, 1);
+    int nk = 0;
+    for (int _i = 0; _i < N; ++_i) {
+        int i = order[_i];
+        if (sup[i]) continue;
+        keep[nk++] = i;
+        for (int _j = _i + 1; _j < N; ++_j) {
+            int j = order[_j];
+            if (sup[j]) continue;
+            if (standup_iou[(size_t)i * N + j] <= 0.f) continue;
+            float sa, sb;
+            float inter = orc_quad_intersection_f32(corners + 8 * i, corners + 8 * j, &sa, &sb);
+            if (inter <= 0.f) continue;
+            float uni = sa + sb - inter;
+            float ov = inter / uni;
+            if (iou_out) iou_out[(size_t)i * N + j] = (double)ov;
+            if (ov >= thresh) sup[j] = 1;
         }
     }
     free(sup);

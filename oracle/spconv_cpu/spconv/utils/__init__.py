@@ -43,6 +43,8 @@ def _load():
     lib.orc_nms_cpu.argtypes = [f32p, i32p, ctypes.c_int, ctypes.c_float, ctypes.c_float, i32p]
     lib.orc_rotate_nms.restype = ctypes.c_int
     lib.orc_rotate_nms.argtypes = [f32p, i32p, f32p, ctypes.c_int, ctypes.c_float, i32p, f64p]
+    lib.orc_rotate_nms_f32.restype = ctypes.c_int
+    lib.orc_rotate_nms_f32.argtypes = [f32p, i32p, f32p, ctypes.c_int, ctypes.c_float, i32p, f64p]
     lib.orc_rbbox_iou.restype = None
     lib.orc_rbbox_iou.argtypes = [f32p, f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                   ctypes.c_int, f32p]
@@ -161,7 +163,10 @@ def non_max_suppression_cpu(boxes, order, thresh, eps=0.0):
     return keep[:k].tolist()
 
 
-def rotate_non_max_suppression_cpu(box_corners, order, standup_iou, thresh, return_iou=False):
+def rotate_non_max_suppression_cpu(box_corners, order, standup_iou, thresh, return_iou=False, precision="f64"):
+    """precision="f64": polygon clip in double (default).  "f32": the same loop with the clip in float -- the
+    precision the float corners arrive in and the CUDA kernel computes in; tests/test_oracle_nms.py counts how many
+    keep lists depend on that choice."""
     lib = _load()
     box_corners = np.ascontiguousarray(box_corners, dtype=np.float32)
     order = np.ascontiguousarray(order, dtype=np.int32)
@@ -171,7 +176,8 @@ def rotate_non_max_suppression_cpu(box_corners, order, standup_iou, thresh, retu
         return ([], np.zeros((0, 0))) if return_iou else []
     keep = np.zeros(n, dtype=np.int32)
     iou = np.full((n, n), -1.0, dtype=np.float64) if return_iou else None
-    k = lib.orc_rotate_nms(_f32(box_corners), _i32(order), _f32(standup_iou), n, float(thresh),
+    fn = lib.orc_rotate_nms if precision == "f64" else lib.orc_rotate_nms_f32
+    k = fn(_f32(box_corners), _i32(order), _f32(standup_iou), n, float(thresh),
                            _i32(keep),
                            iou.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if return_iou else None)
     if return_iou:

@@ -62,8 +62,6 @@ class InferenceEngine:
         self.spec = s = net if isinstance(net, _spec.NetSpec) else _spec.spec_from_module(net, max_voxels)
         if max_voxels:
             s.max_voxels = int(max_voxels)
-        if s.multiclass_nms:
-            raise _spec.UnsupportedNetwork("per-class NMS branch (voxelnet.py:458-547) is not on the fused path yet")
         self.B = int(batch_size)
         dev = torch.device(device) if device is not None else s.device
         assert dev.type == "cuda", "InferenceEngine needs the network on a CUDA device"
@@ -302,16 +300,43 @@ class InferenceEngine:
         self.use_mask = False
         self.cand_cap = int(cand_cap or min(self.A, 32768))
         B, cc, code = self.B, self.cand_cap, self.code
-        self.cand_box = torch.zeros(B, cc, code, dtype=torch.float32, device=dev)
-        self.cand_score = torch.zeros(B, cc, dtype=torch.float32, device=dev)
-        self.cand_label = torch.zeros(B, cc, dtype=torch.int32, device=dev)
-        self.cand_dir = torch.zeros(B, cc, dtype=torch.int32, device=dev)
-        self.cand_anchor = torch.zeros(B, cc, dtype=torch.int32, device=dev)
-        self.cand_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        # per-class NMS branch (voxelnet.py:458-547): one candidate list and one NMS per (class, frame) -- "virtual
+        # frames" v = c*B + b -- then the per-class results are concatenated in class order
+        self.mc = bool(s.multiclass_nms)
+        self.ncls = s.num_class
+        V = self.ncls * B if self.mc else B
+        self.cand_box = torch.zeros(V, cc, code, dtype=torch.float32, device=dev)
+        self.cand_score = torch.zeros(V, cc, dtype=torch.float32, device=dev)
+        self.cand_label = torch.zeros(V, cc, dtype=torch.int32, device=dev)
+        self.cand_dir = torch.zeros(V, cc, dtype=torch.int32, device=dev)
+        self.cand_anchor = torch.zeros(V, cc, dtype=torch.int32, device=dev)
+        self.cand_count = torch.zeros(V, dtype=torch.int32, device=dev)
         self.score_thresh = float(s.nms_score_thresholds[0])
         self.pre_max, self.post_max = int(s.nms_pre_max_sizes[0]), int(s.nms_post_max_sizes[0])
         self.iou_thresh = float(s.nms_iou_thresholds[0])
-        self.nms_ws_bytes = self.lib.b2s_nms_workspace_bytes(B, cc, self.pre_max)
+        if self.mc:
+            n = self.ncls
+            assert n <= 16 and all(len(x) >= n for x in (s.nms_score_thresholds, s.nms_pre_max_sizes,
+                                                         s.nms_post_max_sizes, s.nms_iou_thresholds))
+            self.mc_thresh = (ctypes.c_float * n)(*s.nms_score_thresholds[:n])
+            self.mc_pre = [int(x) for x in s.nms_pre_max_sizes[:n]]
+            self.mc_post = [int(x) for x in s.nms_post_max_sizes[:n]]
+            self.mc_iou = [float(x) for x in s.nms_iou_thresholds[:n]]
+            self.mc_uniform = len(set(self.mc_pre)) == 1 and len(set(self.mc_post)) == 1 and len(set(self.mc_iou)) == 1
+            self.pre_max, self.post_max_class = max(self.mc_pre), max(self.mc_post)
+            self.post_max = n * self.post_max_class               # rows of a frame's record
+            if s.nms_class_agnostic:
+                self.mc_lo = self.mc_hi = None
+            else:
+                counts = s.class_anchor_counts
+                if counts is None or len(counts) != n or sum(counts) != self.a_loc:
+                    raise _spec.UnsupportedNetwork("per-class NMS needs target_assigner anchor counts per class")
+                lo = np.cumsum([0] + counts[:-1]).tolist()
+                self.mc_lo = (ctypes.c_int * n)(*lo)
+                self.mc_hi = (ctypes.c_int * n)(*[a + c for a, c in zip(lo, counts)])
+            self.det_mc = torch.zeros(V, self.post_max_class, code + 2, dtype=torch.float32, device=dev)
+            self.cnt_mc = torch.zeros(V, dtype=torch.int32, device=dev)
+        self.nms_ws_bytes = self.lib.b2s_nms_workspace_bytes(V, cc, self.pre_max)
         self.nms_ws = torch.empty(max(self.nms_ws_bytes, 1), dtype=torch.uint8, device=dev)
         # one record per frame: post_max*(code+2) detection floats followed by the count (as a float: < 2^24) --
         # exactly the all-gather payload (b2second/dist.py), written in place by the NMS epilogue
@@ -383,7 +408,7 @@ class InferenceEngine:
                     if "in_split" in lyr:
                         _, hi, lo, stride = lyr["in_split"]
                         L.check(lib.b2s_split_f16(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
-                                                  lyr["cin"], stride, st), "b2s_split_f16")
+                                                  lyr["cin"], lyr["cin_tc"], stride, st), "b2s_split_f16")
                         hilo = (hi, lo, stride)
                     L.check(lib.b2s_sparse_conv_tc(
                         L.ptr(hilo[0]), L.ptr(hilo[1]), hilo[2], lin.cap, lyr["cin_tc"], L.ptr(lyr["w_hi"]),
@@ -420,11 +445,9 @@ class InferenceEngine:
         dirp = rpn.conv_dir_cls(x).contiguous() if s.use_direction_classifier else None
         self._keep = (x, box, cls, dirp)
         self._mark("decode_filter")
-        L.check(lib.b2s_decode_filter(
-            L.ptr(box), L.ptr(cls), L.ptr(dirp), L.ptr(self.anchors), L.ptr(self.anchors_mask) if self.use_mask else None,
-            self.B, self.a_loc, self.fH, self.fW, self.code, s.num_class, s.num_direction_bins, self.score_thresh,
-            L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
-            L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter")
+        HW = self.fH * self.fW
+        self._launch_decode(L.ptr(box), L.ptr(cls), L.ptr(dirp), self.a_loc * self.code * HW, self.a_loc * s.num_class * HW,
+                            self.a_loc * s.num_direction_bins * HW, HW, 1, st)      # NCHW conv outputs
         self._launch_nms(st)
 
     def _launch_tc_tail(self, feats, hilo):
@@ -471,17 +494,50 @@ class InferenceEngine:
         cls_p = ctypes_ptr(heads.data_ptr() + offs[1] * esz)
         dir_p = ctypes_ptr(heads.data_ptr() + offs[2] * esz) if s.use_direction_classifier else None
         bs = self.fH * self.fW * S
+        self._launch_decode(box_p, cls_p, dir_p, bs, bs, bs, 1, S, st)               # packed NHWC head records
+        self._launch_nms(st)
+
+    def _launch_decode(self, box_p, cls_p, dir_p, box_bs, cls_bs, dir_bs, ch_stride, pix_stride, st):
+        """sigmoid + score threshold + box decode over all anchors -> candidate lists (per frame, or per (class, frame))"""
+        L, lib, s = self._L, self.lib, self.spec
+        if self.mc:
+            if self.use_mask:
+                raise RuntimeError("anchors_mask with the per-class NMS branch is ill-defined upstream (masking shifts the "
+                                   "anchors_range indices, voxelnet.py:432-439,492-501)")
+            L.check(lib.b2s_decode_filter_multiclass(
+                box_p, cls_p, dir_p, box_bs, cls_bs, dir_bs, ch_stride, pix_stride, L.ptr(self.anchors), self.B,
+                self.a_loc, self.fH, self.fW, self.code, s.num_class, s.num_direction_bins, self.mc_lo, self.mc_hi,
+                self.mc_thresh, L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label),
+                L.ptr(self.cand_dir), L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.cand_cap,
+                L.ptr(self.status), st), "b2s_decode_filter_multiclass")
+            return
         L.check(lib.b2s_decode_filter_strided(
-            box_p, cls_p, dir_p, bs, bs, bs, 1, S, L.ptr(self.anchors),
+            box_p, cls_p, dir_p, box_bs, cls_bs, dir_bs, ch_stride, pix_stride, L.ptr(self.anchors),
             L.ptr(self.anchors_mask) if self.use_mask else None, self.B, self.a_loc, self.fH, self.fW,
             self.code, s.num_class, s.num_direction_bins, self.score_thresh, L.ptr(self.cand_box),
             L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir), L.ptr(self.cand_anchor),
             L.ptr(self.cand_count), self.cand_cap, L.ptr(self.status), st), "b2s_decode_filter_strided")
-        self._launch_nms(st)
 
     def _launch_nms(self, st):
         L, lib, s = self._L, self.lib, self.spec
         self._mark("nms")
+        if self.mc:
+            B, cc, code, n = self.B, self.cand_cap, self.code, self.ncls
+            groups = [(0, n * B, self.mc_pre[0], self.mc_post[0], self.mc_iou[0])] if self.mc_uniform else \
+                [(c * B, B, self.mc_pre[c], self.mc_post[c], self.mc_iou[c]) for c in range(n)]
+            for v0, nv, pre, post, iou in groups:         # class-major virtual frames: one class = B contiguous lists
+                L.check(lib.b2s_nms(
+                    L.ptr(self.cand_box[v0:]), L.ptr(self.cand_score[v0:]), L.ptr(self.cand_label[v0:]),
+                    L.ptr(self.cand_dir[v0:]), L.ptr(self.cand_anchor[v0:]), L.ptr(self.cand_count[v0:]), nv, cc, code,
+                    1 if s.use_rotate_nms else 0, pre, post, iou, 1 if s.use_direction_classifier else 0,
+                    float(s.direction_offset), float(s.direction_limit_offset), s.num_direction_bins, self.range_host,
+                    L.ptr(self.det_mc[v0:]), self.post_max_class * (code + 2), L.ptr(self.cnt_mc[v0:]),
+                    L.ptr(self.nms_ws), self.nms_ws_bytes, st), "b2s_nms")
+            L.check(lib.b2s_concat_class_detections(L.ptr(self.det_mc), L.ptr(self.cnt_mc), B, n, self.post_max_class,
+                                                    code, L.ptr(self.det_record), self.rec_width, L.ptr(self.det_count),
+                                                    st), "b2s_concat_class_detections")
+            self._mark("end")
+            return
         L.check(lib.b2s_nms(
             L.ptr(self.cand_box), L.ptr(self.cand_score), L.ptr(self.cand_label), L.ptr(self.cand_dir),
             L.ptr(self.cand_anchor), L.ptr(self.cand_count), self.B, self.cand_cap, self.code,
@@ -529,6 +585,8 @@ class InferenceEngine:
             n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
         elif getattr(self, "any_sparse_tc", False):
             n += 1                               # b2s_merge_f16
+        if self.mc:
+            return n + 1 + 1 + 3 * (1 if self.mc_uniform else self.ncls) + 1      # ... + k_concat_classes
         return n + 1 + 1 + 3                     # to_bev, decode_filter, nms: select_sort + iou_mask + reduce
 
     def sparse_layer_stats(self):

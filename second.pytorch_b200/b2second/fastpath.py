@@ -43,8 +43,6 @@ class FastPath:
         self.use_cuda_graph = use_cuda_graph
         self.engine_kw = engine_kw
         self.spec = _spec.spec_from_module(net, max_voxels)      # raises UnsupportedNetwork for foreign layer patterns
-        if self.spec.multiclass_nms:
-            raise _spec.UnsupportedNetwork("per-class NMS branch is not on the fused path yet")
         self.engines = {}
 
     def engine(self, batch_size):

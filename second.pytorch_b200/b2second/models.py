@@ -262,6 +262,37 @@ class RPNV2(nn.Module):
 
 
 # ------------------------------------------------------------------------------ VoxelNet
+class _AnchorGeneratorInfo:
+    def __init__(self, ac):
+        self.class_name = ac.class_name
+        self.num_anchors_per_localization = ac.num_anchors_per_loc
+
+
+class MirrorTargetAssigner:
+    """the slice of second/core/target_assigner.py ``TargetAssigner`` that inference reads: anchors per location,
+    per-class anchor ranges (``anchors_range``, :269-278) and ``generate_anchors`` (:169-207)."""
+
+    def __init__(self, cfg):
+        self._cfg = cfg
+        self._anchor_generators = [_AnchorGeneratorInfo(ac) for ac in cfg.classes]
+        self._classes = [ac.class_name for ac in cfg.classes]
+
+    @property
+    def num_anchors_per_location(self):
+        return self._cfg.num_anchors_per_loc
+
+    def generate_anchors(self, feature_map_size):
+        a = generate_anchors(self._cfg)
+        fm = [int(x) for x in feature_map_size]
+        assert a.shape[0] == self._cfg.num_anchors_per_loc * int(np.prod(fm)), "feature map size does not match the config"
+        return {"anchors": a}
+
+    def anchors_range(self, class_idx):
+        hw = int(np.prod(self._cfg.feature_map_size))
+        start = sum(g.num_anchors_per_localization for g in self._anchor_generators[:class_idx]) * hw
+        return start, start + self._anchor_generators[class_idx].num_anchors_per_localization * hw
+
+
 class VoxelNet(nn.Module):
     """Inference network with the reference's ``forward(example)`` contract.
 
@@ -314,7 +345,7 @@ class VoxelNet(nn.Module):
         self._post_center_range = list(cfg.post_center_limit_range)
         self._dir_offset = cfg.direction_offset
         self._dir_limit_offset = cfg.direction_limit_offset
-        self._fast = None            # b2second.fastpath.FastPath once accelerate() has been called
+        self.target_assigner = MirrorTargetAssigner(cfg)
 
     # -- helpers --------------------------------------------------------------------------
     def anchors(self):
@@ -363,8 +394,6 @@ class VoxelNet(nn.Module):
 
     def predict(self, example, preds_dict):
         cfg = self.cfg
-        if cfg.use_multi_class_nms:
-            raise NotImplementedError("multi-class NMS branch (voxelnet.py:458-547) is a SURVEY §8(f) 'next' row")
         batch_size = example["anchors"].shape[0]
         meta_list = example.get("metadata") or [None] * batch_size
         batch_anchors = example["anchors"].view(batch_size, -1, example["anchors"].shape[-1])
@@ -398,6 +427,13 @@ class VoxelNet(nn.Module):
                     dir_preds = dir_preds[a_mask]
                 dir_labels = torch.max(dir_preds, dim=-1)[1]
             total_scores = torch.sigmoid(cls_preds)
+            if cfg.use_multi_class_nms:
+                # per-class NMS branch (voxelnet.py:458-547)
+                sel = self._predict_multiclass(box_preds, total_scores, dir_labels, a_mask)
+                sel_boxes, sel_labels, sel_scores, sel_dir = sel
+                out.append(self._finish_frame(sel_boxes, sel_scores, sel_labels, sel_dir, post_center_range, meta,
+                                              batch_box_preds))
+                continue
             if cfg.num_class == 1:
                 top_scores = total_scores.squeeze(-1)
                 top_labels = torch.zeros(total_scores.shape[0], device=total_scores.device, dtype=torch.long)
@@ -414,40 +450,90 @@ class VoxelNet(nn.Module):
                         dir_labels = dir_labels[keep_mask]
                     top_labels = top_labels[keep_mask]
                 boxes_for_nms = box_preds[:, [0, 1, 3, 4, 6]]
-                if cfg.use_rotate_nms:
-                    selected = box_ops.rotate_nms(self._sp, boxes_for_nms, top_scores, cfg.nms_pre_max_size,
-                                                  cfg.nms_post_max_size, cfg.nms_iou_threshold)
-                else:
-                    corners = box_ops.corners_2d_torch(boxes_for_nms[:, :2], boxes_for_nms[:, 2:4],
-                                                       boxes_for_nms[:, 4])
-                    selected = box_ops.aligned_nms(self._sp, box_ops.standup_torch(corners), top_scores,
-                                                   cfg.nms_pre_max_size, cfg.nms_post_max_size,
-                                                   cfg.nms_iou_threshold)
+                selected = self._nms(boxes_for_nms, top_scores, cfg.nms_pre_max_size, cfg.nms_post_max_size,
+                                     cfg.nms_iou_threshold)
             else:
                 selected = torch.zeros([0], dtype=torch.long, device=box_preds.device)
-            sel_boxes = box_preds[selected]
-            sel_labels = top_labels[selected]
-            sel_scores = top_scores[selected]
-            if sel_boxes.shape[0] != 0:
-                if cfg.use_direction_classifier:
-                    period = 2 * np.pi / cfg.num_direction_bins
-                    dir_rot = box_ops.limit_period(sel_boxes[..., 6] - cfg.direction_offset,
-                                                   cfg.direction_limit_offset, period)
-                    sel_boxes[..., 6] = dir_rot + cfg.direction_offset \
-                        + period * dir_labels[selected].to(sel_boxes.dtype)
-                if post_center_range is not None:
-                    m = (sel_boxes[:, :3] >= post_center_range[:3]).all(1)
-                    m &= (sel_boxes[:, :3] <= post_center_range[3:]).all(1)
-                    sel_boxes, sel_scores, sel_labels = sel_boxes[m], sel_scores[m], sel_labels[m]
-                out.append({"box3d_lidar": sel_boxes, "scores": sel_scores, "label_preds": sel_labels,
-                            "metadata": meta})
-            else:
-                dev, dt = batch_box_preds.device, batch_box_preds.dtype
-                out.append({"box3d_lidar": torch.zeros([0, cfg.box_code_size], dtype=dt, device=dev),
-                            "scores": torch.zeros([0], dtype=dt, device=dev),
-                            "label_preds": torch.zeros([0], dtype=torch.long, device=dev),
-                            "metadata": meta})
+            sel_dir = dir_labels[selected] if dir_labels is not None else None
+            out.append(self._finish_frame(box_preds[selected], top_scores[selected], top_labels[selected], sel_dir,
+                                          post_center_range, meta, batch_box_preds))
         return out
+
+
+def _voxelnet_nms(self, boxes_for_nms, scores, pre_max, post_max, iou_thr):
+    """rotate_nms / nms on BEV boxes (x, y, w, l, r) (voxelnet.py:449-456,571-584)."""
+    if self.cfg.use_rotate_nms:
+        return box_ops.rotate_nms(self._sp, boxes_for_nms, scores, pre_max, post_max, iou_thr)
+    corners = box_ops.corners_2d_torch(boxes_for_nms[:, :2], boxes_for_nms[:, 2:4], boxes_for_nms[:, 4])
+    return box_ops.aligned_nms(self._sp, box_ops.standup_torch(corners), scores, pre_max, post_max, iou_thr)
+
+
+def _voxelnet_predict_multiclass(self, box_preds, total_scores, dir_labels, a_mask):
+    """voxelnet.py:458-547: one NMS per class over that class's anchors (``target_assigner.anchors_range``) or, with
+    ``nms_class_agnostic``, over all anchors; results concatenated in class order."""
+    cfg = self.cfg
+    assert a_mask is None or cfg.nms_class_agnostic, "anchors_mask + per-class anchor ranges is ill-defined upstream"
+    boxes_for_nms = box_preds[:, [0, 1, 3, 4, 6]]
+    A = box_preds.shape[0]
+    hw = A // cfg.num_anchors_per_loc
+    sel_boxes, sel_labels, sel_scores, sel_dir = [], [], [], []
+    start = 0
+    for c, ac in enumerate(cfg.classes):
+        n_c = ac.num_anchors_per_loc
+        if cfg.nms_class_agnostic:
+            r0, r1 = 0, A
+        else:
+            r0, r1 = start * hw, (start + n_c) * hw
+        start += n_c
+        scores = total_scores[r0:r1, c].contiguous()
+        cb, cbn = box_preds[r0:r1], boxes_for_nms[r0:r1]
+        cd = dir_labels[r0:r1] if dir_labels is not None else None
+        thr = self._nms_score_thresholds[c]
+        if thr > 0.0:
+            m = scores >= thr
+            scores, cb, cbn = scores[m], cb[m], cbn[m]
+            cd = cd[m] if cd is not None else None
+        if scores.shape[0] == 0:
+            continue
+        keep = self._nms(cbn, scores, self._nms_pre_max_sizes[c], self._nms_post_max_sizes[c],
+                         self._nms_iou_thresholds[c])
+        if keep.shape[0] == 0:
+            continue
+        sel_boxes.append(cb[keep])
+        sel_labels.append(torch.full([keep.shape[0]], c, dtype=torch.int64, device=box_preds.device))
+        sel_scores.append(scores[keep])
+        if cd is not None:
+            sel_dir.append(cd[keep])
+    if not sel_boxes:
+        z = torch.zeros([0], dtype=torch.long, device=box_preds.device)
+        return box_preds[z], z, total_scores[z, 0], (z if dir_labels is not None else None)
+    return (torch.cat(sel_boxes), torch.cat(sel_labels), torch.cat(sel_scores),
+            torch.cat(sel_dir) if dir_labels is not None else None)
+
+
+def _voxelnet_finish_frame(self, sel_boxes, sel_scores, sel_labels, sel_dir, post_center_range, meta, like):
+    """direction fix-up + post_center_range test + result dict (voxelnet.py:594-645)."""
+    cfg = self.cfg
+    if sel_boxes.shape[0] != 0:
+        sel_boxes = sel_boxes.clone()
+        if cfg.use_direction_classifier:
+            period = 2 * np.pi / cfg.num_direction_bins
+            dir_rot = box_ops.limit_period(sel_boxes[..., 6] - cfg.direction_offset, cfg.direction_limit_offset, period)
+            sel_boxes[..., 6] = dir_rot + cfg.direction_offset + period * sel_dir.to(sel_boxes.dtype)
+        if post_center_range is not None:
+            m = (sel_boxes[:, :3] >= post_center_range[:3]).all(1)
+            m &= (sel_boxes[:, :3] <= post_center_range[3:]).all(1)
+            sel_boxes, sel_scores, sel_labels = sel_boxes[m], sel_scores[m], sel_labels[m]
+        return {"box3d_lidar": sel_boxes, "scores": sel_scores, "label_preds": sel_labels, "metadata": meta}
+    dev, dt = like.device, like.dtype
+    return {"box3d_lidar": torch.zeros([0, cfg.box_code_size], dtype=dt, device=dev),
+            "scores": torch.zeros([0], dtype=dt, device=dev),
+            "label_preds": torch.zeros([0], dtype=torch.long, device=dev), "metadata": meta}
+
+
+VoxelNet._nms = _voxelnet_nms
+VoxelNet._predict_multiclass = _voxelnet_predict_multiclass
+VoxelNet._finish_frame = _voxelnet_finish_frame
 
 
 def build_network(cfg, backend):

@@ -85,6 +85,97 @@ __global__ void k_decode_filter(const float *__restrict__ box, const float *__re
     cand_anchor[slot] = a;
 }
 
+// Per-class variant for the multi-class NMS branch (voxelnet.py:458-547): one candidate list per (class, frame) --
+// "virtual frame" v = c*batch + b, class-major so that one class's frames are contiguous.  An anchor joins class c's
+// list when its class-c sigmoid score passes that class's threshold and (unless class-agnostic) the anchor belongs
+// to class c's anchor range [cls_lo[c], cls_hi[c]) of a_loc indices (target_assigner.anchors_range).  The label of
+// every candidate of list (c, b) is c.
+struct ClassRanges {
+    int lo[16], hi[16];
+    float thresh[16];
+};
+
+__global__ void k_decode_filter_mc(const float *__restrict__ box, const float *__restrict__ cls,
+                                   const float *__restrict__ dir, HeadStrides hs, const float *__restrict__ anchors,
+                                   int batch, int a_loc, int H, int W, int code, int ncls, int nbins, ClassRanges cr,
+                                   float *cand_box, float *cand_score, int *cand_label, int *cand_dir,
+                                   int *cand_anchor, int *cand_count, int cand_cap, unsigned *status)
+{
+    const int HW = H * W;
+    const int A = a_loc * HW;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)batch * A) return;
+    const int b = (int)(gid / A), a = (int)(gid % A);
+    const int al = a / HW, hw = a % HW;
+    const size_t cs = (size_t)hs.cs, ps = (size_t)hs.ps;
+    const float *cp = cls + (size_t)b * hs.cls_b + (size_t)al * ncls * cs + (size_t)hw * ps;
+    bool decoded = false;
+    float o[kMaxCode];
+    int dl = 0;
+    for (int c = 0; c < ncls; ++c) {
+        if (al < cr.lo[c] || al >= cr.hi[c]) continue;
+        const float score = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-__ldg(cp + (size_t)c * cs))));
+        if (!(score >= cr.thresh[c])) continue;
+        if (!decoded) {
+            const float *bp = box + (size_t)b * hs.box_b + (size_t)al * code * cs + (size_t)hw * ps;
+            const float *an = anchors + (size_t)a * code;
+            float t[kMaxCode], q[kMaxCode];
+            for (int i = 0; i < code; ++i) { t[i] = __ldg(bp + (size_t)i * cs); q[i] = __ldg(&an[i]); }
+            const float diag = sqrtf(__fadd_rn(__fmul_rn(q[4], q[4]), __fmul_rn(q[3], q[3])));
+            o[0] = __fadd_rn(__fmul_rn(t[0], diag), q[0]);
+            o[1] = __fadd_rn(__fmul_rn(t[1], diag), q[1]);
+            o[2] = __fadd_rn(__fmul_rn(t[2], q[5]), q[2]);
+            o[3] = __fmul_rn(expf(t[3]), q[3]);
+            o[4] = __fmul_rn(expf(t[4]), q[4]);
+            o[5] = __fmul_rn(expf(t[5]), q[5]);
+            o[6] = __fadd_rn(t[6], q[6]);
+            for (int i = 7; i < code; ++i) o[i] = __fadd_rn(t[i], q[i]);
+            if (dir != nullptr) {
+                const float *dp = dir + (size_t)b * hs.dir_b + (size_t)al * nbins * cs + (size_t)hw * ps;
+                float bd = __ldg(dp);
+                for (int k = 1; k < nbins; ++k) {
+                    float v = __ldg(dp + (size_t)k * cs);
+                    if (v > bd) { bd = v; dl = k; }
+                }
+            }
+            decoded = true;
+        }
+        const int v = c * batch + b;
+        int pos = atomicAdd(&cand_count[v], 1);
+        if (pos >= cand_cap) { atomicOr(status, B2S_STATUS_CAND_OVERFLOW); continue; }
+        const size_t slot = (size_t)v * cand_cap + pos;
+        float *cb = cand_box + slot * code;
+        for (int i = 0; i < code; ++i) cb[i] = o[i];
+        cand_score[slot] = score;
+        cand_label[slot] = c;
+        cand_dir[slot] = dl;
+        cand_anchor[slot] = a;
+    }
+}
+
+// concatenate the per-class NMS results of one frame in class order (voxelnet.py:528-533): in [ncls*B, post_max, S]
+// + counts [ncls*B] (class-major) -> record b: rows, then (det_frame_stride > rows*S) the count as a float
+__global__ void k_concat_classes(const float *__restrict__ det_mc, const int *__restrict__ cnt_mc, int batch, int ncls,
+                                 int post_max, int S, float *det, int det_frame_stride, int *det_count)
+{
+    const int b = blockIdx.x;
+    __shared__ int s_off[17];
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int c = 0; c < ncls; ++c) { s_off[c] = off; off += min(cnt_mc[c * batch + b], post_max); }
+        s_off[ncls] = off;
+        det_count[b] = off;
+        if (det_frame_stride > ncls * post_max * S) det[(size_t)b * det_frame_stride + det_frame_stride - 1] = (float)off;
+    }
+    __syncthreads();
+    for (int c = 0; c < ncls; ++c) {
+        const int n = s_off[c + 1] - s_off[c];
+        const float *src = det_mc + (size_t)(c * batch + b) * post_max * S;
+        float *dst = det + (size_t)b * det_frame_stride + (size_t)s_off[c] * S;
+        for (int i = threadIdx.x; i < n * S; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------------
@@ -560,6 +651,58 @@ extern "C" int b2s_decode_filter_strided(const float *box, const float *cls, con
     return decode_filter_launch(box, cls, dir, hs, anchors, anchors_mask, batch, a_loc, H, W, code, ncls, nbins,
                                 score_thresh, cand_box, cand_score, cand_label, cand_dir, cand_anchor, cand_count_dev,
                                 cand_cap, status_dev, (cudaStream_t)stream_);
+}
+
+// multi-class NMS branch: per-(class, frame) candidate lists (class-major virtual frames, see k_decode_filter_mc).
+// Head tensors by strides like b2s_decode_filter_strided.  class_lo/class_hi: a_loc index range per class (host
+// [ncls]; NULL = class-agnostic: every anchor competes in every class); score_thresh host [ncls].
+extern "C" int b2s_decode_filter_multiclass(const float *box, const float *cls, const float *dir,
+                                            long long box_batch_stride, long long cls_batch_stride,
+                                            long long dir_batch_stride, int ch_stride, int pix_stride,
+                                            const float *anchors, int batch, int a_loc, int H, int W, int code, int ncls,
+                                            int nbins, const int *class_lo, const int *class_hi,
+                                            const float *score_thresh, float *cand_box, float *cand_score,
+                                            int *cand_label, int *cand_dir, int *cand_anchor, int *cand_count_dev,
+                                            int cand_cap, unsigned *status_dev, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(code >= 7 && code <= kMaxCode && ncls >= 1 && ncls <= 16 && batch >= 1 && a_loc >= 1 && cand_cap >= 1,
+                "b2s_decode_filter_multiclass: bad sizes (ncls <= 16)");
+    B2S_REQUIRE(score_thresh != nullptr && ((class_lo == nullptr) == (class_hi == nullptr)),
+                "b2s_decode_filter_multiclass: score_thresh required; class_lo/class_hi both or neither");
+    HeadStrides hs;
+    hs.box_b = box_batch_stride; hs.cls_b = cls_batch_stride; hs.dir_b = dir_batch_stride;
+    hs.cs = ch_stride; hs.ps = pix_stride;
+    ClassRanges cr;
+    for (int c = 0; c < 16; ++c) {
+        cr.lo[c] = (c < ncls && class_lo) ? class_lo[c] : 0;
+        cr.hi[c] = (c < ncls && class_hi) ? class_hi[c] : a_loc;
+        cr.thresh[c] = c < ncls ? score_thresh[c] : 2.f;
+    }
+    B2S_CUDA_OK(cudaMemsetAsync(cand_count_dev, 0, sizeof(int) * (size_t)batch * ncls, stream));
+    long long total = (long long)batch * a_loc * H * W;
+    k_decode_filter_mc<<<b2s_cdiv(total, 256), 256, 0, stream>>>(box, cls, dir, hs, anchors, batch, a_loc, H, W, code, ncls,
+                                                                nbins, cr, cand_box, cand_score, cand_label, cand_dir,
+                                                                cand_anchor, cand_count_dev, cand_cap, status_dev);
+    B2S_LAUNCH_OK();
+    return 0;
+}
+
+// det_mc [ncls*batch, post_max, code+2] + count_mc [ncls*batch] (class-major, the b2s_nms outputs of the virtual
+// frames) -> per-frame records in class order; det / det_frame_stride / det_count_dev as in b2s_nms with
+// ncls*post_max rows per frame.
+extern "C" int b2s_concat_class_detections(const float *det_mc, const int *count_mc, int batch, int ncls, int post_max,
+                                           int code, float *det, int det_frame_stride, int *det_count_dev, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    B2S_REQUIRE(batch >= 1 && ncls >= 1 && ncls <= 16 && post_max >= 1, "b2s_concat_class_detections: bad sizes");
+    const int S = code + 2;
+    if (det_frame_stride == 0) det_frame_stride = ncls * post_max * S;
+    B2S_REQUIRE(det_frame_stride >= ncls * post_max * S, "b2s_concat_class_detections: det_frame_stride too small");
+    k_concat_classes<<<batch, 256, 0, stream>>>(det_mc, count_mc, batch, ncls, post_max, S, det, det_frame_stride,
+                                                det_count_dev);
+    B2S_LAUNCH_OK();
+    return 0;
 }
 
 extern "C" size_t b2s_nms_workspace_bytes(int batch, int cand_cap, int pre_max)

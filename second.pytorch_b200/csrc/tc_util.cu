@@ -8,9 +8,10 @@ namespace {
 
 // one thread per (row, 8-channel group of the OUTPUT row): reads up to 8 floats, writes 16 bytes per plane
 __global__ void k_split_f16(const float *__restrict__ x, __half *__restrict__ hi, __half *__restrict__ lo,
-                            const int *__restrict__ n_rows_dev, int cap_rows, int row_floats, int out_stride)
+                            const int *__restrict__ n_rows_dev, int cap_rows, int row_floats, int out_channels,
+                            int out_stride)
 {
-    const int groups = out_stride / 8;
+    const int groups = out_channels / 8;
     const long long n = (long long)(n_rows_dev ? min(*n_rows_dev, cap_rows) : cap_rows) * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / groups;
@@ -52,19 +53,21 @@ inline int grid_for(long long items)
 
 }  // namespace
 
-// x [rows, row_floats] fp32 -> hi = fp16(x), lo = fp16(x - hi) as rows of out_stride halves (out_stride >= row_floats,
-// multiple of 8; columns past row_floats are written as zeros).  rows = *num_rows_dev (NULL: cap_rows).
+// x [rows, row_floats] fp32 -> hi = fp16(x), lo = fp16(x - hi): out_channels halves per row and plane (>= row_floats,
+// multiple of 8; columns past row_floats are written as zeros), rows out_stride halves apart (>= out_channels,
+// multiple of 8 -- e.g. 2*out_channels for interleaved [row][hi | lo] storage).  rows = *num_rows_dev (NULL: cap_rows).
 extern "C" int b2s_split_f16(const float *x, b2s_half *hi, b2s_half *lo, const int *num_rows_dev, int cap_rows,
-                             int row_floats, int out_stride, void *stream_)
+                             int row_floats, int out_channels, int out_stride, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    B2S_REQUIRE(row_floats >= 1 && out_stride >= row_floats && out_stride % 8 == 0 && cap_rows >= 0,
-                "b2s_split_f16: out_stride must be a multiple of 8 and >= row_floats");
+    B2S_REQUIRE(row_floats >= 1 && out_channels >= row_floats && out_channels % 8 == 0 && out_stride >= out_channels &&
+                    out_stride % 8 == 0 && cap_rows >= 0,
+                "b2s_split_f16: out_channels / out_stride must be multiples of 8, out_stride >= out_channels >= row_floats");
     B2S_REQUIRE(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "b2s_split_f16: planes must be 16-byte aligned");
-    const long long items = (long long)cap_rows * (out_stride / 8);
+    const long long items = (long long)cap_rows * (out_channels / 8);
     if (items == 0) return 0;
     k_split_f16<<<grid_for(items), 256, 0, stream>>>(x, reinterpret_cast<__half *>(hi), reinterpret_cast<__half *>(lo),
-                                                     num_rows_dev, cap_rows, row_floats, out_stride);
+                                                     num_rows_dev, cap_rows, row_floats, out_channels, out_stride);
     B2S_LAUNCH_OK();
     return 0;
 }

@@ -280,11 +280,11 @@ class SparseConvolution(SparseModule):
 
     def forward(self, input, _epilogue=None):
         assert isinstance(input, SparseConvTensor)
-        if self.training:
+        if self.training and torch.is_grad_enabled() and self.weight.requires_grad:
             # upstream implements indice_conv_backward; this drop-in covers the inference path only.
-            # Failing here beats silently returning zero gradients for the middle extractor.  (eval() with autograd
-            # enabled is the reference's own inference mode -- voxelnet.py:368-374 -- and runs; the outputs simply
-            # carry no grad_fn.)
+            # A training-mode call that autograd would record must fail instead of silently returning gradient-free
+            # tensors.  (eval() with autograd enabled is the reference's own inference mode -- voxelnet.py:368-374 --
+            # and runs; so does anything under torch.no_grad().)
             raise NotImplementedError("b2second spconv: training / autograd through sparse convolutions is not "
                                       "implemented (inference drop-in); call net.eval() and run under torch.no_grad()")
         lib = _lib.load()
@@ -329,7 +329,7 @@ class SparseConvolution(SparseModule):
                 hi, lo, stride = buf[:, 0], buf[:, 1], 2 * cin_tc
                 if n_in > 0:
                     _lib.check(lib.b2s_split_f16(_lib.ptr(feats), _lib.ptr(hi), _lib.ptr(lo), None, n_in,
-                                                 self.in_channels, stride, _lib.stream()), "b2s_split_f16")
+                                                 self.in_channels, cin_tc, stride, _lib.stream()), "b2s_split_f16")
                 input._hilo = (hi[:n_in], lo[:n_in], stride)
             w_hi, w_lo, ws, inv = self._tc_weights(cin_tc)
             scale_tc = inv if scale is None else (scale / ws).contiguous()

@@ -43,6 +43,22 @@ def assert_detections_close(got, fix, box_tol=1e-4, score_tol=1e-5):
     rb, rs, rl = fix["box3d_lidar"], fix["scores"], fix["label_preds"]
     assert gb.shape == rb.shape, "detection count differs: got %d, golden %d" % (gb.shape[0], rb.shape[0])
     np.testing.assert_allclose(gs, rs, rtol=0, atol=score_tol)
+    # detections arrive in descending score order; among (numerically) EQUAL scores the order is whatever torch.topk /
+    # the sort produced -- unspecified upstream -- so rows inside a run of tied scores are matched by nearest centre
+    order = np.arange(len(rs))
+    i = 0
+    while i < len(rs):
+        j = i + 1
+        while j < len(rs) and abs(float(rs[j]) - float(rs[i])) <= 2 * score_tol:
+            j += 1
+        if j - i > 1:
+            free = list(range(i, j))
+            for a in range(i, j):
+                k = min(free, key=lambda q: float(np.abs(gb[q, :3] - rb[a, :3]).sum()))
+                free.remove(k)
+                order[a] = k
+        i = j
+    gb, gs, gl = gb[order], gs[order], gl[order]
     # labels: argmax over class logits; only decided where the top-2 logit margin is above fp32 noise
     decided = np.asarray(fix["label_margin"]) > 1e-3 if "label_margin" in fix else np.ones(rl.shape, bool)
     np.testing.assert_array_equal(gl[decided], rl[decided])

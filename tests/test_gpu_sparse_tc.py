@@ -57,8 +57,8 @@ def test_sparse_conv_tc_matches_oracle(product, oracle, cin, cout, subm, n):
     f_hi, f_lo, fstride = fbuf[:, 0], fbuf[:, 1], 2 * cin_tc
     feats_d = feats.cuda()
     n_in_dev = torch.tensor([n_in], dtype=torch.int32, device="cuda")
-    L.check(lib.b2s_split_f16(L.ptr(feats_d), L.ptr(f_hi), L.ptr(f_lo), L.ptr(n_in_dev), n_in, cin, fstride, L.stream()),
-            "b2s_split_f16")
+    L.check(lib.b2s_split_f16(L.ptr(feats_d), L.ptr(f_hi), L.ptr(f_lo), L.ptr(n_in_dev), n_in, cin, cin_tc, fstride,
+                              L.stream()), "b2s_split_f16")
     ref_hi, ref_lo = tc.split_f16(feats_d)
     torch.cuda.synchronize()
     assert torch.equal(f_hi[:n_in, :cin], ref_hi) and torch.equal(f_lo[:n_in, :cin], ref_lo)   # device split == host split
@@ -135,4 +135,6 @@ def test_drop_in_sparse_sequential_runs_on_tensor_cores(product, oracle):
     # training mode must fail loudly instead of returning gradient-free tensors
     net.train()
     with pytest.raises(NotImplementedError):
+        net(product.SparseConvTensor(feats.cuda(), idx.cuda(), shape, batch))
+    with torch.no_grad():                                          # nothing to record: allowed
         net(product.SparseConvTensor(feats.cuda(), idx.cuda(), shape, batch))

@@ -111,6 +111,37 @@ def test_engine_plan_from_reference_network_equals_plan_from_mirror(ref_env, nam
                 assert o1[k] == o2[k], k
 
 
+@pytest.mark.parametrize("name,agnostic", [("all.fhd", False), ("nuscenes.all.pp.largea", True)])
+def test_multiclass_nms_branch_mirror_equals_reference(ref_env, name, agnostic):
+    """the per-class NMS branch of predict() (voxelnet.py:458-547; off in the five BASELINE configs):
+    the UNMODIFIED reference network with use_multi_class_nms switched on vs the mirror, on the CPU oracle."""
+    import dataclasses
+    cfgp = refcompat.load_config(config.REFERENCE_FILES[name])
+    for cs in cfgp.model.second.target_assigner.class_settings:
+        cs.use_multi_class_nms = True
+    cfgp.model.second.nms_class_agnostic = agnostic
+    ref = refcompat.build_network(cfgp.model.second).eval()
+    assert ref._multiclass_nms and ref._nms_class_agnostic == agnostic
+    b = dataclasses.replace(config.get_config(name), use_multi_class_nms=True, nms_class_agnostic=agnostic)
+    mine = models.build_network(b, ref_env).eval()
+    models.synthetic_weights_(ref, name)
+    models.synthetic_weights_(mine, name)
+    a_ref = refcompat.generate_anchors(ref, cfgp.model.second)
+    pts = synth.nuscenes_cloud(1, 40000) if "nuscenes" in name else synth.kitti_cloud(4, 12000, b.point_cloud_range)
+    res = ref.voxel_generator.generate(pts, b.max_voxels)
+    coords = np.pad(res["coordinates"], ((0, 0), (1, 0)))
+
+    def ex():
+        return {"anchors": torch.from_numpy(a_ref[None].copy()), "voxels": torch.from_numpy(res["voxels"]),
+                "num_points": torch.from_numpy(res["num_points_per_voxel"]), "coordinates": torch.from_numpy(coords)}
+    with torch.no_grad():
+        o_r, o_m = ref(ex())[0], mine(ex())[0]
+    assert o_r["box3d_lidar"].shape == o_m["box3d_lidar"].shape and o_r["box3d_lidar"].shape[0] > 0
+    assert len(set(o_r["label_preds"].tolist())) > 1                      # more than one class produced detections
+    assert torch.allclose(o_r["box3d_lidar"], o_m["box3d_lidar"], atol=1e-6)
+    assert torch.equal(o_r["label_preds"], o_m["label_preds"]) and torch.allclose(o_r["scores"], o_m["scores"])
+
+
 def test_reference_builds_on_cuda_dropin_in_subprocess():
     """`import spconv` == second.pytorch_b200/spconv; the reference's second_builder constructs VoxelNet on it."""
     code = r"""
