@@ -209,7 +209,9 @@ class InferenceEngine:
         self.vox_num = torch.zeros(cap, dtype=torch.int32, device=dev)
         self.vox_slots = torch.zeros(cap, self.T, dtype=torch.int32, device=dev)
         self.num_voxels = torch.zeros(1 + self.B, dtype=torch.int32, device=dev)
-        self.vox_hcap = lib.b2s_voxelize_hash_capacity(self.P_cap)
+        # the voxelizer's hash doubles as level 0's coordinate->row locator: sized for the points it must absorb AND
+        # (pre-voxelised entry, b2s_hash_build) for 2x the voxel rows
+        self.vox_hcap = max(lib.b2s_voxelize_hash_capacity(self.P_cap), _pow2_at_least(2 * cap))
         self.vox_keys = torch.empty(self.vox_hcap, dtype=torch.int64, device=dev)
         self.vox_vals = torch.empty(self.vox_hcap, dtype=torch.int32, device=dev)
         self.vox_ws_bytes = lib.b2s_voxelize_workspace_bytes(self.P_cap, self.B, self.max_voxels, self.T)

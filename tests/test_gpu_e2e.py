@@ -48,7 +48,8 @@ def test_module_path_matches_golden(product, name, seed, n, path):
         pd = net.rpn(sf)
         out = net(ex)[0]
     assert list(sf.shape) == fix["bev_shape"].tolist()
-    assert int((sf != 0).sum()) == int(fix["bev_nonzero"])
+    # active sites are exact; a feature within rounding of the ReLU kink may be +-0 on one side, tiny on the other
+    assert abs(int((sf != 0).sum()) - int(fix["bev_nonzero"])) <= max(2, int(fix["bev_nonzero"]) // 20000)
     np.testing.assert_allclose(sf.flatten()[torch.from_numpy(fix["bev_sel_idx"]).cuda()].cpu().numpy(),
                                fix["bev_sel_val"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(pd["box_preds"].flatten()[torch.from_numpy(fix["box_sel_idx"]).cuda()].cpu().numpy(),
