@@ -65,6 +65,26 @@ typedef uint16_t b2s_half;
 int b2s_version(void);
 const char *b2s_last_error(void);
 
+/* ---- on-GPU input path in front of the voxelizer ------------------------------- */
+/* One NuScenes sweep -> rows [x', y', z', time_lag] of the merged cloud (second/data/nuscenes_dataset.py:166-185):
+ * (x', y', z') = float32(float32(p @ R^T, computed in float64) + t), rotation_host row-major [3,3] / translation_host [3]
+ * float64 (NULL rotation: the key-frame sweep, copied as is).  points_in [P, feat_in] (x, y, z first); out [P, 4],
+ * 16-byte aligned (pass the merged buffer advanced to the sweep's first row). */
+int b2s_transform_sweep(const float *points_in, int num_points, int feat_in, const double *rotation_host,
+                        const double *translation_host, float time_lag, float *out, void *stream);
+
+/* Keep the points strictly inside a convex polytope, in input order: inside <=> a x + b y + c z + d < 0 (float64)
+ * for every plane (a, b, c, d) of planes_host [num_planes, 4] -- the KITTI camera-frustum crop
+ * remove_outside_points (second/core/box_np_ops.py:682-693) with the plane equations of
+ * surface_equ_3d_jitv2 (second/core/geometry.py:332-355).  The kept points of this frame are written to
+ * out_points[offsets_dev[0] ...] (rows of num_feat floats) and offsets_dev[1] = offsets_dev[0] + kept: calling it for
+ * frames 0..B-1 with offsets_dev + b fills the voxelizer's point buffer and frame_offsets without a host sync.
+ * Rows that would pass out_cap_rows are dropped (B2S_STATUS_ROWS_OVERFLOW). */
+size_t b2s_crop_workspace_bytes(int num_points);
+int b2s_crop_convex(const float *points, int num_points, int num_feat, const double *planes_host, int num_planes,
+                    float *out_points, int out_cap_rows, int *offsets_dev, void *workspace, size_t workspace_bytes,
+                    unsigned *status_dev, void *stream);
+
 /* ---- voxelizer -------------------------------------------------------------------------------- */
 /* VFE modes fused into the voxelizer */
 #define B2S_VFE_NONE 0

@@ -214,7 +214,9 @@ class InferenceEngine:
         self.vox_hcap = max(lib.b2s_voxelize_hash_capacity(self.P_cap), _pow2_at_least(2 * cap))
         self.vox_keys = torch.empty(self.vox_hcap, dtype=torch.int64, device=dev)
         self.vox_vals = torch.empty(self.vox_hcap, dtype=torch.int32, device=dev)
-        self.vox_ws_bytes = lib.b2s_voxelize_workspace_bytes(self.P_cap, self.B, self.max_voxels, self.T)
+        # the workspace holds one int per hash slot: query it for a point count whose own hash capacity is vox_hcap
+        self.vox_ws_bytes = lib.b2s_voxelize_workspace_bytes(max(self.P_cap, self.vox_hcap // 2), self.B,
+                                                             self.max_voxels, self.T)
         self.vox_ws = torch.empty(max(self.vox_ws_bytes, 1), dtype=torch.uint8, device=dev)
         if s.vfe_kind == "mean":
             self.vfe_mode, self.vfe_nf, c = 1, s.vfe_num_features, s.vfe_num_features
@@ -665,6 +667,43 @@ class InferenceEngine:
         self.offsets.copy_(offs.pin_memory(), non_blocking=True)
         return total
 
+    def load_points_cropped(self, frames, planes):
+        """frames: list of B CUDA float32 [P_i, F] raw clouds; planes: one [n,4] float64 array per frame (or one for
+        all): the points strictly inside the convex region (``b2second.inputs.frustum_planes``: the KITTI camera-FOV
+        crop, box_np_ops.py:682-693) are compacted on the device straight into the static point buffer, in input
+        order, and ``offsets`` is filled on the device -- no host sync, no host copy of the cropped cloud."""
+        from . import inputs
+        assert len(frames) == self.B
+        if not isinstance(planes, (list, tuple)):
+            planes = [planes] * self.B
+        if getattr(self, "_crop", None) is None:
+            self._crop = inputs.ConvexCrop(self.P_cap, self.dev)
+            self.in_status = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self.offsets.zero_()
+            self._crop_keep = [self._crop.crop_into(f if f.is_cuda else f.to(self.dev, non_blocking=True), pl,
+                                                    self.points, self.offsets, b, self.in_status)
+                               for b, (f, pl) in enumerate(zip(frames, planes))]
+
+    def load_sweeps(self, frames):
+        """frames: list of B dicts {"sweeps": [CUDA float32 [P_i, F>=3], key frame first], "rotations": [..[3,3]..],
+        "translations": [..[3]..], "time_lags": [..]} (the ``sweep2lidar_*`` fields of a NuScenes info record).  The
+        merged [x, y, z, dt] cloud of every frame (nuscenes_dataset.py:166-185) is written straight into the static
+        point buffer."""
+        from . import inputs
+        assert len(frames) == self.B and self.F == 4, "sweep merging produces [x, y, z, dt] rows"
+        sizes = [sum(int(s.shape[0]) for s in fr["sweeps"]) for fr in frames]
+        assert sum(sizes) <= self.P_cap, "more points (%d) than the engine's capacity (%d)" % (sum(sizes), self.P_cap)
+        off = 0
+        with torch.cuda.device(self.dev):
+            for fr, n in zip(frames, sizes):
+                sw = [s if s.is_cuda else s.to(self.dev, non_blocking=True) for s in fr["sweeps"]]
+                inputs.merge_sweeps(sw, fr["rotations"], fr["translations"], fr["time_lags"], out=self.points[off:off + n])
+                off += n
+            offs = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32)
+            self.offsets.copy_(offs.pin_memory(), non_blocking=True)
+        return off
+
     def load_voxels(self, voxels, num_points, coordinates):
         """the reference's example tensors (voxels [N,T,F], num_points [N], coordinates [N,4] (b,z,y,x)), on any
         device, -> static buffers.  N is known on the host (a tensor shape): no sync."""
@@ -722,6 +761,9 @@ class InferenceEngine:
     def check_status(self):
         """sync + raise on data-dependent overflow (call when results are read back)."""
         st = int(self.status.item())
+        if getattr(self, "in_status", None) is not None:
+            if int(self.in_status.item()):
+                raise RuntimeError("b2second engine: cropped clouds exceed the point buffer (max_points)")
         if st & ~1:   # bit 1 (voxel overflow) is the reference's own drop-extra-voxels behaviour
             raise RuntimeError("b2second engine: " + self._L.status_message(st))
         return st

@@ -14,7 +14,10 @@ runs as one CUDA graph per frame batch (``b2second.engine.InferenceEngine``).  A
   engine's static buffers and everything after the voxelizer is fused;
 * the same dict with ``points`` (a list of B float32 ``[P_i, F]`` tensors: CUDA, pinned or plain host memory)
   instead of the three voxel keys -- then the voxelizer runs on the GPU as well (SURVEY.md §8b "a fast path may
-  additionally accept example['points']").
+  additionally accept example['points']"); with ``crop_planes`` (``b2second.inputs.frustum_planes``) the raw clouds
+  are first cropped to the camera field of view on the GPU (the ``velodyne_reduced`` step, box_np_ops.py:682-693);
+* ``sweeps``: per frame the NuScenes key-frame cloud + its sweeps with their ``sweep2lidar`` calibration, merged on
+  the GPU (nuscenes_dataset.py:166-185) -- see ``InferenceEngine.load_sweeps``.
 
 The list of result dicts holds GPU tensors like the reference's (``output="device"``); ``accelerate(net,
 output="host")`` returns CPU tensors through ONE pinned device-to-host copy of the detection records instead of one
@@ -57,15 +60,15 @@ class FastPath:
     def applicable(self, example):
         if self.net.training:
             return False
-        if "points" in example:
+        if "points" in example or "sweeps" in example:
             return True
         if not all(k in example for k in ("voxels", "num_points", "coordinates")):
             return False
         return example["num_points"].dim() == 1          # 2-D = DataParallel padded layout (voxelnet.py:345-357)
 
     def __call__(self, example):
-        if "points" in example:
-            frames = example["points"]
+        if "points" in example or "sweeps" in example:
+            frames = example["points"] if "points" in example else example["sweeps"]
             B = len(frames)
         else:
             B = int(example["anchors"].shape[0])
@@ -76,7 +79,13 @@ class FastPath:
         elif eng._anchors_key is None:
             raise KeyError("example has no 'anchors' and the network cannot generate them")
         eng.set_anchors_mask(example.get("anchors_mask"))
-        if "points" in example:
+        if "sweeps" in example:
+            eng.load_sweeps(list(frames))             # NuScenes: key frame + sweeps merged on the GPU
+            eng.run("points")
+        elif "points" in example and example.get("crop_planes") is not None:
+            eng.load_points_cropped(list(frames), example["crop_planes"])    # KITTI: camera-FOV crop on the GPU
+            eng.run("points")
+        elif "points" in example:
             eng.infer(list(frames))
         else:
             eng.infer_voxels(example["voxels"], example["num_points"], example["coordinates"])

@@ -158,7 +158,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             int acc = 0;
             uint32_t acc_phase = 0;
             const bool timing = (p.flags & 16) != 0;
-            long long t_full = 0, t_tempty = 0, t_begin = clock64();
+            long long t_full = 0, t_tempty = 0, t_fence = 0, t_begin = clock64();
             int n_kb = 0;
             mbar_wait(&bar_tempty[0], 1);
             mbar_wait(&bar_full[0], 0);
@@ -192,8 +192,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                             mbar_wait(&bar_full[stn], phn);
                             const long long w1 = timing ? clock64() : 0;
                             if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
+                            const long long w2 = timing ? clock64() : 0;
                             tc_fence_after();
-                            if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; ++n_kb; }
+                            if (timing) { t_full += w1 - w0; t_tempty += w2 - w1; t_fence += clock64() - w2; ++n_kb; }
                         }
                         {
                             const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
@@ -209,9 +210,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             }
             if (timing && blockIdx.x == 0)
                 printf("[sparse_tc<%d,%d>] issuer: %d K blocks, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
-                       "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
+                       "wait tempty %lld (%.0f/kb), fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
                        (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1), t_tempty,
-                       (double)t_tempty / (n_kb + 1));
+                       (double)t_tempty / (n_kb + 1), t_fence, (double)t_fence / (n_kb + 1));
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 4 + GW) {
@@ -239,9 +240,14 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         const uint32_t copy_mask = (p.flags & 2) ? 0u : 0xFFu;  // diagnostic bit 2: no copies at all
         const uint32_t smem0 = smem_u32(smem);
 
+        const bool timing_g = (p.flags & 16) != 0 && blockIdx.x == 0 && gw == 0 && lane == 0;
+        long long tg_empty = 0, tg_stage = 0, tg_begin = clock64();
+        int tg_kb = 0;
         // one K block: wait for the stage, issue this lane's (predicated) copies, arrive
         auto copy_block = [&](uint32_t valid, const char *const *g_hi, const char *const *g_lo, int byte_off) {
+            const long long te0 = timing_g ? clock64() : 0;
             mbar_wait(&bar_empty[stage], phase ^ 1);
+            if (timing_g) { tg_empty += clock64() - te0; ++tg_kb; }
             const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
             const uint32_t zst = (zeroed >> (stage * 8)) & 0xFFu;          // slots of this stage holding zeros
             const uint32_t need = (valid | ~zst | (zskip_on ? 0u : 0xFFu)) & copy_mask;
@@ -260,6 +266,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             // stage the tile's neighbour table in shared memory (coalesced), shared by the gather warps
+            const long long ts0 = timing_g ? clock64() : 0;
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");     // previous tile's readers are done
             {
                 const int row0 = tile * BLOCK_M;
@@ -283,6 +290,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
+            if (timing_g) tg_stage += clock64() - ts0;
             if constexpr (!PACKED) {
                 // addresses and validity are constant per kernel offset; the channel chunks are unrolled so that
                 // ch * 128 folds into the copy instructions' address immediates
@@ -320,18 +328,28 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
+        if (timing_g)
+            printf("[sparse_tc<%d,%d>] gather warp 0: %d K blocks, total %lld cyc (%.0f/kb), wait empty %lld (%.0f/kb), "
+                   "nbr-table staging %lld (%.0f/kb)\n", CIN, COUT, tg_kb, clock64() - tg_begin,
+                   (double)(clock64() - tg_begin) / (tg_kb + 1), tg_empty, (double)tg_empty / (tg_kb + 1), tg_stage,
+                   (double)tg_stage / (tg_kb + 1));
     } else if (warp >= 4 + GW) {
         // ===================== epilogue =====================
         const int ew = warp - (4 + GW);                // == warp % 4: TMEM lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool timing_e = (p.flags & 16) != 0 && blockIdx.x == 0 && ew == 0 && lane == 0;
+        long long te_wait = 0, te_drain = 0, te_store = 0, te_begin = clock64();
+        int te_chains = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;
             for (int g = 0; g < num_chains; ++g) {
+                const long long e0 = timing_e ? clock64() : 0;
                 mbar_wait(&bar_tfull[acc], acc_phase);
                 tc_fence_after();
+                const long long e1 = timing_e ? clock64() : 0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_W);
 #pragma unroll
                 for (int c0 = 0; c0 < N; c0 += 16) {
@@ -349,7 +367,9 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_tempty[acc]);
                 if (++acc == ACC_SLOTS) { acc = 0; acc_phase ^= 1; }
+                if (timing_e) { te_wait += e1 - e0; te_drain += clock64() - e1; ++te_chains; }
             }
+            const long long es0 = timing_e ? clock64() : 0;
             // coalesced stores: transpose 32 rows x CW channels through a padded shared tile so every store
             // instruction writes whole contiguous row segments (a lane-per-row store is 16 B at a row stride).
             // fp16 planes: a staged row = WP words of hi pairs, then (at word 16) WP words of lo pairs; the first CP
@@ -424,7 +444,12 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 }
             }
             if (__any_sync(0xffffffffu, range_bad) && lane == 0 && p.status) atomicOr(p.status, B2S_STATUS_F16_RANGE);
+            if (timing_e) te_store += clock64() - es0;
         }
+        if (timing_e)
+            printf("[sparse_tc<%d,%d>] epilogue warp 0: %d chains, total %lld cyc, wait tfull %lld (%.0f/chain), drain %lld "
+                   "(%.0f/chain), output stage %lld\n", CIN, COUT, te_chains, clock64() - te_begin, te_wait,
+                   (double)te_wait / (te_chains + 1), te_drain, (double)te_drain / (te_chains + 1), te_store);
     }
     tc_fence_before();
     __syncthreads();

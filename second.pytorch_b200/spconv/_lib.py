@@ -22,6 +22,10 @@ _F6 = ctypes.c_float * 6
 SIGNATURES = {
     "b2s_version": (c_int, []),
     "b2s_last_error": (ctypes.c_char_p, []),
+    "b2s_transform_sweep": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "b2s_crop_workspace_bytes": (c_size_t, [c_int]),
+    "b2s_crop_convex": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t,
+                                c_void_p, c_void_p]),
     "b2s_voxelize_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b2s_voxelize_hash_capacity": (c_int, [c_int]),
     "b2s_voxelize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
