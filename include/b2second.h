@@ -145,6 +145,14 @@ int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int cap_in, in
                       unsigned long long *hash_keys_out, int *hash_vals_out, int hash_cap_out,
                       void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream);
 
+/* SubM rulebook of the level b2s_rulebook_conv has JUST produced, read off the occupancy structure that call left in
+ * `workspace` (same batch / shape, nothing else run on the workspace in between): coordinate -> row is a bit test +
+ * popcount rank, no hash table.  Pass hash_keys_out = hash_vals_out = NULL to b2s_rulebook_conv when every SubM of
+ * the produced level is built this way.  nbr as b2s_rulebook_subm. */
+int b2s_rulebook_subm_ranked(const int *coors, const int *num_rows_dev, int cap_rows, int batch, const int *shape,
+                             const int *ksize, const int *dilation, const void *workspace, size_t workspace_bytes,
+                             int *nbr, void *stream);
+
 /* pair-list view of a neighbour table (spconv's indice_pairs [K,2,L] + indice_pair_num [K]) --
  * only for parity checks / API completeness; the conv kernels consume `nbr` directly. */
 int b2s_rulebook_pairs(const int *nbr, const int *num_out_dev, int cap_out, int K, int L,

@@ -149,6 +149,12 @@ class InferenceEngine:
                 if key not in rulebooks:
                     rulebooks[key] = {"nbr": torch.empty(level.cap, K, dtype=torch.int32, device=dev)}
                     lyr["build_rb"] = True
+                    # the strided conv right before this layer produced `level`: its occupancy bitmap is still in the
+                    # rulebook workspace, so this SubM table is built by rank lookups (b2s_rulebook_subm_ranked) and
+                    # the level needs no hash table
+                    prev = self.layers[-1] if self.layers else None
+                    lyr["ranked"] = bool(prev is not None and not prev["subm"] and prev["out_level"] is level
+                                         and os.environ.get("B2S_RB_RANKED", "1") != "0")
                 else:
                     lyr["build_rb"] = False
                 lyr["rb"] = rulebooks[key]
@@ -172,6 +178,11 @@ class InferenceEngine:
             lyr["tc"] = bool(self.sparse_impl == "tc" and cin_tc is not None and (thin_ok or cin_tc >= 32) and
                              self.lib.b2s_sparse_conv_tc_supported(cin_tc, ls["cout"]))
             self.layers.append(lyr)
+        # a level's coordinate hash is only built when some SubM rulebook still looks rows up by hash
+        for lyr in self.layers:
+            if not lyr["subm"]:
+                lyr["want_hash"] = any(l["subm"] and l.get("build_rb") and l["in_level"] is lyr["out_level"]
+                                       and not l.get("ranked") for l in self.layers)
         # once a layer runs on the tensor pipe all later ones must too (hi/lo planes flow forward)
         seen_tc = False
         for lyr in self.layers:
@@ -395,7 +406,12 @@ class InferenceEngine:
                 lin, lout = lyr["in_level"], lyr["out_level"]
                 if lyr["build_rb"]:
                     self._mark("rulebook%d" % lyr["index"])
-                    if lyr["subm"]:
+                    if lyr["subm"] and lyr.get("ranked"):
+                        L.check(lib.b2s_rulebook_subm_ranked(
+                            L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, self.B, L.i3(lin.shape),
+                            L.i3(lyr["kernel_size"]), L.i3(lyr["dilation"]), L.ptr(self.rb_ws), self.rb_ws_bytes,
+                            L.ptr(lyr["rb"]["nbr"]), st), "b2s_rulebook_subm_ranked")
+                    elif lyr["subm"]:
                         L.check(lib.b2s_rulebook_subm(L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, L.i3(lin.shape),
                                                       L.i3(lyr["kernel_size"]), L.i3(lyr["dilation"]), L.ptr(lin.keys),
                                                       L.ptr(lin.vals), lin.hcap, L.ptr(lyr["rb"]["nbr"]), st),
@@ -405,7 +421,8 @@ class InferenceEngine:
                             L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, self.B, L.i3(lin.shape), L.i3(lout.shape),
                             L.i3(lyr["kernel_size"]), L.i3(lyr["stride"]), L.i3(lyr["padding"]), L.i3(lyr["dilation"]),
                             L.ptr(lin.keys), L.ptr(lin.vals), lin.hcap, L.ptr(lout.coors), L.ptr(lout.n_dev), lout.cap,
-                            L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys), L.ptr(lout.vals), lout.hcap,
+                            L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys) if lyr["want_hash"] else None,
+                            L.ptr(lout.vals) if lyr["want_hash"] else None, lout.hcap,
                             L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
                 self._mark("sparse_conv%d" % lyr["index"])
                 if lyr["tc"]:
@@ -581,7 +598,9 @@ class InferenceEngine:
             n += 1                               # b2s_pfn
         for lyr in self.layers:
             if lyr["build_rb"]:
-                n += 1 if lyr["subm"] else 6     # subm_nbr | mark, popc_scan, scan_sums, emit, hash_build, conv_nbr
+                # subm_nbr / subm_ranked | mark, summary_scan, scan_sums, compact_words, nz_scan, scan_sums, emit,
+                # (hash_build,) scatter_nbr
+                n += 1 if lyr["subm"] else (8 + (1 if lyr.get("want_hash") else 0))
             n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc
             if lyr.get("in_split") is not None:
                 n += 1                           # b2s_split_f16

@@ -11,6 +11,14 @@
 // are one step: an occupancy bitmap over the output grid plus a popcount prefix scan gives every
 // active output cell its sorted rank directly.
 //
+// The occupancy structure is two-level (round 2): a summary bitmap (one bit per 32-cell word) is set by the marking
+// pass, so ranking and emitting touch only the NON-EMPTY words (a few hundred thousand) instead of scanning the whole
+// output grid (21 x 800 x 704 x 32 frames = 11.8 M words at the first strided conv of car.fhd: k_popc_scan +
+// k_conv_emit cost 138 us per step there, ncu launch list).  Every non-empty word w also records the output row of
+// its first cell, wrow0[w]; coordinate -> row is then `bit set ? wrow0[w] + popc(bits below) : none` -- two loads, no
+// probing -- which b2s_rulebook_subm_ranked uses for the SubM table of the level a strided conv has just produced
+// (no hash table for that level at all).
+//
 // All row counts are read from device memory; grids are bounded (a few CTAs per SM) with grid-stride loops,
 // so the cost follows the live row count, not the buffer capacity (capacity-sized grids cost ~40 us per
 // launch of mostly-idle threads in the first profile).
@@ -79,7 +87,7 @@ __global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict_
 
 // one thread per input row: mark every output cell the row contributes to
 __global__ void k_conv_mark(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
-                            ConvGeom g, unsigned *bitmap)
+                            ConvGeom g, unsigned *bitmap, unsigned *summary)
 {
     const int n = min(*n_dev, cap_rows);
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
@@ -106,28 +114,36 @@ __global__ void k_conv_mark(const int *__restrict__ coors, const int *__restrict
                     unsigned long long key = b2s_flat_key(c.x, oc[0][a], oc[1][b], oc[2][e], g.out_shape[0],
                                                           g.out_shape[1], g.out_shape[2]);
                     unsigned bit = 1u << (key & 31);
-                    unsigned *w = &bitmap[key >> 5];
-                    if (!(*(volatile unsigned *)w & bit)) atomicOr(w, bit);
+                    const unsigned long long wi = key >> 5;
+                    unsigned *w = &bitmap[wi];
+                    if (!(*(volatile unsigned *)w & bit)) {
+                        // exactly one thread sees the word go from empty to non-empty: it sets the summary bit
+                        if (atomicOr(w, bit) == 0u) atomicOr(&summary[wi >> 5], 1u << (wi & 31));
+                    }
                 }
     }
 }
 
-__global__ void k_popc_scan(const unsigned *__restrict__ bitmap, long long nwords, int *word_prefix,
-                            int *block_sums)
+// level 1: exclusive scan of popc(summary word) -> rank of the first non-empty bitmap word below each summary word
+__global__ void k_summary_scan(const unsigned *__restrict__ summary, long long nsw, int *sum_prefix, int *block_sums)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int v = i < nwords ? __popc(bitmap[i]) : 0;
+    int v = i < nsw ? __popc(summary[i]) : 0;
     int total;
     int ex = b2s_block_exscan(v, &total);
-    if (i < nwords) word_prefix[i] = ex;
+    if (i < nsw) sum_prefix[i] = ex;
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void k_scan_sums(int *block_sums, int nblk, int *num_out_dev, int cap_out, unsigned *status)
+// single-block exclusive scan of per-block sums; nblk from the host, or (nblk_dev) ceil(*nblk_dev / kScanThreads).
+// total -> *total_dev (clamped to cap, raising the overflow flag, when status is given)
+__global__ void k_scan_sums(int *block_sums, int nblk_host, const int *items_dev, int *total_dev, int cap,
+                            unsigned *status)
 {
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
+    const int nblk = items_dev ? (*items_dev + kScanThreads - 1) / kScanThreads : nblk_host;
     for (int base = 0; base < nblk; base += blockDim.x) {
         int idx = base + threadIdx.x;
         int v = idx < nblk ? block_sums[idx] : 0;
@@ -141,40 +157,80 @@ __global__ void k_scan_sums(int *block_sums, int nblk, int *num_out_dev, int cap
     }
     if (threadIdx.x == 0) {
         int n = carry;
-        if (n > cap_out) { atomicOr(status, B2S_STATUS_ROWS_OVERFLOW); n = cap_out; }
-        *num_out_dev = n;
+        if (status && n > cap) { atomicOr(status, B2S_STATUS_ROWS_OVERFLOW); n = cap; }
+        *total_dev = n;
     }
 }
 
-// warp per 32 bitmap words; the bits of each non-empty word are expanded by the 32 lanes in parallel
-__global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nwords,
-                            const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
-                            ConvGeom g, int cap_out, int *coors_out, int *nbr_fill)
+// compact the non-empty bitmap words: nz_word[r] = word index, nz_cnt[r] = its popcount (r ascending in word index)
+__global__ void k_compact_words(const unsigned *__restrict__ summary, long long nsw, const int *__restrict__ sum_prefix,
+                                const int *__restrict__ block_prefix, const unsigned *__restrict__ bitmap, int *nz_word,
+                                int *nz_cnt)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nsw; i += (long long)gridDim.x * blockDim.x) {
+        unsigned sbits = summary[i];
+        if (!sbits) continue;
+        int r = block_prefix[i / kScanThreads] + sum_prefix[i];
+        while (sbits) {
+            const int j = __ffs(sbits) - 1;
+            sbits &= sbits - 1;
+            const long long w = i * 32 + j;
+            nz_word[r] = (int)w;
+            nz_cnt[r] = __popc(bitmap[w]);
+            ++r;
+        }
+    }
+}
+
+// level 2: exclusive scan of the non-empty words' popcounts in chunks of kScanThreads (bounded grid, chunk-stride)
+__global__ void k_nz_scan(int *nz_cnt /*in: counts, out: exclusive prefix inside the chunk*/, const int *__restrict__ nnz_dev,
+                          int *chunk_sums)
+{
+    const int nnz = *nnz_dev;
+    for (long long base = (long long)blockIdx.x * kScanThreads; base < nnz; base += (long long)gridDim.x * kScanThreads) {
+        const long long i = base + threadIdx.x;
+        int v = i < nnz ? nz_cnt[i] : 0;
+        int total;
+        int ex = b2s_block_exscan(v, &total);
+        if (i < nnz) nz_cnt[i] = ex;
+        if (threadIdx.x == 0) chunk_sums[base / kScanThreads] = total;
+    }
+}
+
+// warp per 32 non-empty words; the bits of each word are expanded by the 32 lanes in parallel.  Writes the output
+// coordinates (ascending flat key = the order upstream's sort + unique produces), wrow0[word] = first row of the word,
+// and pre-fills the rows' neighbour-table entries with -1.
+__global__ void k_conv_emit(const unsigned *__restrict__ bitmap, const int *__restrict__ nz_word,
+                            const int *__restrict__ nz_prefix, const int *__restrict__ chunk_prefix,
+                            const int *__restrict__ nnz_dev, ConvGeom g, int cap_out, int *coors_out, int *nbr_fill,
+                            int *wrow0)
 {
     const int lane = threadIdx.x & 31;
     const long long warps_total = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned W = g.out_shape[2], H = g.out_shape[1], D = g.out_shape[0];
-    for (long long base = warp0 * 32; base < nwords; base += warps_total * 32) {
-        long long i = base + lane;
-        unsigned bits = i < nwords ? bitmap[i] : 0u;
-        unsigned nonempty = __ballot_sync(0xffffffffu, bits != 0u);
-        int my_row0 = bits ? block_prefix[i / kScanThreads] + word_prefix[i] : 0;
-        while (nonempty) {
-            int src = __ffs(nonempty) - 1;
-            nonempty &= nonempty - 1;
-            unsigned wbits = __shfl_sync(0xffffffffu, bits, src);
-            int row0 = __shfl_sync(0xffffffffu, my_row0, src);
+    const int nnz = *nnz_dev;
+    for (long long base = warp0 * 32; base < nnz; base += warps_total * 32) {
+        const long long i = base + lane;
+        const int my_word = i < nnz ? nz_word[i] : 0;
+        const unsigned bits = i < nnz ? bitmap[my_word] : 0u;
+        const int my_row0 = i < nnz ? chunk_prefix[i / kScanThreads] + nz_prefix[i] : 0;
+        if (i < nnz) wrow0[my_word] = my_row0;
+        const int cnt_here = (int)min((long long)32, (long long)nnz - base);
+        for (int src = 0; src < cnt_here; ++src) {
+            const unsigned wbits = __shfl_sync(0xffffffffu, bits, src);
+            const int row0 = __shfl_sync(0xffffffffu, my_row0, src);
+            const int word = __shfl_sync(0xffffffffu, my_word, src);
             if (nbr_fill) {
                 // the rows of one bitmap word are consecutive: pre-fill their neighbour-table entries with -1
                 // (coalesced) for k_conv_scatter_nbr, instead of a capacity-sized memset
                 const int cnt = min(__popc(wbits), max(cap_out - row0, 0));
-                for (int i = lane; i < cnt * g.K; i += 32) nbr_fill[(size_t)row0 * g.K + i] = -1;
+                for (int q = lane; q < cnt * g.K; q += 32) nbr_fill[(size_t)row0 * g.K + q] = -1;
             }
             if (wbits & (1u << lane)) {
                 int row = row0 + __popc(wbits & ((1u << lane) - 1u));
                 if (row < cap_out) {
-                    unsigned long long key = (((unsigned long long)(base + src)) << 5) + lane;
+                    unsigned long long key = (((unsigned long long)(unsigned)word) << 5) + lane;
                     unsigned long long r = key / W;
                     int x = (int)(key - r * W);
                     unsigned long long r2 = r / H;
@@ -182,9 +238,6 @@ __global__ void k_conv_emit(const unsigned *__restrict__ bitmap, long long nword
                     int b = (int)(r2 / D);
                     int z = (int)(r2 - (unsigned long long)b * D);
                     *reinterpret_cast<int4 *>(coors_out + (size_t)row * 4) = make_int4(b, z, y, x);
-                    // the coordinate->row hash of the output set is built by k_hash_build afterwards (one row per
-                    // thread): inserting here put up to 32 dependent atomicCAS round trips on one warp's critical
-                    // path -- ~38 us per launch regardless of the level's size (ncu launch list, round 1)
                 }
             }
         }
@@ -226,8 +279,7 @@ __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restr
 // level's 14 us mark pass, ncu launch list round 1); nbr is pre-filled with -1 by the caller.
 __global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *__restrict__ n_in_dev, int cap_in,
                                    ConvGeom g, const unsigned *__restrict__ bitmap,
-                                   const int *__restrict__ word_prefix, const int *__restrict__ block_prefix,
-                                   int cap_out, int *nbr)
+                                   const int *__restrict__ wrow0, int cap_out, int *nbr)
 {
     const int n = min(*n_in_dev, cap_in);
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
@@ -254,11 +306,41 @@ __global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *
                                                                 g.out_shape[1], g.out_shape[2]);
                     const long long w = (long long)(key >> 5);
                     const unsigned bit = (unsigned)(key & 31);
-                    const int row_out = block_prefix[w / kScanThreads] + word_prefix[w] +
-                                        __popc(bitmap[w] & ((1u << bit) - 1u));
+                    const int row_out = wrow0[w] + __popc(bitmap[w] & ((1u << bit) - 1u));
                     const int k = (okk[0][a] * g.k[1] + okk[1][b]) * g.k[2] + okk[2][e];
                     if (row_out < cap_out) nbr[(size_t)row_out * g.K + k] = row;
                 }
+    }
+}
+
+// SubM neighbour table of a level whose occupancy structure (bitmap + wrow0, from the strided conv that produced it)
+// is still in the workspace: coordinate -> row is a bit test + rank, no hash probing.  Symmetric like k_subm_nbr: one
+// thread per (row, k < K/2) writes both directions.
+__global__ void k_subm_ranked(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows, ConvGeom g,
+                              const unsigned *__restrict__ bitmap, const int *__restrict__ wrow0, int *nbr)
+{
+    const int n = min(*n_dev, cap_rows);
+    const int half = g.K / 2;
+    const long long total = (long long)n * (half + 1);
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
+         gid += (long long)gridDim.x * blockDim.x) {
+        int row = (int)(gid / (half + 1)), k = (int)(gid % (half + 1));
+        if (k == half) { nbr[(size_t)row * g.K + half] = row; continue; }
+        int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
+        int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
+        int z = c.y + (kz - g.k[0] / 2) * g.d[0];
+        int y = c.z + (ky - g.k[1] / 2) * g.d[1];
+        int x = c.w + (kx - g.k[2] / 2) * g.d[2];
+        if (z < 0 || z >= g.in_shape[0] || y < 0 || y >= g.in_shape[1] || x < 0 || x >= g.in_shape[2]) continue;
+        const unsigned long long key = b2s_flat_key(c.x, z, y, x, g.in_shape[0], g.in_shape[1], g.in_shape[2]);
+        const unsigned bits = __ldg(&bitmap[key >> 5]);
+        const unsigned bit = (unsigned)(key & 31);
+        if (!((bits >> bit) & 1u)) continue;
+        const int j = __ldg(&wrow0[key >> 5]) + __popc(bits & ((1u << bit) - 1u));
+        if (j < n) {
+            nbr[(size_t)row * g.K + k] = j;
+            nbr[(size_t)j * g.K + (g.K - 1 - k)] = row;
+        }
     }
 }
 
@@ -281,24 +363,35 @@ __global__ void k_pairs(const int *__restrict__ nbr, const int *__restrict__ n_o
 }
 
 struct ConvWorkspace {
-    unsigned *bitmap;
-    int *word_prefix;
-    int *block_sums;
-    long long nwords;
-    int nblk;
+    unsigned *bitmap, *summary;
+    int *sum_prefix, *sum_blocks, *nnz, *nz_word, *nz_prefix, *chunk_sums, *wrow0;
+    long long nwords, nsw;
+    int nblk_s, nchunks;
 };
 
 size_t carve(ConvWorkspace *w, char *base, int batch, const int *out_shape)
 {
     long long cells = (long long)batch * out_shape[0] * out_shape[1] * out_shape[2];
     long long nwords = (cells + 31) / 32;
-    int nblk = b2s_cdiv(nwords > 0 ? nwords : 1, kScanThreads);
+    long long nsw = (nwords + 31) / 32;
+    int nblk_s = b2s_cdiv(nsw > 0 ? nsw : 1, kScanThreads);
+    int nchunks = b2s_cdiv(nwords > 0 ? nwords : 1, kScanThreads);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += b2s_align(bytes); return base ? base + o : nullptr; };
-    unsigned *bitmap = (unsigned *)take(sizeof(unsigned) * (size_t)nwords);
-    int *wp = (int *)take(sizeof(int) * (size_t)nwords);
-    int *bs = (int *)take(sizeof(int) * (size_t)(nblk + 1));
-    if (w) { w->bitmap = bitmap; w->word_prefix = wp; w->block_sums = bs; w->nwords = nwords; w->nblk = nblk; }
+    // bitmap and summary are contiguous: one memset clears both
+    unsigned *bitmap = (unsigned *)take(sizeof(unsigned) * (size_t)(nwords + nsw));
+    int *sp = (int *)take(sizeof(int) * (size_t)nsw);
+    int *sb = (int *)take(sizeof(int) * (size_t)(nblk_s + 1));
+    int *nnz = (int *)take(sizeof(int) * 4);
+    int *nzw = (int *)take(sizeof(int) * (size_t)nwords);
+    int *nzp = (int *)take(sizeof(int) * (size_t)nwords);
+    int *cs = (int *)take(sizeof(int) * (size_t)(nchunks + 1));
+    int *wr = (int *)take(sizeof(int) * (size_t)nwords);
+    if (w) {
+        w->bitmap = bitmap; w->summary = bitmap ? bitmap + nwords : nullptr; w->sum_prefix = sp; w->sum_blocks = sb;
+        w->nnz = nnz; w->nz_word = nzw; w->nz_prefix = nzp; w->chunk_sums = cs; w->wrow0 = wr;
+        w->nwords = nwords; w->nsw = nsw; w->nblk_s = nblk_s; w->nchunks = nchunks;
+    }
     return off;
 }
 
@@ -384,39 +477,77 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
                     g.out_shape[j], expect);
         B2S_REQUIRE((g.k[j] + g.s[j] - 1) / g.s[j] <= 4, "b2s_rulebook_conv: kernel/stride ratio > 4 in dim %d", j);
     }
-    B2S_REQUIRE((hash_cap_out & (hash_cap_out - 1)) == 0 && hash_cap_out >= 2 * cap_out && hash_cap_out >= 2,
+    const bool want_hash = hash_keys_out != nullptr;      // NULL: the level's SubM table comes from b2s_rulebook_subm_ranked
+    B2S_REQUIRE(!want_hash || ((hash_cap_out & (hash_cap_out - 1)) == 0 && hash_cap_out >= 2 * cap_out && hash_cap_out >= 2),
                 "b2s_rulebook_conv: hash_cap_out must be a power of two >= 2*cap_out");
     ConvWorkspace w;
     size_t need = carve(&w, (char *)workspace, batch, out_shape);
     B2S_REQUIRE(workspace_bytes >= need, "b2s_rulebook_conv: workspace too small (%zu < %zu)", workspace_bytes, need);
-    B2S_CUDA_OK(cudaMemsetAsync(w.bitmap, 0, sizeof(unsigned) * (size_t)w.nwords, stream));
-    B2S_CUDA_OK(cudaMemsetAsync(hash_keys_out, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap_out, stream));
-    B2S_CUDA_OK(cudaMemsetAsync(hash_vals_out, 0xFF, sizeof(int) * (size_t)hash_cap_out, stream));
+    B2S_CUDA_OK(cudaMemsetAsync(w.bitmap, 0, sizeof(unsigned) * (size_t)(w.nwords + w.nsw), stream));
+    if (want_hash) {
+        B2S_CUDA_OK(cudaMemsetAsync(hash_keys_out, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap_out, stream));
+        B2S_CUDA_OK(cudaMemsetAsync(hash_vals_out, 0xFF, sizeof(int) * (size_t)hash_cap_out, stream));
+    }
     if (cap_in > 0) {
-        k_conv_mark<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(coors_in, num_in_dev, cap_in, g, w.bitmap);
+        k_conv_mark<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(coors_in, num_in_dev, cap_in, g, w.bitmap,
+                                                                             w.summary);
         B2S_LAUNCH_OK();
     }
-    k_popc_scan<<<w.nblk, kScanThreads, 0, stream>>>(w.bitmap, w.nwords, w.word_prefix, w.block_sums);
+    // level 1: rank the non-empty words; level 2: rank the cells inside them
+    k_summary_scan<<<w.nblk_s, kScanThreads, 0, stream>>>(w.summary, w.nsw, w.sum_prefix, w.sum_blocks);
     B2S_LAUNCH_OK();
-    k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.block_sums, w.nblk, num_out_dev, cap_out, status_dev);
+    k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.sum_blocks, w.nblk_s, nullptr, w.nnz, 0, nullptr);
+    B2S_LAUNCH_OK();
+    k_compact_words<<<bounded_grid(w.nsw, kThreads), kThreads, 0, stream>>>(w.summary, w.nsw, w.sum_prefix, w.sum_blocks,
+                                                                            w.bitmap, w.nz_word, w.nz_prefix);
+    B2S_LAUNCH_OK();
+    k_nz_scan<<<bounded_grid(w.nwords, kScanThreads), kScanThreads, 0, stream>>>(w.nz_prefix, w.nnz, w.chunk_sums);
+    B2S_LAUNCH_OK();
+    k_scan_sums<<<1, kScanThreads, 0, stream>>>(w.chunk_sums, 0, w.nnz, num_out_dev, cap_out, status_dev);
     B2S_LAUNCH_OK();
     static int use_scatter = -1;   // B2S_RB_SCATTER=0: neighbour table by hash probes from the output side (k_conv_nbr)
     if (use_scatter < 0) { const char *e = getenv("B2S_RB_SCATTER"); use_scatter = (e && e[0] == '0') ? 0 : 1; }
-    k_conv_emit<<<bounded_grid(w.nwords, kThreads), kThreads, 0, stream>>>(
-        w.bitmap, w.nwords, w.word_prefix, w.block_sums, g, cap_out, coors_out, use_scatter ? nbr : nullptr);
+    if (!hash_keys_in) use_scatter = 1;
+    k_conv_emit<<<bounded_grid(w.nwords < (1ll << 22) ? w.nwords : (1ll << 22), kThreads), kThreads, 0, stream>>>(
+        w.bitmap, w.nz_word, w.nz_prefix, w.chunk_sums, w.nnz, g, cap_out, coors_out, use_scatter ? nbr : nullptr, w.wrow0);
     B2S_LAUNCH_OK();
     if (cap_out > 0) {
-        k_hash_build<<<bounded_grid(cap_out, kThreads), kThreads, 0, stream>>>(
-            coors_out, num_out_dev, cap_out, g.out_shape[0], g.out_shape[1], g.out_shape[2], hash_keys_out,
-            hash_vals_out, hash_cap_out - 1, status_dev);
-        B2S_LAUNCH_OK();
+        if (want_hash) {
+            k_hash_build<<<bounded_grid(cap_out, kThreads), kThreads, 0, stream>>>(
+                coors_out, num_out_dev, cap_out, g.out_shape[0], g.out_shape[1], g.out_shape[2], hash_keys_out,
+                hash_vals_out, hash_cap_out - 1, status_dev);
+            B2S_LAUNCH_OK();
+        }
         if (use_scatter && cap_in > 0) {
             k_conv_scatter_nbr<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(
-                coors_in, num_in_dev, cap_in, g, w.bitmap, w.word_prefix, w.block_sums, cap_out, nbr);
+                coors_in, num_in_dev, cap_in, g, w.bitmap, w.wrow0, cap_out, nbr);
         } else {
             k_conv_nbr<<<bounded_grid((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
                 coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
         }
+        B2S_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// SubM rulebook of the level b2s_rulebook_conv has JUST produced with this workspace (same batch and shape): the
+// occupancy bitmap + per-word first rows are still there, so no hash table is needed for the level.
+extern "C" int b2s_rulebook_subm_ranked(const int *coors, const int *num_rows_dev, int cap_rows, int batch,
+                                        const int *shape, const int *ksize, const int *dilation, const void *workspace,
+                                        size_t workspace_bytes, int *nbr, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ConvGeom g;
+    B2S_REQUIRE(fill_geom(&g, shape, nullptr, ksize, nullptr, nullptr, dilation) == 0,
+                "b2s_rulebook_subm_ranked: bad geometry");
+    B2S_REQUIRE((g.k[0] & 1) && (g.k[1] & 1) && (g.k[2] & 1), "b2s_rulebook_subm_ranked: kernel sizes must be odd");
+    ConvWorkspace w;
+    size_t need = carve(&w, (char *)workspace, batch, shape);
+    B2S_REQUIRE(workspace_bytes >= need, "b2s_rulebook_subm_ranked: workspace too small (%zu < %zu)", workspace_bytes, need);
+    if (cap_rows > 0) {
+        B2S_CUDA_OK(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)cap_rows * g.K, stream));
+        k_subm_ranked<<<bounded_grid((long long)cap_rows * (g.K / 2 + 1), kThreads), kThreads, 0, stream>>>(
+            coors, num_rows_dev, cap_rows, g, w.bitmap, w.wrow0, nbr);
         B2S_LAUNCH_OK();
     }
     return 0;

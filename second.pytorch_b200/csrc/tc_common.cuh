@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t addr = smem_u32(bar);
+    // not unrolled: the compiler otherwise replicates the try_wait ~60x at every call site, and these warp-specialised
+    // kernels (several roles = several instruction streams per SM) are sensitive to instruction-cache footprint
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 28); ++it) {
         uint32_t done;
         asm volatile(

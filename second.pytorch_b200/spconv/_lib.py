@@ -38,6 +38,8 @@ SIGNATURES = {
     "b2s_rulebook_conv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                   c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "b2s_rulebook_subm_ranked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                         c_void_p, c_void_p]),
     "b2s_rulebook_pairs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2s_sparse_conv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_int, c_void_p]),

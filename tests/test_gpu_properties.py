@@ -118,9 +118,11 @@ def test_sparse_conv_tc_linearity_full_size(product, cin, cout):
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def conv(f):
-        f_hi, f_lo = tc.split_f16(f)
+        buf = torch.empty(n, 2, cin, dtype=torch.float16, device="cuda")        # interleaved rows [hi | lo]
+        buf[:, 0], buf[:, 1] = tc.split_f16(f)
+        f_hi, f_lo = buf[:, 0], buf[:, 1]
         o = torch.zeros(n, cout, device="cuda")            # fp32 output variant (out_lo NULL)
-        L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), cin, n, cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr), 27,
+        L.check(lib.b2s_sparse_conv_tc(L.ptr(f_hi), L.ptr(f_lo), 2 * cin, n, cin, L.ptr(w_hi), L.ptr(w_lo), L.ptr(nbr), 27,
                                        L.ptr(rb.num_out_dev), n, L.ptr(inv), None, 0, L.ptr(o), None, 0, cout,
                                        L.ptr(status), L.stream()), "b2s_sparse_conv_tc")
         torch.cuda.synchronize()
