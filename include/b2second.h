@@ -204,7 +204,9 @@ int b2s_to_bev(const float *feat, const int *coors, const int *num_rows_dev, int
  * (feat_hi/lo NULL) or already split as feat_hi/feat_lo rows of feat_stride halves (feat NULL). */
 int b2s_to_bev_tc(const float *feat, const b2s_half *feat_hi, const b2s_half *feat_lo, int feat_stride,
                   const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch, int D, int H, int W,
-                  b2s_half *out_hi, b2s_half *out_lo, void *stream);
+                  b2s_half *out_hi, b2s_half *out_lo,
+                  uint8_t *occupancy /*optional [B,H,W]: 1 where a pixel received data (input of b2s_rpn_bg_plan)*/,
+                  void *stream);
 
 /* ---- dense RPN convolution on the tensor pipe (second/pytorch/models/rpn.py:467-497 blocks, :264-299 deblocks,
  *      :386-391 heads): 3x3 stride-1 pad-1 (taps=9) or 1x1 (taps=1) conv + per-channel scale/shift (+ReLU).
@@ -233,7 +235,32 @@ int b2s_conv2d_tc_ex(const b2s_half *in_hi, const b2s_half *in_lo, int batch, in
                      const b2s_half *w_hi, const b2s_half *w_lo, int kh, int kw, int stride, int pad, int Cout,
                      int n_pad, const float *scale, const float *shift, int relu, int Hg, int Wg, void *out_hi,
                      b2s_half *out_lo, int Hout, int Wout, int out_padded, int out_stride, int out_mul, int off_h,
-                     int off_w, unsigned *status_dev, void *stream);
+                     int off_w,
+                     const int *work_list /*optional (device): ids of the 16x16 output tiles to compute, from
+                                            b2s_rpn_bg_plan; only for the 3x3 stride-1 128-channel form; NULL: all*/,
+                     const int *work_count_dev,
+                     const int *bg_list /*optional, with work_list: the background tiles of the output; the kernel's
+                                          epilogue warps store the constant bg_hi/bg_lo [Cout] there while they wait
+                                          for the tensor pipe (instead of a separate b2s_rpn_bg_fill launch)*/,
+                     const int *bg_count_dev, const b2s_half *bg_hi, const b2s_half *bg_lo, unsigned *status_dev,
+                     void *stream);
+
+/* ---- background tiles of the dense RPN ---------------------------------------------------------------
+ * Where the whole 3x3 receptive field of a conv layer is background -- exactly 0 in front of layer 1, the constant
+ * vector c_{l-1} in front of layer l -- the layer's output is the data-independent constant
+ * c_l = relu(scale_l * (sum_taps W_l) c_{l-1} + shift_l) (host: b2second/tc.py background_constants).
+ * b2s_rpn_bg_plan dilates the non-background mask through `num_layers` consecutive 3x3 stride-1 pad-1 layers (the zero
+ * halo counts as data from layer 2 on) and compacts, per layer l, the 16x16 output tiles into
+ *   work_lists[l*num_tiles ..]  tiles holding data (ascending), counts[2l]     of them  -> b2s_conv2d_tc_ex work_list
+ *   bg_lists  [l*num_tiles ..]  background tiles,               counts[2l + 1] of them  -> b2s_rpn_bg_fill
+ * with num_tiles = batch * ceil(H/16) * ceil(W/16), tile id = (b * tiles_h + th) * tiles_w + tw.
+ * scratch: 2*batch*H*W bytes; tile_flags: num_layers*num_tiles ints. */
+int b2s_rpn_bg_plan(const uint8_t *occupancy /*[B,H,W]*/, int batch, int H, int W, int num_layers, uint8_t *scratch,
+                    int *tile_flags, int *work_lists, int *bg_lists, int *counts, void *stream);
+/* store the constant c (fp16 hi/lo planes, [C]) into every pixel of the listed background tiles of a halo-padded
+ * NHWC map [B, H+2, W+2, out_stride] */
+int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int batch, int H, int W, int C, const b2s_half *c_hi,
+                    const b2s_half *c_lo, b2s_half *out_hi, b2s_half *out_lo, int out_stride, void *stream);
 
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,

@@ -275,6 +275,20 @@ class InferenceEngine:
         self.tc_heads = torch.zeros(B, hd["H"], hd["W"], self.tc_head_stride, dtype=torch.float32, device=dev)
         self.tc_bufs["heads"] = (self.tc_heads, None)
         self.tc_hw = (H, W)
+        # background tiles (csrc/rpn_bg.cu): through the leading chain of 3x3 stride-1 layers, output tiles whose whole
+        # receptive field is empty BEV are not computed but filled with the layer's data-independent constant
+        self.bg_idx = _tc.background_layers(plan) if os.environ.get("B2S_RPN_BG", "1") != "0" else []
+        self.bg_fused_fill = os.environ.get("B2S_RPN_BG_FILL", "fused") == "fused"
+        if self.bg_idx:
+            nl = len(self.bg_idx)
+            self.bg_const = _tc.background_constants(plan, self.bg_idx)
+            self.bg_tiles = B * (-(-H // 16)) * (-(-W // 16))
+            self.bg_occ = torch.zeros(B, H, W, dtype=torch.uint8, device=dev)
+            self.bg_scratch = torch.zeros(2, B, H, W, dtype=torch.uint8, device=dev)
+            self.bg_flags = torch.zeros(nl, self.bg_tiles, dtype=torch.int32, device=dev)
+            self.bg_work = torch.zeros(nl, self.bg_tiles, dtype=torch.int32, device=dev)
+            self.bg_list = torch.zeros(nl, self.bg_tiles, dtype=torch.int32, device=dev)
+            self.bg_counts = torch.zeros(nl, 2, dtype=torch.int32, device=dev)
 
     def _feature_hw(self):
         if self.rpn_impl == "tc":
@@ -481,14 +495,19 @@ class InferenceEngine:
         if hilo is not None:
             L.check(lib.b2s_to_bev_tc(None, L.ptr(hilo[0]), L.ptr(hilo[1]), hilo[2], L.ptr(fl.coors), L.ptr(fl.n_dev),
                                       fl.cap, self.feat_final_c, self.B, D, H, W, L.ptr(self.tc_bev[0]),
-                                      L.ptr(self.tc_bev[1]), st), "b2s_to_bev_tc")
+                                      L.ptr(self.tc_bev[1]), L.ptr(self.bg_occ) if self.bg_idx else None, st),
+                    "b2s_to_bev_tc")
         else:
             L.check(lib.b2s_to_bev_tc(L.ptr(feats), None, None, 0, L.ptr(fl.coors), L.ptr(fl.n_dev), fl.cap,
                                       self.feat_final_c, self.B, D, H, W, L.ptr(self.tc_bev[0]), L.ptr(self.tc_bev[1]),
-                                      st), "b2s_to_bev_tc")
+                                      L.ptr(self.bg_occ) if self.bg_idx else None, st), "b2s_to_bev_tc")
         self._mark("rpn")
+        if self.bg_idx:
+            L.check(lib.b2s_rpn_bg_plan(L.ptr(self.bg_occ), self.B, H, W, len(self.bg_idx), L.ptr(self.bg_scratch),
+                                        L.ptr(self.bg_flags), L.ptr(self.bg_work), L.ptr(self.bg_list),
+                                        L.ptr(self.bg_counts), st), "b2s_rpn_bg_plan")
         marked_tail = False
-        for op in self.tc_plan:
+        for oi, op in enumerate(self.tc_plan):
             if not op["v2"] and op["kind"] != "block" and not marked_tail:
                 self._mark("rpn_1x1")          # the 3x3 stack (k_conv3x3_tc2) is timed apart from the deblock/heads tail
                 marked_tail = True
@@ -497,13 +516,24 @@ class InferenceEngine:
             esz = dst[0].element_size()
             o_hi = ctypes_ptr(dst[0].data_ptr() + esz * op["dst_coff"])
             o_lo = ctypes_ptr(dst[1].data_ptr() + esz * op["dst_coff"]) if op["planes"] == 2 else None
+            work = work_n = bgl = bgn = bhi = blo = None
+            if oi in self.bg_idx:
+                bl = self.bg_idx.index(oi)
+                chi, clo, _ = self.bg_const[bl]
+                work, work_n = L.ptr(self.bg_work[bl]), L.ptr(self.bg_counts[bl, 0:])
+                if self.bg_fused_fill:       # the conv kernel's epilogue warps store the constant into the background tiles
+                    bgl, bgn, bhi, blo = L.ptr(self.bg_list[bl]), L.ptr(self.bg_counts[bl, 1:]), L.ptr(chi), L.ptr(clo)
+                else:
+                    L.check(lib.b2s_rpn_bg_fill(L.ptr(self.bg_list[bl]), L.ptr(self.bg_counts[bl, 1:]), self.B,
+                                                op["Hout"], op["Wout"], op["cout"], L.ptr(chi), L.ptr(clo), o_hi, o_lo,
+                                                cdst, st), "b2s_rpn_bg_fill")
             L.check(lib.b2s_conv2d_tc_ex(
                 L.ptr(src[0]), L.ptr(src[1]), self.B, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]),
                 L.ptr(op["w_lo"]), op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
                 L.ptr(op["scale"]), L.ptr(op["shift"]) if op["shift"] is not None else None,
                 1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi, o_lo, op["Hout"], op["Wout"],
-                1 if op["padded"] else 0, cdst, op["out_mul"], op["off_h"], op["off_w"], L.ptr(self.status), st),
-                "b2s_conv2d_tc_ex(%s)" % op["kind"])
+                1 if op["padded"] else 0, cdst, op["out_mul"], op["off_h"], op["off_w"], work, work_n, bgl, bgn, bhi, blo,
+                L.ptr(self.status), st), "b2s_conv2d_tc_ex(%s)" % op["kind"])
         if not marked_tail:
             self._mark("rpn_1x1")
         S = self.tc_head_stride
@@ -606,6 +636,9 @@ class InferenceEngine:
                 n += 1                           # b2s_split_f16
         if self.rpn_impl == "tc":
             n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
+            if self.bg_idx:
+                # k_bg_layer per layer, k_bg_compact (+ k_bg_fill per layer unless the conv epilogue fills)
+                n += len(self.bg_idx) + 1 + (0 if self.bg_fused_fill else len(self.bg_idx))
         elif getattr(self, "any_sparse_tc", False):
             n += 1                               # b2s_merge_f16
         if self.mc:
@@ -638,7 +671,11 @@ class InferenceEngine:
             px = self.B * op["Hg"] * op["Wg"]
             px_in = self.B * op["Hin"] * op["Win"]
             out_b = 2 * 2 * px * cout if op["planes"] == 2 else 4 * px * cout
+            frac = 1.0                        # share of the 16x16 output tiles actually computed (the rest: background)
+            if getattr(self, "bg_idx", None) and i in self.bg_idx:
+                frac = float(self.bg_counts[self.bg_idx.index(i), 0].item()) / self.bg_tiles
             out.append({"index": i, "kind": op["kind"], "v2": op["v2"], "cin": cin, "cout": cout, "taps": taps,
+                        "tiles_computed_frac": frac,
                         "pixels": px, "flops": 2 * px * taps * cin * cout,
                         "bytes": 2 * 2 * px_in * cin + out_b + 2 * 2 * taps * cin * op["n_pad"],
                         "bytes_fp32_algorithmic": 4 * (px_in * cin + px * cout + taps * cin * cout)})
@@ -677,11 +714,27 @@ class InferenceEngine:
         sizes = [int(f.shape[0]) for f in frames]
         total = sum(sizes)
         assert total <= self.P_cap, "more points (%d) than the engine's capacity (%d)" % (total, self.P_cap)
-        off = 0
-        for f, n in zip(frames, sizes):
-            if n:
-                self.points[off:off + n].copy_(f, non_blocking=True)
-            off += n
+        # frames that lie back to back in memory (views of one pinned slab, or of one device tensor) go over in ONE copy:
+        # a serving loop that reads clouds into a pinned ring buffer pays one cudaMemcpyAsync per batch instead of B
+        off, i = 0, 0
+        while i < len(frames):
+            f = frames[i]
+            run_rows, j = sizes[i], i + 1
+            if f.is_contiguous() and f.dtype == torch.float32:
+                end = f.data_ptr() + 4 * f.numel()
+                while j < len(frames) and frames[j].dtype == torch.float32 and frames[j].device == f.device and \
+                        frames[j].is_contiguous() and frames[j].data_ptr() == end:
+                    end += 4 * frames[j].numel()
+                    run_rows += sizes[j]
+                    j += 1
+            if run_rows:
+                if j - i > 1:
+                    src = torch.as_strided(f, (run_rows, self.F), (self.F, 1))      # the whole run through frame i's storage
+                    self.points[off:off + run_rows].copy_(src, non_blocking=True)
+                else:
+                    self.points[off:off + run_rows].copy_(f, non_blocking=True)
+            off += run_rows
+            i = j
         offs = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32)
         self.offsets.copy_(offs.pin_memory(), non_blocking=True)
         return total

@@ -45,7 +45,7 @@ __global__ void k_to_bev(const float *__restrict__ feat, const int *__restrict__
 __global__ void k_to_bev_tc(const float *__restrict__ feat, const __half *__restrict__ feat_hi,
                             const __half *__restrict__ feat_lo, int feat_stride, const int *__restrict__ coors,
                             const int *__restrict__ n_dev, int cap_rows, int C, int batch, int D, int H, int W,
-                            __half *__restrict__ out_hi, __half *__restrict__ out_lo)
+                            __half *__restrict__ out_hi, __half *__restrict__ out_lo, uint8_t *__restrict__ occ)
 {
     const int n = min(*n_dev, cap_rows);
     const long long total = (long long)n * C;
@@ -58,6 +58,7 @@ __global__ void k_to_bev_tc(const float *__restrict__ feat, const __half *__rest
             continue;
         size_t CD = (size_t)C * D;
         size_t idx = (((size_t)q.x * (H + 2) + (q.z + 1)) * (W + 2) + (q.w + 1)) * CD + (size_t)c * D + q.y;
+        if (occ && c == 0) occ[((size_t)q.x * H + q.z) * W + q.w] = 1;      // the pixel holds data (b2s_rpn_bg_plan)
         if (feat) {
             const uint32_t pk = b2s_tc::split_f16(__ldg(&feat[gid]));
             out_hi[idx] = __ushort_as_half((unsigned short)(pk & 0xFFFFu));
@@ -159,7 +160,7 @@ extern "C" int b2s_to_bev(const float *feat, const int *coors, const int *num_ro
 
 extern "C" int b2s_to_bev_tc(const float *feat, const b2s_half *feat_hi, const b2s_half *feat_lo, int feat_stride,
                              const int *coors, const int *num_rows_dev, int cap_rows, int C, int batch, int D, int H,
-                             int W, b2s_half *out_hi, b2s_half *out_lo, void *stream_)
+                             int W, b2s_half *out_hi, b2s_half *out_lo, uint8_t *occupancy, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE(C >= 1 && batch >= 1 && D >= 1 && H >= 1 && W >= 1, "b2s_to_bev_tc: bad sizes");
@@ -168,11 +169,12 @@ extern "C" int b2s_to_bev_tc(const float *feat, const b2s_half *feat_hi, const b
     size_t total = (size_t)batch * (H + 2) * (W + 2) * C * D;
     B2S_CUDA_OK(cudaMemsetAsync(out_hi, 0, sizeof(__half) * total, stream));
     B2S_CUDA_OK(cudaMemsetAsync(out_lo, 0, sizeof(__half) * total, stream));
+    if (occupancy) B2S_CUDA_OK(cudaMemsetAsync(occupancy, 0, (size_t)batch * H * W, stream));
     if (cap_rows > 0) {
         k_to_bev_tc<<<bounded_grid((long long)cap_rows * C), kThreads, 0, stream>>>(
             feat, reinterpret_cast<const __half *>(feat_hi), reinterpret_cast<const __half *>(feat_lo), feat_stride, coors,
             num_rows_dev, cap_rows, C, batch, D, H, W, reinterpret_cast<__half *>(out_hi),
-            reinterpret_cast<__half *>(out_lo));
+            reinterpret_cast<__half *>(out_lo), occupancy);
         B2S_LAUNCH_OK();
     }
     return 0;

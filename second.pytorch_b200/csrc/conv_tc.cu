@@ -322,7 +322,9 @@ int launch(const CUtensorMap &a_hi, const CUtensorMap &a_lo, const CUtensorMap &
 // conv_tc2.cu
 int b2s_conv3x3_tc2(const __half *in_hi, const __half *in_lo, int B, int H, int W, int Cin, const __half *w_hi,
                     const __half *w_lo, int Cout, const float *scale, const float *shift, int relu, __half *out_hi,
-                    __half *out_lo, int out_stride, int *status, int num_sms, cudaStream_t stream);
+                    __half *out_lo, int out_stride, const int *work_list, const int *work_count, const int *bg_list,
+                    const int *bg_count, const __half *bg_hi, const __half *bg_lo, int *status, int num_sms,
+                    cudaStream_t stream);
 
 // General form (include/b2second.h).  Input: halo-padded fp16 hi/lo planes [B, Hin+2, Win+2, Cin].  One GEMM pixel
 // (h, w) of the Hg x Wg grid reads input pixels (h*stride + dy - pad, w*stride + dx - pad), dy < kh, dx < kw, and is
@@ -334,7 +336,9 @@ extern "C" int b2s_conv2d_tc_ex(const b2s_half *in_hi_, const b2s_half *in_lo_, 
                                 const b2s_half *w_hi_, const b2s_half *w_lo_, int kh, int kw, int stride, int pad,
                                 int Cout, int n_pad, const float *scale, const float *shift, int relu, int Hg, int Wg,
                                 void *out_hi, b2s_half *out_lo_, int Hout, int Wout, int out_padded, int out_stride,
-                                int out_mul, int off_h, int off_w, unsigned *status_dev, void *stream_)
+                                int out_mul, int off_h, int off_w, const int *work_list, const int *work_count_dev,
+                                const int *bg_list, const int *bg_count_dev, const b2s_half *bg_hi,
+                                const b2s_half *bg_lo, unsigned *status_dev, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     const __half *in_hi = reinterpret_cast<const __half *>(in_hi_), *in_lo = reinterpret_cast<const __half *>(in_lo_);
@@ -360,10 +364,18 @@ extern "C" int b2s_conv2d_tc_ex(const b2s_half *in_hi_, const b2s_half *in_lo_, 
         const char *e = getenv("B2S_CONV_V2");
         use_v2 = (e && e[0] == '0') ? 0 : 1;
     }
-    if (use_v2 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && n_pad == 128 && out_lo != nullptr && out_padded &&
-        out_mul == 1 && off_h == 0 && off_w == 0 && Hg == Hin && Wg == Win && Hout == Hin && Wout == Win)
+    const bool v2 = use_v2 && kh == 3 && kw == 3 && stride == 1 && pad == 1 && n_pad == 128 && out_lo != nullptr &&
+                    out_padded && out_mul == 1 && off_h == 0 && off_w == 0 && Hg == Hin && Wg == Win && Hout == Hin &&
+                    Wout == Win;
+    B2S_REQUIRE(work_list == nullptr || (v2 && work_count_dev != nullptr),
+                "b2s_conv2d_tc: a tile work list is only taken by the 3x3 stride-1 128-channel kernel (16x16 tiles)");
+    B2S_REQUIRE(bg_list == nullptr || (work_list != nullptr && bg_count_dev != nullptr && bg_hi != nullptr && bg_lo != nullptr),
+                "b2s_conv2d_tc: a background-tile list needs the work list, its count and the constant's hi/lo planes");
+    if (v2)
         return b2s_conv3x3_tc2(in_hi, in_lo, B, Hin, Win, Cin, w_hi, w_lo, Cout, scale, shift, relu,
-                               reinterpret_cast<__half *>(out_hi), out_lo, out_stride, (int *)status_dev, num_sms, stream);
+                               reinterpret_cast<__half *>(out_hi), out_lo, out_stride, work_list, work_count_dev, bg_list,
+                               bg_count_dev, reinterpret_cast<const __half *>(bg_hi), reinterpret_cast<const __half *>(bg_lo),
+                               (int *)status_dev, num_sms, stream);
     CUtensorMap a_hi, a_lo, b_hi, b_lo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(Win + 2), (cuuint64_t)(Hin + 2), (cuuint64_t)B};
@@ -421,5 +433,6 @@ extern "C" int b2s_conv2d_tc(const b2s_half *in_hi, const b2s_half *in_lo, int B
     B2S_REQUIRE(taps == 1 || taps == 9, "b2s_conv2d_tc: taps must be 1 or 9");
     const int k = taps == 9 ? 3 : 1;
     return b2s_conv2d_tc_ex(in_hi, in_lo, B, H, W, Cin, w_hi, w_lo, k, k, 1, taps == 9 ? 1 : 0, Cout, n_pad, scale, shift,
-                            relu, H, W, out_hi, out_lo, H, W, out_padded, out_stride, 1, 0, 0, status_dev, stream_);
+                            relu, H, W, out_hi, out_lo, H, W, out_padded, out_stride, 1, 0, 0, nullptr, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, status_dev, stream_);
 }

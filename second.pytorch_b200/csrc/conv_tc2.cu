@@ -53,6 +53,11 @@ constexpr uint32_t DY_BYTES = T2_W * BLOCK_K * ELEM_BYTES;                 // on
 struct Conv2Params {
     int B, H, W, Cin, Cout, relu;
     int tiles_h, tiles_w, num_tiles;
+    const int *work_list, *work_count;   // optional (device): the tiles to compute, work_list[0 .. *work_count); tiles that
+                                         // are not listed are "background" (b2s_rpn_bg_plan) and get their constant from
+                                         // b2s_rpn_bg_fill.  NULL: every tile
+    const int *bg_list, *bg_count;       // optional (device): background tiles of this layer's output; the epilogue warps
+    const __half *bg_hi, *bg_lo;         // store the constant bg_hi/bg_lo [Cout] there in the shadow of the MMA main loop
     int last_half;                   // 1: the last tile row covers <= 8 image rows -> its MMAs run at N = 128 (upper half
                                      // of the pixel tile only); H = 200 = 12.5 tiles of 16 rows saves 3.8 % of the MMA work
     int out_stride;
@@ -63,6 +68,10 @@ struct Conv2Params {
     __half *out_hi, *out_lo;         // [B, H+2, W+2, out_stride] halo-padded fp16 planes (interior written)
     int *status;                     // bit B2S_STATUS_F16_RANGE raised when an activation exceeds the fp16 range
 };
+
+// number of work items and the i-th tile of this launch (dense: identity)
+__device__ __forceinline__ int work_total(const Conv2Params &p) { return p.work_list ? min(*p.work_count, p.num_tiles) : p.num_tiles; }
+__device__ __forceinline__ int work_tile(const Conv2Params &p, int i) { return p.work_list ? __ldg(&p.work_list[i]) : i; }
 
 __global__ void __launch_bounds__(kThreads2, 1)
 k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
@@ -76,9 +85,15 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
     __shared__ __align__(8) uint64_t bar_xfull[X_STAGES], bar_xempty[X_STAGES], bar_wfull[W_STAGES],
         bar_wempty[W_STAGES], bar_tfull[ACC2], bar_tempty[ACC2];
     __shared__ uint32_t s_tmem_base;
+    __shared__ __align__(16) __half s_bg[2][128];             // the layer's background constant (hi, lo)
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BLOCK_K;
+    const int n_work = work_total(p);
+    if (p.bg_list && threadIdx.x < 128) {
+        s_bg[0][threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bg_hi[threadIdx.x] : __float2half(0.f);
+        s_bg[1][threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bg_lo[threadIdx.x] : __float2half(0.f);
+    }
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < X_STAGES; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
@@ -108,7 +123,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                 const long long t0 = clock64(), d = (long long)(blockIdx.x & 3) * p.dephase;
                 while (clock64() - t0 < d) { }
             }
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+                const int tile = work_tile(p, wi);
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
                 const int h0 = th * T2_H, w0 = tw * T2_W;
                 for (int dx = 0; dx < 3; ++dx)
@@ -133,7 +149,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         if (lane == 0) {
             int ws = 0;
             uint32_t wph = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x)
+            for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x)
                 for (int dx = 0; dx < 3; ++dx)
                     for (int chunk = 0; chunk < kchunks; ++chunk)
                         for (int dy = 0; dy < 3; ++dy)
@@ -161,7 +177,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         // still has MMAs to issue, so the tensor queue never runs dry between bursts.  (tests/cuda/mma_probe2.cu
         // shows the pipe sustains 128 cycles per N=256 MMA on exactly this operand pattern; with a
         // wait -> fence -> elect -> issue sequence between bursts the kernel measured 188.)
-        const int my_tiles = (blockIdx.x < (unsigned)p.num_tiles) ? (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int my_tiles = ((int)blockIdx.x < n_work) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         const int total_g = my_tiles * 3 * kchunks;
         if (elect_one_sync() && total_g > 0) {
             int xs = 0, ws = 0, acc = 0;
@@ -172,7 +188,7 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
             tc_fence_after();
             const int gpt = 3 * kchunks;                     // groups per tile
             for (int gi = 0; gi < total_g; ++gi) {
-                const int tile = (int)blockIdx.x + (gi / gpt) * (int)gridDim.x;
+                const int tile = work_tile(p, (int)blockIdx.x + (gi / gpt) * (int)gridDim.x);
                 const bool half_tile = p.last_half && ((tile / p.tiles_w) % p.tiles_h) == p.tiles_h - 1;
                 const uint32_t idesc = half_tile ? idesc_half : idesc_full;
                 const uint32_t tmem_d = tmem_u + (uint32_t)(acc * N_PIX);
@@ -247,7 +263,36 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         const float sh = (p.shift && c_ok) ? p.shift[c] : 0.f;
         int acc = 0;
         uint32_t aph = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        // Background tiles (csrc/rpn_bg.cu) of this layer's output are filled by the epilogue warps, which otherwise
+        // spend most of a tile waiting for the tensor pipe: CTA c owns background tiles c, c + grid, ... and spreads
+        // them over its work items.  One store instruction of the 256 epilogue threads = one tile row of one plane
+        // (16 pixels x 256 B, contiguous).
+        const int n_bg = p.bg_list ? min(*p.bg_count, p.num_tiles) : 0;
+        const int my_bg = ((int)blockIdx.x < n_bg) ? (n_bg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int my_work = ((int)blockIdx.x < n_work) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        const int bg_quota = my_work > 0 ? (my_bg + my_work - 1) / my_work : my_bg;
+        int bg_done = 0;
+        const int e_tid = (warp - 4) * 32 + lane;                 // 0..255
+        auto fill_bg = [&](int count) {
+            const int chunk = e_tid & 15, px = e_tid >> 4;
+            const uint4 vh = *reinterpret_cast<const uint4 *>(&s_bg[0][chunk * 8]);
+            const uint4 vl = *reinterpret_cast<const uint4 *>(&s_bg[1][chunk * 8]);
+            for (int q = 0; q < count && bg_done < my_bg; ++q, ++bg_done) {
+                const int t = __ldg(&p.bg_list[(int)blockIdx.x + bg_done * (int)gridDim.x]);
+                const int btw = t % p.tiles_w, bth = (t / p.tiles_w) % p.tiles_h, bb = t / (p.tiles_w * p.tiles_h);
+                const int w = btw * T2_W + px;
+                if (w >= p.W || chunk * 8 >= p.Cout) continue;
+                for (int r = 0; r < T2_H; ++r) {
+                    const int h = bth * T2_H + r;
+                    if (h >= p.H) break;
+                    const size_t pix = ((size_t)bb * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
+                    *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_stride + chunk * 8) = vh;
+                    *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_stride + chunk * 8) = vl;
+                }
+            }
+        };
+        for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+            const int tile = work_tile(p, wi);
             const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
             float sum[128];
 #pragma unroll
@@ -305,7 +350,9 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
                 }
             }
             if (range_bad && c_ok && p.status) atomicOr(p.status, B2S_STATUS_F16_RANGE);
+            fill_bg(bg_quota);
         }
+        fill_bg(my_bg);                                          // whatever is left (a CTA without work items: all of it)
     }
     tc_fence_before();
     __syncthreads();
@@ -320,7 +367,9 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
 // called by b2s_conv2d_tc (conv_tc.cu) for taps == 9, n_pad == 128, halo-padded hi/lo output
 int b2s_conv3x3_tc2(const __half *in_hi, const __half *in_lo, int B, int H, int W, int Cin, const __half *w_hi,
                     const __half *w_lo, int Cout, const float *scale, const float *shift, int relu, __half *out_hi,
-                    __half *out_lo, int out_stride, int *status, int num_sms, cudaStream_t stream)
+                    __half *out_lo, int out_stride, const int *work_list, const int *work_count, const int *bg_list,
+                    const int *bg_count, const __half *bg_hi, const __half *bg_lo, int *status, int num_sms,
+                    cudaStream_t stream)
 {
     using namespace b2s_tc;
     CUtensorMap x_hi, x_lo, m_w_hi, m_w_lo;
@@ -343,6 +392,8 @@ int b2s_conv3x3_tc2(const __half *in_hi, const __half *in_lo, int B, int H, int 
     p.tiles_w = (W + T2_W - 1) / T2_W;
     p.num_tiles = B * p.tiles_h * p.tiles_w;
     p.last_half = (H % T2_H != 0 && H % T2_H <= T2_H / 2) ? 1 : 0;
+    p.work_list = work_list; p.work_count = work_list ? work_count : nullptr;
+    p.bg_list = bg_list; p.bg_count = bg_count; p.bg_hi = bg_hi; p.bg_lo = bg_lo;
     p.out_stride = out_stride;
     {
         static int dbg = -1, deph = -1;
@@ -358,7 +409,7 @@ int b2s_conv3x3_tc2(const __half *in_hi, const __half *in_lo, int B, int H, int 
     p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = out_lo; p.status = status;
     const size_t smem = (size_t)X_STAGES * X_STAGE_BYTES + (size_t)W_STAGES * W_PLANE_BYTES + 1024;
     B2S_SMEM_OPT_IN(k_conv3x3_tc2, smem);
-    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+    const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;     // (with a work list some CTAs may only fill)
     k_conv3x3_tc2<<<grid, kThreads2, smem, stream>>>(x_hi, x_lo, m_w_hi, m_w_lo, p);
     B2S_LAUNCH_OK();
     return 0;

@@ -111,7 +111,7 @@ def run_rpn_plan(product, plan, x_nchw):
             L.ptr(op["scale"]),
             L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi, o_lo,
             op["Hout"], op["Wout"], 1 if op["padded"] else 0, dst[0].shape[-1], op["out_mul"], op["off_h"], op["off_w"],
-            L.ptr(status), L.stream()), "b2s_conv2d_tc_ex")
+            None, None, None, None, None, None, L.ptr(status), L.stream()), "b2s_conv2d_tc_ex")
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     return heads

@@ -98,10 +98,14 @@ def test_to_bev_tc_scatter(product, D, C):
     r_hi, r_lo = tc.split_f16(ref)
     o_hi = torch.full((B, H + 2, W + 2, C * D), 7.0, dtype=torch.float16, device="cuda")   # stale contents must vanish
     o_lo = torch.full_like(o_hi, 7.0)
+    occ = torch.full((B, H, W), 9, dtype=torch.uint8, device="cuda")
     L.check(lib.b2s_to_bev_tc(L.ptr(feats), None, None, 0, L.ptr(coors), L.ptr(n_dev), n, C, B, D, H, W, L.ptr(o_hi),
-                              L.ptr(o_lo), L.stream()), "b2s_to_bev_tc")
+                              L.ptr(o_lo), L.ptr(occ), L.stream()), "b2s_to_bev_tc")
     torch.cuda.synchronize()
     assert torch.equal(o_hi.cpu(), r_hi) and torch.equal(o_lo.cpu(), r_lo)
+    ref_occ = torch.zeros(B, H, W, dtype=torch.uint8)
+    ref_occ[cc[:n - 7, 0].long(), cc[:n - 7, 2].long(), cc[:n - 7, 3].long()] = 1
+    assert torch.equal(occ.cpu(), ref_occ)                         # occupancy map for b2s_rpn_bg_plan
     # rows that arrive already split (interleaved [row][hi | lo], as the last sparse layer writes them)
     buf = torch.zeros(n, 2, C, dtype=torch.float16, device="cuda")
     f_hi, f_lo = tc.split_f16(feats)
@@ -109,7 +113,7 @@ def test_to_bev_tc_scatter(product, D, C):
     o_hi.fill_(3.0)
     o_lo.fill_(3.0)
     L.check(lib.b2s_to_bev_tc(None, L.ptr(buf[:, 0]), L.ptr(buf[:, 1]), 2 * C, L.ptr(coors), L.ptr(n_dev), n, C, B, D, H, W,
-                              L.ptr(o_hi), L.ptr(o_lo), L.stream()), "b2s_to_bev_tc")
+                              L.ptr(o_hi), L.ptr(o_lo), None, L.stream()), "b2s_to_bev_tc")
     torch.cuda.synchronize()
     assert torch.equal(o_hi.cpu(), r_hi) and torch.equal(o_lo.cpu(), r_lo)
 
@@ -343,3 +347,59 @@ def test_multiclass_nms_branch_on_the_fused_engine(product, name, agnostic):
         m = (ref["label_preds"] == c).cpu().numpy()
         fix = {k: ref[k].cpu().numpy()[m] for k in ("box3d_lidar", "scores", "label_preds")}
         gu.assert_detections_close({k: got[k].cpu().numpy()[m] for k in fix}, fix)
+
+
+# ------------------------------------------------------------------------------------------------ RPN background tiles
+def test_rpn_background_plan_matches_numpy_and_engine_results_do_not_change(product, monkeypatch):
+    """b2s_rpn_bg_plan against its numpy restatement (tests/test_host_rpn_plan.py), and the fused engine with the
+    background-tile skip on vs off: same candidates, same detections, head tensors within fp32 rounding."""
+    import test_host_rpn_plan as hp
+    from b2second.engine import InferenceEngine
+    L = product._lib
+    lib = L.load()
+    rng = np.random.default_rng(0)
+    B, H, W, nl = 3, 200, 176, 6
+    occ = (rng.random((B, H, W)) < 0.002).astype(np.uint8)
+    occ[1] = 0                                         # an empty frame: everything is background in layer 1
+    occ[2, 90:130, 60:120] = 1
+    th, tw = -(-H // 16), -(-W // 16)
+    nt = B * th * tw
+    d_occ = torch.from_numpy(occ).cuda()
+    scratch = torch.zeros(2, B, H, W, dtype=torch.uint8, device="cuda")
+    flags = torch.zeros(nl, nt, dtype=torch.int32, device="cuda")
+    work = torch.full((nl, nt), -1, dtype=torch.int32, device="cuda")
+    bg = torch.full((nl, nt), -1, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(nl, 2, dtype=torch.int32, device="cuda")
+    L.check(lib.b2s_rpn_bg_plan(L.ptr(d_occ), B, H, W, nl, L.ptr(scratch), L.ptr(flags), L.ptr(work), L.ptr(bg),
+                                L.ptr(counts), L.stream()), "b2s_rpn_bg_plan")
+    torch.cuda.synchronize()
+    ref = hp.bg_plan_numpy(occ, nl)
+    for l in range(nl):
+        f = ref[l].reshape(-1)
+        assert np.array_equal(flags[l].cpu().numpy(), f)
+        nw = int(counts[l, 0])
+        assert nw == int(f.sum()) and int(counts[l, 1]) == nt - nw
+        assert np.array_equal(work[l, :nw].cpu().numpy(), np.nonzero(f)[0])
+        assert np.array_equal(bg[l, :nt - nw].cpu().numpy(), np.nonzero(f == 0)[0])
+    assert int(counts[0, 1]) > nt // 3                 # layer 1 really skips a lot here
+    # engine on / off
+    name = "car.fhd"
+    net = models.build_network(config.get_config(name), product).eval()
+    models.synthetic_weights_(net, name, seed=0)
+    net = net.cuda()
+    clouds = [torch.from_numpy(gu.make_cloud(name, s, n)).cuda() for s, n in ((0, 20000), (1, 29000))]
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B2S_RPN_BG", mode)
+        eng = InferenceEngine(net, batch_size=2, max_points=30000, use_cuda_graph=(mode == "1"))
+        assert bool(eng.bg_idx) == (mode == "1")
+        eng.infer(clouds)
+        res[mode] = (eng.detections(), eng.tc_heads.clone(), eng.cand_count.clone(),
+                     eng.bg_counts.clone() if eng.bg_idx else None)
+    assert torch.equal(res["1"][2], res["0"][2])
+    assert int(res["1"][3][:, 1].sum()) > 0            # some tiles were skipped
+    assert float((res["1"][1] - res["0"][1]).abs().max()) <= 2e-5
+    for a, b in zip(res["1"][0], res["0"][0]):
+        assert a["box3d_lidar"].shape == b["box3d_lidar"].shape and a["box3d_lidar"].shape[0] > 0
+        torch.testing.assert_close(a["box3d_lidar"], b["box3d_lidar"], rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(a["scores"], b["scores"], rtol=0, atol=1e-5)

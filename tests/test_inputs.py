@@ -60,9 +60,7 @@ needs_ref = pytest.mark.skipif(not refcompat.reference_available(), reason="refe
 
 
 @needs_ref
-def test_crop_restatement_equals_reference_remove_outside_points():
-    from b2second import loader
-    refcompat.install(loader.ORACLE_DIR)
+def test_crop_restatement_equals_reference_remove_outside_points(ref_env):
     from second.core import box_np_ops
     P2, rect, Trv2c, shape = kitti_calib()
     pts = raw_kitti_cloud(0, 20000)
@@ -74,11 +72,9 @@ def test_crop_restatement_equals_reference_remove_outside_points():
 
 
 @needs_ref
-def test_sweep_merge_restatement_equals_reference_dataset_code(tmp_path):
+def test_sweep_merge_restatement_equals_reference_dataset_code(ref_env, tmp_path):
     """run the reference's own NuScenesDataset.get_sensor_data on sweep files written to disk."""
     import types
-    from b2second import loader
-    refcompat.install(loader.ORACLE_DIR)
     # external shims for modules the dataset file imports at top level but this code path never uses (the reference
     # tree itself is untouched): scikit-image (kitti_common.py:9) and fire (nuscenes_dataset.py:10)
     for name in ("skimage", "skimage.io", "fire"):

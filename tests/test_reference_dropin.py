@@ -18,26 +18,6 @@ from b2second import config, loader, models, refcompat, synth
 pytestmark = pytest.mark.skipif(not refcompat.reference_available(), reason="reference tree not present")
 
 
-@pytest.fixture(scope="module")
-def ref_env():
-    # the reference imports its plugin by the name `spconv`: make that name the CPU oracle for this module's
-    # tests (other test modules in the same process use the CUDA drop-in under that name), then restore
-    saved = {k: v for k, v in sys.modules.items() if k == "spconv" or k.startswith("spconv.")}
-    for k in saved:
-        del sys.modules[k]
-    saved_path = list(sys.path)
-    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != os.path.abspath(loader.PRODUCT_DIR)] + \
-        [loader.PRODUCT_DIR]
-    refcompat.install(loader.ORACLE_DIR)
-    import spconv
-    assert getattr(spconv, "__oracle__", False)
-    yield spconv
-    for k in [k for k in sys.modules if k == "spconv" or k.startswith("spconv.")]:
-        del sys.modules[k]
-    sys.modules.update(saved)
-    sys.path[:] = saved_path
-
-
 @pytest.mark.parametrize("name", sorted(config.BUILTIN))
 def test_builtin_config_equals_reference_file(name):
     path = os.path.join(refcompat.REFERENCE_ROOT, "second", "configs", config.REFERENCE_FILES[name])

@@ -34,7 +34,7 @@ for i, op in enumerate(eng.tc_plan):
             op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"], L.ptr(op["scale"]),
             L.ptr(op["shift"]) if op["shift"] is not None else None, 1 if op["relu"] else 0, op["Hg"], op["Wg"], o_hi,
             o_lo, op["Hout"], op["Wout"], 1 if op["padded"] else 0, dst[0].shape[-1], op["out_mul"], op["off_h"],
-            op["off_w"], L.ptr(eng.status), st), "conv")
+            op["off_w"], None, None, None, None, None, None, L.ptr(eng.status), st), "conv")
     run()
     ts = []
     for r in range(5):
