@@ -61,9 +61,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--sparse", default="tc", choices=["tc", "fma"],
-                    help="sparse-conv inner product: tc = tcgen05 3xTF32 (wide layers), fma = fp32 FMA tiles")
+                    help="sparse-conv inner product: tc = tcgen05 3xF16 split, fma = fp32 FMA tiles")
     ap.add_argument("--rpn", default="auto", choices=["auto", "tc", "cudnn"],
-                    help="RPN implementation: tc = hand-written tcgen05 3xTF32 implicit GEMM, cudnn = torch fp32")
+                    help="RPN implementation: tc = hand-written tcgen05 3xF16 implicit GEMM, cudnn = torch fp32")
     return ap.parse_args()
 
 
