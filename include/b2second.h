@@ -240,27 +240,30 @@ int b2s_conv2d_tc_ex(const b2s_half *in_hi, const b2s_half *in_lo, int batch, in
                                             b2s_rpn_bg_plan; only for the 3x3 stride-1 128-channel form; NULL: all*/,
                      const int *work_count_dev,
                      const int *bg_list /*optional, with work_list: the background tiles of the output; the kernel's
-                                          epilogue warps store the constant bg_hi/bg_lo [Cout] there while they wait
-                                          for the tensor pipe (instead of a separate b2s_rpn_bg_fill launch)*/,
+                                          epilogue warps copy them from the layer's empty-frame response bg_hi/bg_lo
+                                          [Hout+2, Wout+2, Cout] while they wait for the tensor pipe (instead of a
+                                          separate b2s_rpn_bg_fill launch)*/,
                      const int *bg_count_dev, const b2s_half *bg_hi, const b2s_half *bg_lo, unsigned *status_dev,
                      void *stream);
 
 /* ---- background tiles of the dense RPN ---------------------------------------------------------------
- * Where the whole 3x3 receptive field of a conv layer is background -- exactly 0 in front of layer 1, the constant
- * vector c_{l-1} in front of layer l -- the layer's output is the data-independent constant
- * c_l = relu(scale_l * (sum_taps W_l) c_{l-1} + shift_l) (host: b2second/tc.py background_constants).
- * b2s_rpn_bg_plan dilates the non-background mask through `num_layers` consecutive 3x3 stride-1 pad-1 layers (the zero
- * halo counts as data from layer 2 on) and compacts, per layer l, the 16x16 output tiles into
- *   work_lists[l*num_tiles ..]  tiles holding data (ascending), counts[2l]     of them  -> b2s_conv2d_tc_ex work_list
- *   bg_lists  [l*num_tiles ..]  background tiles,               counts[2l + 1] of them  -> b2s_rpn_bg_fill
+ * The output of layer l of a chain of 3x3 stride-1 pad-1 layers at pixel p depends on the BEV only inside the
+ * (2l+1)^2 window around p.  Where that window holds no data the output equals the layer's response to an EMPTY frame
+ * at p, a field that depends on the weights only (constant in the interior, different within l pixels of the border).
+ * The caller computes that field once per layer by running the layer itself on an empty frame, and keeps it as one
+ * halo-padded frame [H+2, W+2, C] of hi/lo planes.
+ * b2s_rpn_bg_plan dilates the data mask through `num_layers` consecutive 3x3 stride-1 pad-1 layers and compacts, per
+ * layer l, the 16x16 output tiles into
+ *   work_lists[l*num_tiles ..]  tiles with a masked pixel (ascending), counts[2l] of them -> b2s_conv2d_tc_ex work_list
+ *   bg_lists  [l*num_tiles ..]  background tiles,               counts[2l + 1] of them  -> bg_list / b2s_rpn_bg_fill
  * with num_tiles = batch * ceil(H/16) * ceil(W/16), tile id = (b * tiles_h + th) * tiles_w + tw.
  * scratch: 2*batch*H*W bytes; tile_flags: num_layers*num_tiles ints. */
 int b2s_rpn_bg_plan(const uint8_t *occupancy /*[B,H,W]*/, int batch, int H, int W, int num_layers, uint8_t *scratch,
                     int *tile_flags, int *work_lists, int *bg_lists, int *counts, void *stream);
-/* store the constant c (fp16 hi/lo planes, [C]) into every pixel of the listed background tiles of a halo-padded
- * NHWC map [B, H+2, W+2, out_stride] */
-int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int batch, int H, int W, int C, const b2s_half *c_hi,
-                    const b2s_half *c_lo, b2s_half *out_hi, b2s_half *out_lo, int out_stride, void *stream);
+/* copy the listed background tiles of a halo-padded NHWC map [B, H+2, W+2, out_stride] from the layer's empty-frame
+ * response f_hi/f_lo [H+2, W+2, C] (fp16 hi/lo planes) */
+int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int batch, int H, int W, int C, const b2s_half *f_hi,
+                    const b2s_half *f_lo, b2s_half *out_hi, b2s_half *out_lo, int out_stride, void *stream);
 
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,

@@ -276,12 +276,11 @@ class InferenceEngine:
         self.tc_bufs["heads"] = (self.tc_heads, None)
         self.tc_hw = (H, W)
         # background tiles (csrc/rpn_bg.cu): through the leading chain of 3x3 stride-1 layers, output tiles whose whole
-        # receptive field is empty BEV are not computed but filled with the layer's data-independent constant
+        # receptive field is empty BEV are not computed but copied from the layer's response to an empty frame
         self.bg_idx = _tc.background_layers(plan) if os.environ.get("B2S_RPN_BG", "1") != "0" else []
         self.bg_fused_fill = os.environ.get("B2S_RPN_BG_FILL", "fused") == "fused"
         if self.bg_idx:
             nl = len(self.bg_idx)
-            self.bg_const = _tc.background_constants(plan, self.bg_idx)
             self.bg_tiles = B * (-(-H // 16)) * (-(-W // 16))
             self.bg_occ = torch.zeros(B, H, W, dtype=torch.uint8, device=dev)
             self.bg_scratch = torch.zeros(2, B, H, W, dtype=torch.uint8, device=dev)
@@ -289,6 +288,32 @@ class InferenceEngine:
             self.bg_work = torch.zeros(nl, self.bg_tiles, dtype=torch.int32, device=dev)
             self.bg_list = torch.zeros(nl, self.bg_tiles, dtype=torch.int32, device=dev)
             self.bg_counts = torch.zeros(nl, 2, dtype=torch.int32, device=dev)
+            self.bg_field = self._empty_frame_response()
+
+    def _empty_frame_response(self):
+        """per background-tracked layer: what the layer's own kernel produces for an empty frame, as one halo-padded
+        frame [H+2, W+2, C] of fp16 hi/lo planes.  Run once at plan time on frame 0 of the (still all-zero) buffers."""
+        L, lib = self._L, self.lib
+        st = L.stream()
+        fields = []
+        for oi in self.bg_idx:
+            op = self.tc_plan[oi]
+            src, dst = self.tc_bufs[op["src"]], self.tc_bufs[op["dst"]]
+            cdst = dst[0].shape[-1]
+            L.check(lib.b2s_conv2d_tc_ex(
+                L.ptr(src[0]), L.ptr(src[1]), 1, op["Hin"], op["Win"], op["cin"], L.ptr(op["w_hi"]),
+                L.ptr(op["w_lo"]), op["kh"], op["kw"], op["stride"], op["pad"], op["cout"], op["n_pad"],
+                L.ptr(op["scale"]), L.ptr(op["shift"]) if op["shift"] is not None else None,
+                1 if op["relu"] else 0, op["Hg"], op["Wg"], L.ptr(dst[0]), L.ptr(dst[1]), op["Hout"], op["Wout"],
+                1, cdst, op["out_mul"], op["off_h"], op["off_w"], None, None, None, None, None, None,
+                L.ptr(self.status), st), "b2s_conv2d_tc_ex(empty frame)")
+            fields.append((dst[0][0, :, :, :op["cout"]].clone().contiguous(),
+                           dst[1][0, :, :, :op["cout"]].clone().contiguous()))
+        torch.cuda.synchronize(self.dev)
+        for oi in self.bg_idx:                    # leave the activation buffers as they were (all zero)
+            for t in self.tc_bufs[self.tc_plan[oi]["dst"]]:
+                t[0].zero_()
+        return fields
 
     def _feature_hw(self):
         if self.rpn_impl == "tc":
@@ -519,7 +544,7 @@ class InferenceEngine:
             work = work_n = bgl = bgn = bhi = blo = None
             if oi in self.bg_idx:
                 bl = self.bg_idx.index(oi)
-                chi, clo, _ = self.bg_const[bl]
+                chi, clo = self.bg_field[bl]
                 work, work_n = L.ptr(self.bg_work[bl]), L.ptr(self.bg_counts[bl, 0:])
                 if self.bg_fused_fill:       # the conv kernel's epilogue warps store the constant into the background tiles
                     bgl, bgn, bhi, blo = L.ptr(self.bg_list[bl]), L.ptr(self.bg_counts[bl, 1:]), L.ptr(chi), L.ptr(clo)

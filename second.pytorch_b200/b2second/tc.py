@@ -226,28 +226,3 @@ def background_layers(plan):
         else:
             break
     return idx
-
-
-def background_constants(plan, layer_idx):
-    """per tracked layer l the data-independent output of a pixel whose whole 3x3 receptive field is background:
-    c_0 = 0 (empty BEV), c_l = relu(scale_l * (sum_taps W_l) c_{l-1} + shift_l) (csrc/rpn_bg.cu).  Computed in float64
-    from exactly the operands the kernel multiplies (fp16 hi + lo planes, power-of-two pre-scale folded into scale),
-    rounded to float32 like the kernel's epilogue input, then split to fp16 hi/lo like its output.
-    -> list of (c_hi [C] fp16, c_lo [C] fp16, c fp32)."""
-    out = []
-    c = None
-    for i in layer_idx:
-        op = plan["ops"][i]
-        w = (op["w_hi"].double() + op["w_lo"].double())[:, :op["cout"]]          # [9, cout, cin], scaled by w_scale
-        wsum = w.sum(0)                                                          # sum over the taps
-        cin = w.shape[2]
-        prev = torch.zeros(cin, dtype=torch.float64, device=w.device) if c is None else c.double()
-        y = wsum @ prev
-        y = y * op["scale"].double() + (op["shift"].double() if op["shift"] is not None else 0.0)
-        if op["relu"]:
-            y = y.clamp(min=0.0)
-        c = y.float()
-        hi, lo = split_f16(c)
-        c = hi.float() + lo.float()                     # what the next layer actually reads
-        out.append((hi.contiguous(), lo.contiguous(), c))
-    return out

@@ -57,7 +57,8 @@ struct Conv2Params {
                                          // are not listed are "background" (b2s_rpn_bg_plan) and get their constant from
                                          // b2s_rpn_bg_fill.  NULL: every tile
     const int *bg_list, *bg_count;       // optional (device): background tiles of this layer's output; the epilogue warps
-    const __half *bg_hi, *bg_lo;         // store the constant bg_hi/bg_lo [Cout] there in the shadow of the MMA main loop
+    const __half *bg_hi, *bg_lo;         // copy them from the layer's empty-frame response bg_hi/bg_lo [H+2, W+2, Cout]
+                                         // (one halo-padded frame) in the shadow of the MMA main loop
     int last_half;                   // 1: the last tile row covers <= 8 image rows -> its MMAs run at N = 128 (upper half
                                      // of the pixel tile only); H = 200 = 12.5 tiles of 16 rows saves 3.8 % of the MMA work
     int out_stride;
@@ -85,15 +86,10 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
     __shared__ __align__(8) uint64_t bar_xfull[X_STAGES], bar_xempty[X_STAGES], bar_wfull[W_STAGES],
         bar_wempty[W_STAGES], bar_tfull[ACC2], bar_tempty[ACC2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ __align__(16) __half s_bg[2][128];             // the layer's background constant (hi, lo)
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int kchunks = p.Cin / BLOCK_K;
     const int n_work = work_total(p);
-    if (p.bg_list && threadIdx.x < 128) {
-        s_bg[0][threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bg_hi[threadIdx.x] : __float2half(0.f);
-        s_bg[1][threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bg_lo[threadIdx.x] : __float2half(0.f);
-    }
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < X_STAGES; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
@@ -265,8 +261,8 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         uint32_t aph = 0;
         // Background tiles (csrc/rpn_bg.cu) of this layer's output are filled by the epilogue warps, which otherwise
         // spend most of a tile waiting for the tensor pipe: CTA c owns background tiles c, c + grid, ... and spreads
-        // them over its work items.  One store instruction of the 256 epilogue threads = one tile row of one plane
-        // (16 pixels x 256 B, contiguous).
+        // them over its work items.  One load / store instruction of the 256 epilogue threads = one tile row of one
+        // plane (16 pixels x 256 B, contiguous) of the layer's empty-frame response, which stays L2 resident.
         const int n_bg = p.bg_list ? min(*p.bg_count, p.num_tiles) : 0;
         const int my_bg = ((int)blockIdx.x < n_bg) ? (n_bg - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
         const int my_work = ((int)blockIdx.x < n_work) ? (n_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -275,19 +271,24 @@ k_conv3x3_tc2(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constan
         const int e_tid = (warp - 4) * 32 + lane;                 // 0..255
         auto fill_bg = [&](int count) {
             const int chunk = e_tid & 15, px = e_tid >> 4;
-            const uint4 vh = *reinterpret_cast<const uint4 *>(&s_bg[0][chunk * 8]);
-            const uint4 vl = *reinterpret_cast<const uint4 *>(&s_bg[1][chunk * 8]);
             for (int q = 0; q < count && bg_done < my_bg; ++q, ++bg_done) {
                 const int t = __ldg(&p.bg_list[(int)blockIdx.x + bg_done * (int)gridDim.x]);
                 const int btw = t % p.tiles_w, bth = (t / p.tiles_w) % p.tiles_h, bb = t / (p.tiles_w * p.tiles_h);
                 const int w = btw * T2_W + px;
                 if (w >= p.W || chunk * 8 >= p.Cout) continue;
-                for (int r = 0; r < T2_H; ++r) {
-                    const int h = bth * T2_H + r;
-                    if (h >= p.H) break;
-                    const size_t pix = ((size_t)bb * (p.H + 2) + (h + 1)) * (p.W + 2) + (w + 1);
-                    *reinterpret_cast<uint4 *>(p.out_hi + pix * p.out_stride + chunk * 8) = vh;
-                    *reinterpret_cast<uint4 *>(p.out_lo + pix * p.out_stride + chunk * 8) = vl;
+                const int rows = min(T2_H, p.H - bth * T2_H);
+                const size_t fpix = (size_t)(bth * T2_H + 1) * (p.W + 2) + (w + 1);            // in the one-frame field
+                const size_t opix = (size_t)bb * (p.H + 2) * (p.W + 2) + fpix;
+                const uint4 *fh = reinterpret_cast<const uint4 *>(p.bg_hi + fpix * p.Cout + chunk * 8);
+                const uint4 *fl = reinterpret_cast<const uint4 *>(p.bg_lo + fpix * p.Cout + chunk * 8);
+                uint4 *oh = reinterpret_cast<uint4 *>(p.out_hi + opix * p.out_stride + chunk * 8);
+                uint4 *ol = reinterpret_cast<uint4 *>(p.out_lo + opix * p.out_stride + chunk * 8);
+                const size_t fstep = (size_t)(p.W + 2) * p.Cout / 8, ostep = (size_t)(p.W + 2) * p.out_stride / 8;
+#pragma unroll 4
+                for (int r = 0; r < rows; ++r) {
+                    const uint4 vh = __ldg(fh + r * fstep), vl = __ldg(fl + r * fstep);
+                    oh[r * ostep] = vh;
+                    ol[r * ostep] = vl;
                 }
             }
         };

@@ -1,16 +1,17 @@
 // rpn_bg.cu -- background-tile planning for the dense RPN (b2s_rpn_bg_plan, b2s_rpn_bg_fill).
 //
 // The BEV map that enters the RPN is mostly empty: 6-8 % of the 200 x 176 pixels of a synthetic KITTI cloud hold
-// data (real clouds: the camera-FOV wedge).  Where a 3x3 layer's whole receptive field is "background", its output
-// does not depend on the data:
-//   layer 1 : the input is exactly 0 there (BEV zero fill, zero halo)  -> out = relu(shift_1)              =: c_1
-//   layer l : the input is the constant vector c_{l-1} on all 9 taps   -> out = relu(scale_l * (sum_taps W_l) c_{l-1} + shift_l) =: c_l
-// (for l >= 2 the zero halo is NOT background, so a one-pixel ring along the image border always counts as data).
-// The constants depend on the weights only and are computed once on the host (b2second/tc.py: background_constants).
-// Per step, the non-background mask is dilated layer by layer (one tiny kernel per layer); a 16 x 16 output tile of
-// k_conv3x3_tc2 whose pixels are all background is not computed -- b2s_rpn_bg_fill stores c_l there -- and the conv
-// kernel walks the compacted list of the remaining tiles, so the work stays balanced over the SMs.
-// Everything the reference computes is still produced; only multiplications by a known constant field are skipped.
+// data (real clouds: the camera-FOV wedge).  The output of layer l of a chain of 3x3 stride-1 pad-1 layers at pixel p
+// depends on the BEV only inside the (2l+1)^2 window around p; where that window holds no data, the output is what the
+// layer produces for an EMPTY frame at p -- a field that depends on the weights only (constant in the interior,
+// different within l pixels of the image border, where the zero padding is felt).  The engine computes that
+// empty-frame response once per layer with the very kernel that runs the layer (so the values are bit-identical to
+// what the kernel would have produced) and keeps it as one halo-padded frame [H+2, W+2, C] of hi/lo planes.
+// Per step, the data mask is dilated by one pixel per layer (one tiny kernel per layer); a 16 x 16 output tile of
+// k_conv3x3_tc2 without a masked pixel is not computed -- it is copied from the empty-frame response (by the conv
+// kernel's own epilogue warps, or b2s_rpn_bg_fill) -- and the conv kernel walks the compacted list of the remaining
+// tiles, so the work stays balanced over the SMs.
+// Everything the reference computes is still produced; only the recomputation of a known field is skipped.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -19,10 +20,10 @@ namespace {
 
 constexpr int TILE = 16;          // must equal conv_tc2.cu T2_H / T2_W
 
-// one block per (frame, tile): out(p) = OR of `in` over the 3x3 window of p (outside the image: `border`);
+// one block per (frame, tile): out(p) = OR of `in` over the 3x3 window of p (outside the image: 0);
 // tile flag = OR of out over the tile's in-image pixels
 __global__ void __launch_bounds__(TILE * TILE)
-k_bg_layer(const uint8_t *__restrict__ in, int H, int W, int tiles_h, int tiles_w, int border, uint8_t *__restrict__ out,
+k_bg_layer(const uint8_t *__restrict__ in, int H, int W, int tiles_h, int tiles_w, uint8_t *__restrict__ out,
            int *__restrict__ tile_flag)
 {
     const int tile = blockIdx.x;
@@ -36,7 +37,7 @@ k_bg_layer(const uint8_t *__restrict__ in, int H, int W, int tiles_h, int tiles_
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
                 const int y = h + dy, x = w + dx;
-                v |= (y < 0 || y >= H || x < 0 || x >= W) ? border : (int)f[(size_t)y * W + x];
+                v |= (y < 0 || y >= H || x < 0 || x >= W) ? 0 : (int)f[(size_t)y * W + x];
             }
         out[((size_t)b * H + h) * W + w] = (uint8_t)(v != 0);
     }
@@ -74,19 +75,18 @@ k_bg_compact(const int *__restrict__ tile_flag, int num_tiles, int *work_list, i
     }
 }
 
-// one block per background tile (grid-stride): thread = (pixel of a tile row, 16-byte channel chunk), so one store
-// instruction of the block writes one whole tile row of a plane (16 pixels x 256 B, contiguous in NHWC)
+// one block per background tile (grid-stride): thread = (pixel of a tile row, 16-byte channel chunk), so one load /
+// store instruction of the block moves one whole tile row of a plane (16 pixels x 256 B, contiguous in NHWC) from
+// the empty-frame response `f` [H+2, W+2, C] to the output map
 __global__ void __launch_bounds__(256)
 k_bg_fill(const int *__restrict__ bg_list, const int *__restrict__ bg_count, int H, int W, int tiles_h, int tiles_w, int C,
-          const __half *__restrict__ c_hi, const __half *__restrict__ c_lo, __half *__restrict__ out_hi,
+          const __half *__restrict__ f_hi, const __half *__restrict__ f_lo, __half *__restrict__ out_hi,
           __half *__restrict__ out_lo, int out_stride)
 {
     const int n = *bg_count;
     const int chunks = C / 8;                         // 16-byte chunks per pixel and plane
     const int px_per_pass = 256 / chunks;             // pixels of a tile row covered per pass (C = 128: 16)
     const int chunk = threadIdx.x % chunks, px = threadIdx.x / chunks;
-    const uint4 vh = *reinterpret_cast<const uint4 *>(c_hi + chunk * 8);
-    const uint4 vl = *reinterpret_cast<const uint4 *>(c_lo + chunk * 8);
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const int tile = bg_list[i];
         const int tw = tile % tiles_w, th = (tile / tiles_w) % tiles_h, b = tile / (tiles_w * tiles_h);
@@ -96,9 +96,12 @@ k_bg_fill(const int *__restrict__ bg_list, const int *__restrict__ bg_count, int
             for (int p0 = 0; p0 < TILE; p0 += px_per_pass) {
                 const int w = tw * TILE + p0 + px;
                 if (p0 + px < TILE && w < W) {
-                    const size_t pix = ((size_t)b * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
-                    *reinterpret_cast<uint4 *>(out_hi + pix * out_stride + chunk * 8) = vh;
-                    *reinterpret_cast<uint4 *>(out_lo + pix * out_stride + chunk * 8) = vl;
+                    const size_t fpix = (size_t)(h + 1) * (W + 2) + (w + 1);
+                    const size_t pix = (size_t)b * (H + 2) * (W + 2) + fpix;
+                    *reinterpret_cast<uint4 *>(out_hi + pix * out_stride + chunk * 8) =
+                        __ldg(reinterpret_cast<const uint4 *>(f_hi + fpix * C + chunk * 8));
+                    *reinterpret_cast<uint4 *>(out_lo + pix * out_stride + chunk * 8) =
+                        __ldg(reinterpret_cast<const uint4 *>(f_lo + fpix * C + chunk * 8));
                 }
             }
         }
@@ -118,7 +121,7 @@ extern "C" int b2s_rpn_bg_plan(const uint8_t *occupancy, int batch, int H, int W
     const uint8_t *in = occupancy;
     for (int l = 0; l < num_layers; ++l) {
         uint8_t *out = scratch + (size_t)(l & 1) * map;
-        k_bg_layer<<<num_tiles, TILE * TILE, 0, stream>>>(in, H, W, tiles_h, tiles_w, l == 0 ? 0 : 1, out,
+        k_bg_layer<<<num_tiles, TILE * TILE, 0, stream>>>(in, H, W, tiles_h, tiles_w, out,
                                                           tile_flags + (size_t)l * num_tiles);
         B2S_LAUNCH_OK();
         in = out;
@@ -129,7 +132,7 @@ extern "C" int b2s_rpn_bg_plan(const uint8_t *occupancy, int batch, int H, int W
 }
 
 extern "C" int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int batch, int H, int W, int C,
-                               const b2s_half *c_hi, const b2s_half *c_lo, b2s_half *out_hi, b2s_half *out_lo,
+                               const b2s_half *f_hi, const b2s_half *f_lo, b2s_half *out_hi, b2s_half *out_lo,
                                int out_stride, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -139,7 +142,7 @@ extern "C" int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int 
     const int num_tiles = batch * tiles_h * tiles_w;
     int blocks = num_tiles < 148 * 8 ? num_tiles : 148 * 8;
     k_bg_fill<<<blocks, 256, 0, stream>>>(bg_list, bg_count_dev, H, W, tiles_h, tiles_w, C,
-                                          reinterpret_cast<const __half *>(c_hi), reinterpret_cast<const __half *>(c_lo),
+                                          reinterpret_cast<const __half *>(f_hi), reinterpret_cast<const __half *>(f_lo),
                                           reinterpret_cast<__half *>(out_hi), reinterpret_cast<__half *>(out_lo), out_stride);
     B2S_LAUNCH_OK();
     return 0;
