@@ -183,6 +183,24 @@ int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_
                        const float *scale, const float *shift, int relu, void *out_hi, b2s_half *out_lo, int out_stride,
                        int cout, unsigned *status_dev, void *stream);
 
+/* Tile plan of a sparse convolution for b2s_sparse_conv_tc_plan (csrc/sparse_plan.cu): the conv kernel owns 128 output
+ * rows per CTA and can skip a kernel offset only when NONE of the tile's rows has that neighbour.
+ *   tile_mask[t]  bit k: some row of tile t (positions 128t .. 128t+127) has a neighbour through offset k
+ *   perm[pos]     (sort = 1) output row at tile position pos: rows are grouped by the shape of their neighbourhood
+ *                 (neighbours below / above the centre plane, before / after the centre row; ksize = (kz,ky,kx) names
+ *                 the planes) inside chunks of 8192 rows, stable -- roughly halves the (tile, offset) blocks of
+ *                 SECOND's middle encoder; sort = 0: tiles in storage order, perm untouched (may be NULL).
+ * The convolution result does not depend on the plan (bit-identical with and without). */
+int b2s_sparse_tile_plan(const int *nbr, int K, const int *ksize /*[3] or NULL*/, const int *num_out_dev, int cap_out,
+                         int sort, int *perm /*[cap_out]*/, unsigned *tile_mask /*[ceil(cap_out/128)]*/, void *stream);
+/* b2s_sparse_conv_tc with a tile plan: perm / tile_mask from b2s_sparse_tile_plan (either may be NULL: identity order /
+ * every offset). */
+int b2s_sparse_conv_tc_plan(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,
+                            const b2s_half *w_hi, const b2s_half *w_lo, const int *nbr, int K, const int *num_out_dev,
+                            int cap_out, const int *perm, const unsigned *tile_mask, const float *scale,
+                            const float *shift, int relu, void *out_hi, b2s_half *out_lo, int out_stride, int cout,
+                            unsigned *status_dev, void *stream);
+
 /* fp32 rows <-> fp16 hi/lo planes (hi = fp16 round-to-nearest, lo = fp16-rounded remainder; saturating).
  * split: x [rows, row_floats] -> out_channels halves per row and plane (>= row_floats, multiple of 8, zero padded), rows
  *        out_stride halves apart (>= out_channels; 2*out_channels for interleaved [row][hi | lo] storage).

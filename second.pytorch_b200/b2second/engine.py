@@ -137,6 +137,7 @@ class InferenceEngine:
         rulebooks = {}
         max_ws = 0
         thin_ok = os.environ.get("B2S_THIN_TC", "1") != "0"      # A/B switch: thin layers on the FMA core
+        plan_mode = int(os.environ.get("B2S_SP_PLAN", "3"))
         for j, ls in enumerate(s.layers):
             K = ls["K"]
             lyr = dict(ls)
@@ -171,6 +172,15 @@ class InferenceEngine:
                 lyr["in_level"], lyr["out_level"] = level, new
                 max_ws = max(max_ws, self.lib.b2s_rulebook_conv_workspace_bytes(self.B, self._L.i3(out_shape)))
                 level = new
+            # tile plan of the rulebook (csrc/sparse_plan.cu): which kernel offsets each 128-row tile needs, and an order
+            # of the rows that makes that set small.  B2S_SP_PLAN: 0 off, 1 masks only, 2 rows grouped for SubM
+            # rulebooks (shared by 2-3 layers), 3 (default) rows grouped for every 27-offset rulebook
+            rb = lyr["rb"]
+            if "tile_mask" not in rb and plan_mode > 0:
+                cap_rb = lyr["out_level"].cap
+                rb["tile_mask"] = torch.zeros((cap_rb + 127) // 128, dtype=torch.int32, device=dev)
+                rb["sort"] = bool(K > 3 and (plan_mode >= 3 or (plan_mode == 2 and ls["subm"])))
+                rb["perm"] = torch.zeros(cap_rb, dtype=torch.int32, device=dev) if rb["sort"] else None
             # tensor-pipe core (csrc/sparse_conv_tc.cu): the library says which (Cin, Cout) it was built for;
             # 3-/4-feature input layers are zero-padded to 8 channels.  Everything else: fp32 FMA core.
             cin_tc = _tc.sparse_tc_cin(ls["cin"])
@@ -463,6 +473,12 @@ class InferenceEngine:
                             L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys) if lyr["want_hash"] else None,
                             L.ptr(lout.vals) if lyr["want_hash"] else None, lout.hcap,
                             L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
+                    if lyr["tc"] and "tile_mask" in lyr["rb"]:
+                        rb = lyr["rb"]
+                        L.check(lib.b2s_sparse_tile_plan(
+                            L.ptr(rb["nbr"]), lyr["K"], L.i3(lyr["kernel_size"]), L.ptr(lout.n_dev), lout.cap,
+                            1 if rb["sort"] else 0, L.ptr(rb["perm"]), L.ptr(rb["tile_mask"]), st),
+                            "b2s_sparse_tile_plan")
                 self._mark("sparse_conv%d" % lyr["index"])
                 if lyr["tc"]:
                     if "in_split" in lyr:
@@ -470,12 +486,13 @@ class InferenceEngine:
                         L.check(lib.b2s_split_f16(L.ptr(feats), L.ptr(hi), L.ptr(lo), L.ptr(lin.n_dev), lin.cap,
                                                   lyr["cin"], lyr["cin_tc"], stride, st), "b2s_split_f16")
                         hilo = (hi, lo, stride)
-                    L.check(lib.b2s_sparse_conv_tc(
+                    L.check(lib.b2s_sparse_conv_tc_plan(
                         L.ptr(hilo[0]), L.ptr(hilo[1]), hilo[2], lin.cap, lyr["cin_tc"], L.ptr(lyr["w_hi"]),
                         L.ptr(lyr["w_lo"]), L.ptr(lyr["rb"]["nbr"]), lyr["K"], L.ptr(lout.n_dev), lout.cap,
+                        L.ptr(lyr["rb"].get("perm")), L.ptr(lyr["rb"].get("tile_mask")),
                         L.ptr(lyr["scale_tc"]), L.ptr(lyr["shift"]), 1 if lyr["relu"] else 0, L.ptr(lyr["out_hi"]),
                         L.ptr(lyr["out_lo"]), lyr["out_stride"], lyr["cout"], L.ptr(self.status), st),
-                        "b2s_sparse_conv_tc")
+                        "b2s_sparse_conv_tc_plan")
                     feats, hilo = None, (lyr["out_hi"], lyr["out_lo"], lyr["out_stride"])
                 else:
                     L.check(lib.b2s_sparse_conv(L.ptr(feats), lyr["cin"], L.ptr(lyr["w"]), L.ptr(lyr["rb"]["nbr"]),
@@ -656,7 +673,9 @@ class InferenceEngine:
                 # subm_nbr / subm_ranked | mark, summary_scan, scan_sums, compact_words, nz_scan, scan_sums, emit,
                 # (hash_build,) scatter_nbr
                 n += 1 if lyr["subm"] else (8 + (1 if lyr.get("want_hash") else 0))
-            n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc
+                if lyr["tc"] and "tile_mask" in lyr["rb"]:
+                    n += 1                       # b2s_sparse_tile_plan
+            n += 1                               # b2s_sparse_conv / b2s_sparse_conv_tc_plan
             if lyr.get("in_split") is not None:
                 n += 1                           # b2s_split_f16
         if self.rpn_impl == "tc":
@@ -747,8 +766,12 @@ class InferenceEngine:
             run_rows, j = sizes[i], i + 1
             if f.is_contiguous() and f.dtype == torch.float32:
                 end = f.data_ptr() + 4 * f.numel()
+                # (same STORAGE, not just adjacent addresses: two separate allocations can end up back to back in the
+                # caching allocator, and a strided view must stay inside its own storage)
+                base = f.untyped_storage().data_ptr()
                 while j < len(frames) and frames[j].dtype == torch.float32 and frames[j].device == f.device and \
-                        frames[j].is_contiguous() and frames[j].data_ptr() == end:
+                        frames[j].is_contiguous() and frames[j].data_ptr() == end and \
+                        frames[j].untyped_storage().data_ptr() == base:
                     end += 4 * frames[j].numel()
                     run_rows += sizes[j]
                     j += 1

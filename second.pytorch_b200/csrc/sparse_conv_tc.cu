@@ -1,35 +1,40 @@
-// sparse_conv_tc.cu -- sparse convolution inner product on the tensor pipe (b2s_sparse_conv_tc).
+// sparse_conv_tc.cu -- sparse convolution inner product on the tensor pipe (b2s_sparse_conv_tc, b2s_sparse_conv_tc_plan).
 //
-// Same output-stationary formulation as sparse_conv.cu (one CTA owns 128 output rows and walks the K kernel
-// offsets; nbr[o][k] names the input row feeding output row o through offset k), but the per-offset product
+// Output-stationary like sparse_conv.cu (one CTA owns 128 output rows = one tcgen05 accumulator; nbr[o][k] names the
+// input row feeding output row o through kernel offset k), but the per-offset product
 //     D[128 rows, Cout] += A[128 gathered rows, 64 channels] * W[k][Cout, 64 channels]^T
 // is a tcgen05.mma (kind::f16) on the 3xF16 hi/lo split (tc_common.cuh), accumulating in TMEM.
 //
-// K block = one 128-byte-wide slice of the reduction (64 fp16 channels):
-//   Cin >= 64 : (kernel offset k, 64-channel chunk ch)                      -- K * Cin/64 K blocks per tile
-//   Cin <  64 : PACK = 64/Cin consecutive kernel offsets side by side        -- ceil(K / PACK) K blocks per tile
-//               (Cin = 32: 2 offsets, 16: 4 offsets, 8: 8 offsets per K block; the weights arrive pre-packed as
-//               [K block][Cout][64], see b2second/tc.py: pack_sparse_weights.  A 3- or 4-feature input layer is
-//               zero-padded to 8 channels = one 16-byte cp.async per row and plane.)
+// K block = one 128-byte-wide slice of the reduction (64 fp16 channels) = PACK = 64/Cin consecutive kernel offsets
+// side by side (Cin = 64: one offset; 32: 2; 16: 4; 8: 8; the weights arrive pre-packed as [K block][Cout][64], see
+// b2second/tc.py: pack_sparse_weights; a 3- or 4-feature input layer is zero-padded to 8 channels).
+//
+// Tile plan (round 2, sparse_plan.cu): tile_mask[tile] says which kernel offsets ANY of the tile's 128 rows needs; a K
+// block none of whose offsets is needed is skipped by every role (weights not loaded, rows not gathered, MMAs not
+// issued).  perm[] (optional) makes a tile = 128 rows with a similar neighbourhood shape, which roughly halves the
+// K blocks of the SECOND middle encoder.  A missing neighbour contributes exact zeros and the accumulation chains have
+// FIXED K-block boundaries (chain c = K blocks [c*CHAIN_KB, (c+1)*CHAIN_KB)), so the value of an output row does not
+// depend on which rows share its tile: planned, unplanned and round-1 results are bit-identical.
 //
 // Warp roles (16 warps):
 //   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
 //   warp 1      MMA issuer (one elected lane, software-pipelined)
 //   warp 2      TMEM allocator
-//   warps 4-11  gather producers: 16-byte cp.async copies of the neighbour rows (hi and lo planes) into the
-//               K-major SWIZZLE_128B A tile, zero-fill for missing neighbours, completion signalled on the
-//               stage's mbarrier with cp.async.mbarrier.arrive.noinc.  (A TMA tile::gather4 producer was tried
-//               -- tests/cuda/gather4_probe.cu proves the instruction works -- but 64 four-row TMA ops per K
-//               block ran 3x SLOWER than cp.async: ~60+ cycles per gather4 issue, measured round 1.)
+//   warps 4-11  gather producers.  Gather warp w OWNS pipeline stage w % 4 and the tile's row half w / 4: it handles
+//               every 4th K block, all 16-byte cp.async copies of its 64 rows (hi and lo planes) into the K-major
+//               SWIZZLE_128B A tile, zero-fill for missing neighbours, completion signalled on the stage's mbarrier
+//               with cp.async.mbarrier.arrive.noinc.  The neighbour-table entries of the NEXT owned K block are
+//               loaded (straight from global / L1) before the current one is waited for.
+//               History: until round 2 all 8 warps worked on EVERY K block (16 rows each) behind a shared-memory copy
+//               of the tile's table.  clock64 showed the issuer waiting ~410 of ~900 cycles per K block for gather
+//               warps that were themselves busy ~670 cycles: one short dependent instruction chain per K block and
+//               warp (wait, 4 table reads, 8 copies, arrive), serialised K block after K block -- neither the copies
+//               (diagnostic: off) nor the 256 mbarrier arrivals (diagnostic: one per warp) were the cost.  Owning a
+//               stage gives a warp four K-block times for 32 independent copies.  (A TMA tile::gather4 producer
+//               was tried in round 1 -- tests/cuda/gather4_probe.cu -- 3x slower than cp.async.)
 //   warps 12-15 epilogue: drain per-chain partial sums from TMEM (round-to-nearest adds in registers, the
 //               tensor core's own accumulate is not RN -- see conv_tc.cu), BN scale/shift + ReLU, hi/lo split,
 //               coalesced row stores through a small staging tile
-//
-// What bounds it (clock64 instrumentation, B2S_SP_ZSKIP bit 16, round 1): the gather producers' own instruction
-// stream.  With 4 gather warps and address arithmetic inside the K-block loop the MMA issuer waited ~940 of
-// ~1340 cycles per K block for them although the copies themselves cost 4 %; hoisting everything that is constant
-// per kernel offset, unrolling the channel chunks and doubling the gather warps brought the K block to ~760
-// cycles (tensor pipe 448 of them, tests/cuda/mma_probe2.cu).
 #include <cuda_fp16.h>
 
 #include "tc_common.cuh"
@@ -37,10 +42,12 @@
 namespace {
 
 using namespace b2s_tc;
+constexpr int STAGES = 4;                 // pipeline stages; gather warp w owns stage w % STAGES
 constexpr int GW = 8;                     // gather warps (warps 4 .. 4+GW-1); epilogue = the 4 warps after them
-constexpr int RI = 128 / GW / 4;          // 4-row copy iterations per gather warp and K block
+// gather ownership: OWN = 4: warp w owns every 4th K block (pairs of warps share a K block, 64 rows each);
+//                   OWN = 1: all 8 warps work on every K block (16 rows each)
 constexpr int kThreads = 32 * (4 + GW + 4);
-constexpr int GROUP = 3;                  // kernel offsets per accumulation chain (Cin >= 32)
+constexpr int GROUP = 3;                  // kernel offsets per accumulation chain (Cin = 64)
 constexpr int ACC_SLOTS = 4;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gsrc, uint32_t src_bytes)
@@ -52,32 +59,88 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar)
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// non-blocking poll (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 30); ++it) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// warp-level wait: only lane 0 polls the barrier (32 lanes spinning on try_wait are 32 shared-memory operations per
+// iteration competing with the copies for the LSU), the others are released through __syncwarp
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, bool lane0_only)
+{
+    if (lane0_only) {
+        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+        __syncwarp();
+    } else {
+        mbar_wait(bar, parity);
+    }
+}
+
+#ifdef B2S_DIAG
+// make DIAG=1 + B2S_SP_ZSKIP bit 64: per-K-block clock64 stamps of every role of CTA 0 (K blocks 0..127), printed at exit
+__device__ long long g_trace[10][128];
+#define B2S_TRACE(ROLE, G) do { if ((p.flags & 64) && blockIdx.x == 0 && (G) < 128 && ((ROLE) < 5 || (threadIdx.x & 31) == 0)) g_trace[ROLE][G] = clock64(); } while (0)
+#else
+#define B2S_TRACE(ROLE, G) do { } while (0)
+#endif
+
 struct SpParams {
     const __half *in_hi, *in_lo;
     int in_stride, out_stride;   // halves between consecutive rows of the input / output planes
     int *status;
     const int *nbr;
     const int *n_out_dev;
+    const int *perm;             // tile position -> output row (NULL: identity)
+    const unsigned *tile_mask;   // per 128-position tile: kernel offsets some row of the tile has (NULL: all)
     int cap_out, K, relu;
-    int flags;               // B2S_SP_ZSKIP: bit 0 zero-slot skip (default on); diagnostics (wrong results): 2 no gather
-                             // copies, 4 no weight loads, 8 no neighbour-table staging; 16 print the issuer's wait times
+    int flags;                   // B2S_SP_ZSKIP: bit 0 zero-slot skip (default on); 16 print the issuer's wait times
     const float *scale, *shift;
     void *out_hi;                // fp16 hi plane, or (out_lo == NULL) fp32 rows [cap_out, COUT]
     __half *out_lo;
 };
 
+// K blocks a tile needs, from its offset mask: bit j = K block j (offsets j*PACK .. j*PACK+PACK-1).  Never empty:
+// K block 0 stands in for a tile without any neighbour (cannot happen for SubM / strided conv outputs, but every role
+// must agree on the sequence whatever the table holds).
+template <int PACK>
+__device__ __forceinline__ uint32_t kb_mask_of(uint32_t offsets, int num_kb)
+{
+    uint32_t m = 0;
+    if constexpr (PACK == 1) {
+        m = offsets;
+    } else {
+        constexpr int MAXKB = (27 + PACK - 1) / PACK;
+#pragma unroll
+        for (int j = 0; j < MAXKB; ++j)
+            if (j < num_kb && ((offsets >> (j * PACK)) & ((1u << PACK) - 1u))) m |= 1u << j;
+    }
+    return m ? m : 1u;
+}
+
 // CIN in {8, 16, 32, 64}; COUT (= UMMA N) in {16, 32, 64}
-template <int CIN, int COUT, int STAGES>
+template <int CIN, int COUT, int OWN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SpParams p)
 {
     constexpr int N = COUT;
-    constexpr bool PACKED = CIN < BLOCK_K;
-    constexpr int PACK = PACKED ? BLOCK_K / CIN : 1;          // kernel offsets per K block
-    constexpr int KCH = PACKED ? 1 : CIN / BLOCK_K;           // 64-channel chunks per offset
+    constexpr int HALVES = GW / OWN;          // gather warps sharing one K block (each takes BLOCK_M / HALVES rows)
+    constexpr int RI = BLOCK_M / HALVES / 4;  // 4-row copy iterations per gather warp and K block
+    static_assert(GW % OWN == 0 && RI * 4 * HALVES == BLOCK_M && (OWN & (OWN - 1)) == 0 && RI * STAGES <= 64, "gather warp layout");
+    static_assert(CIN <= BLOCK_K && BLOCK_K % CIN == 0, "one K block holds whole kernel offsets");
+    constexpr int PACK = BLOCK_K / CIN;                       // kernel offsets per K block
     constexpr int CPO = 8 / PACK;                             // 16-byte chunks per offset inside a 128-byte row
-    constexpr int CHAIN_KB = PACKED ? 2 : GROUP * KCH;        // K blocks per accumulation chain (short chains)
+    constexpr int CHAIN_KB = PACK > 1 ? 2 : GROUP;            // K blocks per accumulation chain (short chains)
+    constexpr uint32_t CHAIN_BITS = (1u << CHAIN_KB) - 1u;
     constexpr uint32_t B_TILE_BYTES = N * BLOCK_K * ELEM_BYTES;
     constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     // B-operand concatenation: the stage holds W_hi (N rows) directly followed by W_lo (N rows), so ONE MMA with
@@ -87,29 +150,32 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     constexpr int ACC_W = 2 * N;                              // accumulator slot width in TMEM columns
     constexpr uint32_t TMEM_COLS = (ACC_SLOTS * ACC_W <= 128) ? 128 : (ACC_SLOTS * ACC_W <= 256) ? 256 : 512;
     static_assert(N % 16 == 0 && ACC_SLOTS * ACC_W <= 512, "TMEM capacity");
-    static_assert(STAGES * 8 <= 32, "zero-slot bookkeeping uses 8 bits per stage");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_tfull[ACC_SLOTS], bar_tempty[ACC_SLOTS];
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale[N], s_shift[N];
-    __shared__ int s_nbr[BLOCK_M * 27];                      // the tile's neighbour table (K <= 27)
     __shared__ __align__(16) uint32_t s_stage[4][32 * 36];   // per epilogue warp: 32 rows x 32 words transpose tile
 
     const int warp = warp_idx_uniform(), lane = threadIdx.x & 31;
     const int n_out = min(*p.n_out_dev, p.cap_out);
     const int num_tiles = (n_out + BLOCK_M - 1) / BLOCK_M;
     const int K = p.K;
-    const int num_kb = PACKED ? (K + PACK - 1) / PACK : K * KCH;
+    const int num_kb = (K + PACK - 1) / PACK;
     const int num_chains = (num_kb + CHAIN_KB - 1) / CHAIN_KB;
+    const bool poll1 = (p.flags & 32) == 0;                 // B2S_SP_ZSKIP bit 32: every lane polls (the round-1 behaviour)
+    const uint32_t all_offsets = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
+    auto tile_kbm = [&](int tile) -> uint32_t {
+        return kb_mask_of<PACK>(p.tile_mask ? __ldg(&p.tile_mask[tile]) & all_offsets : all_offsets, num_kb);
+    };
 
     if (threadIdx.x < N) {
         s_scale[threadIdx.x] = p.scale ? p.scale[threadIdx.x] : 1.f;
         s_shift[threadIdx.x] = p.shift ? p.shift[threadIdx.x] : 0.f;
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 32 * GW + 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&bar_full[i], 32 * HALVES + 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < ACC_SLOTS; ++i) { mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -125,23 +191,31 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
 
     if (warp == 0) {
         // ===================== weight TMA producer =====================
-        if (lane == 0) {
+        if (lane == 0 && (int)blockIdx.x < num_tiles) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                for (int kb = 0; kb < num_kb; ++kb) {
+            uint32_t kbm_next = tile_kbm(blockIdx.x);
+            int wg = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                uint32_t kbm = kbm_next;
+                if (tile + (int)gridDim.x < num_tiles) kbm_next = tile_kbm(tile + gridDim.x);
+                while (kbm) {
+                    const int kb = __ffs(kbm) - 1;
+                    kbm &= kbm - 1;
                     mbar_wait(&bar_empty[stage], phase ^ 1);
+                    B2S_TRACE(0, wg);
                     uint8_t *st = smem + (size_t)stage * STAGE_BYTES;
-                    if (p.flags & 4) {                     // diagnostic: no weight loads (results wrong)
-                        mbar_arrive(&bar_full[stage]);
-                    } else {
-                        const int c0 = PACKED ? 0 : (kb % KCH) * BLOCK_K, c2 = PACKED ? kb : kb / KCH;
-                        mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
-                        tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], c0, 0, c2);
-                        tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], c0, 0, c2);
-                    }
+#ifdef B2S_DIAG
+                    if (p.flags & 4) { mbar_arrive(&bar_full[stage]); if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+#endif
+                    mbar_arrive_expect_tx(&bar_full[stage], 2 * B_TILE_BYTES);
+                    tma_load_3d(st + 2 * A_TILE_BYTES, &map_w_hi, &bar_full[stage], 0, 0, kb);
+                    tma_load_3d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_w_lo, &bar_full[stage], 0, 0, kb);
+                    B2S_TRACE(1, wg);
+                    ++wg;
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -158,181 +232,242 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             int acc = 0;
             uint32_t acc_phase = 0;
             const bool timing = (p.flags & 16) != 0;
-            long long t_full = 0, t_tempty = 0, t_fence = 0, t_begin = clock64();
+            const bool commit_first = (p.flags & 512) != 0, spin = (p.flags & 256) != 0;
+            long long t_full = 0, t_tempty = 0, t_begin = clock64();
             int n_kb = 0;
             mbar_wait(&bar_tempty[0], 1);
             mbar_wait(&bar_full[0], 0);
             tc_fence_after();
+            uint32_t kbm_next = tile_kbm(blockIdx.x);
             for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
                 const bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
-                for (int g = 0; g < num_chains; ++g) {
+                uint32_t kbm = kbm_next;
+                if (!last_tile) kbm_next = tile_kbm(tile + gridDim.x);
+                bool fresh = true;                              // the next MMA opens an accumulation chain
+                while (kbm) {
+                    const int kb = __ffs(kbm) - 1;
+                    kbm &= kbm - 1;
+                    const bool chain_end = (kbm & (CHAIN_BITS << ((kb / CHAIN_KB) * CHAIN_KB))) == 0;
                     const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
-                    const int kb_end = min(num_kb, (g + 1) * CHAIN_KB) - g * CHAIN_KB;   // K blocks of this chain
                     int accn = acc + 1;
                     uint32_t acc_phase_n = acc_phase;
                     if (accn == ACC_SLOTS) { accn = 0; acc_phase_n ^= 1; }
-                    for (int kb = 0; kb < kb_end; ++kb) {
-                        const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
-                        const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
-                        const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
+                    const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+                    const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
+                    const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
 #pragma unroll
-                        for (int kk = 0; kk < 3; ++kk) {
-                            const uint64_t koff = (uint64_t)((kk * UMMA_K * ELEM_BYTES) >> 4);
-                            umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kb | kk) != 0);   // cols [0,2N)
-                            umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                 // cols [0,N)
-                        }
-                        // look ahead
-                        int stn = stage + 1;
-                        uint32_t phn = phase;
-                        if (stn == STAGES) { stn = 0; phn ^= 1; }
-                        const bool chain_end = kb == kb_end - 1;
-                        const bool last = last_tile && chain_end && g == num_chains - 1;
-                        if (!last) {
-                            const long long w0 = timing ? clock64() : 0;
-                            mbar_wait(&bar_full[stn], phn);
-                            const long long w1 = timing ? clock64() : 0;
-                            if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
-                            const long long w2 = timing ? clock64() : 0;
-                            tc_fence_after();
-                            if (timing) { t_full += w1 - w0; t_tempty += w2 - w1; t_fence += clock64() - w2; ++n_kb; }
-                        }
-                        {
-                            const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
-                            umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
-                            umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
-                        }
-                        umma_commit(&bar_empty[stage]);
-                        if (chain_end) umma_commit(&bar_tfull[acc]);
-                        stage = stn; phase = phn;
+                    for (int kk = 0; kk < 3; ++kk) {
+                        const uint64_t koff = (uint64_t)((kk * UMMA_K * ELEM_BYTES) >> 4);
+                        umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kk != 0 || !fresh) ? 1u : 0u);   // cols [0,2N)
+                        umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                                // cols [0,N)
                     }
-                    acc = accn; acc_phase = acc_phase_n;
+                    int stn = stage + 1;
+                    uint32_t phn = phase;
+                    if (stn == STAGES) { stn = 0; phn ^= 1; }
+                    const bool last = last_tile && kbm == 0;
+                    B2S_TRACE(2, n_kb);
+                    if (!last && !commit_first) {
+                        const long long w0 = timing ? clock64() : 0;
+                        if (spin) mbar_wait_spin(&bar_full[stn], phn); else mbar_wait(&bar_full[stn], phn);
+                        B2S_TRACE(3, n_kb);
+                        const long long w1 = timing ? clock64() : 0;
+                        if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
+                        tc_fence_after();
+                        if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; }
+                    }
+                    {
+                        const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
+                        umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
+                        umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
+                    }
+                    umma_commit(&bar_empty[stage]);
+                    B2S_TRACE(4, n_kb);
+                    ++n_kb;
+                    fresh = false;
+                    if (chain_end) {
+                        umma_commit(&bar_tfull[acc]);
+                        acc = accn; acc_phase = acc_phase_n;
+                        fresh = true;
+                    }
+                    if (!last && commit_first) {
+                        const long long w0 = timing ? clock64() : 0;
+                        if (spin) mbar_wait_spin(&bar_full[stn], phn); else mbar_wait(&bar_full[stn], phn);
+                        B2S_TRACE(3, n_kb - 1);
+                        const long long w1 = timing ? clock64() : 0;
+                        if (chain_end) mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
+                        tc_fence_after();
+                        if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; }
+                    }
+                    stage = stn; phase = phn;
                 }
             }
             if (timing && blockIdx.x == 0)
-                printf("[sparse_tc<%d,%d>] issuer: %d K blocks, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
-                       "wait tempty %lld (%.0f/kb), fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, clock64() - t_begin,
-                       (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1), t_tempty,
-                       (double)t_tempty / (n_kb + 1), t_fence, (double)t_fence / (n_kb + 1));
+                printf("[sparse_tc<%d,%d>] issuer: %d K blocks in %d tiles, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
+                       "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, (num_tiles_u + (int)gridDim.x - 1) / (int)gridDim.x,
+                       clock64() - t_begin, (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1),
+                       t_tempty, (double)t_tempty / (n_kb + 1));
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 4 + GW) {
         // ===================== gather producers =====================
         // Lane mapping: one warp instruction covers 4 rows x 8 sixteen-byte chunks, so the 32 lanes write 4 whole
         // 128-byte smem rows (bank-conflict free under the 128B swizzle) and read 4 x 128 contiguous global bytes.
-        // (One lane per row -- the first version -- was a 4-way bank conflict on every cp.async.)
-        const int gw = warp - 4;                               // rows 4*RI*gw .. of the tile
+        // The loop body is written for instruction count: a gather warp is ONE instruction stream, ~8 cycles per
+        // dependent instruction, and the first version of this loop (lambdas, branches around the copies) compiled to
+        // ~740 instructions per K block for 32 copies -- the gather warps, not memory, bounded the kernel.
+        const int gw = warp - 4;
+        const int my_own = gw % OWN;                           // this warp takes K blocks g with g % OWN == my_own
+        const int half = gw / OWN;                             // rows half*(128/HALVES) .. of the tile
         const int sub = lane >> 3;                             // row within a group of 4
         const uint32_t chunk = (uint32_t)(lane & 7);           // 16-byte chunk of the 128-byte row
-        int stage = 0;
-        uint32_t phase = 0;
-        // ~70 % of the neighbour slots are empty.  Bit (stage*8 + i) of `zeroed` remembers that this lane's 16-byte
-        // chunk of row slot i in that stage already holds zeros (from an earlier empty neighbour), so an empty
-        // neighbour needs no shared-memory write at all (predication, uniform issue).
-        uint32_t zeroed = 0;
-        uint32_t dst_off[RI];                                   // swizzled byte offset of (row slot i, chunk) in a stage
-#pragma unroll
-        for (int i = 0; i < RI; ++i) {
-            const uint32_t rl = (uint32_t)(gw * (4 * RI) + i * 4 + sub);
-            dst_off[i] = rl * 128u + ((chunk ^ (rl & 7u)) << 4);
-        }
-        const ptrdiff_t lo_delta = reinterpret_cast<const char *>(p.in_lo) - reinterpret_cast<const char *>(p.in_hi);
+        // row slot rl = half*64 + i*4 + sub (i = 0..RI-1): byte offset rl*128 + ((chunk ^ (rl & 7)) << 4), and
+        // rl & 7 = sub for even i, sub + 4 for odd i
+        const uint32_t rl0 = (uint32_t)(half * (BLOCK_M / HALVES) + sub);
+        const uint32_t sa0 = smem_u32(smem);
+        const uint32_t dst_even = rl0 * 128u + ((chunk ^ (uint32_t)sub) << 4);
+        const uint32_t dst_odd = rl0 * 128u + ((chunk ^ (uint32_t)(sub + 4)) << 4);
+        const int ko = (int)chunk / CPO;                       // offset inside the pack this lane's chunk belongs to
+        const char *src_base = reinterpret_cast<const char *>(p.in_hi) + (((int)chunk % CPO) * 16);
+        asm volatile("" : "+l"(src_base));                     // one 64-bit register (not base + lane part re-added per copy)
+        const long long lo_delta = reinterpret_cast<const char *>(p.in_lo) - reinterpret_cast<const char *>(p.in_hi);
+        const uint32_t row_bytes = (uint32_t)p.in_stride * ELEM_BYTES;       // rows_in * row_bytes < 2^32 (checked on the host)
         const bool zskip_on = (p.flags & 1) != 0;
-        const uint32_t copy_mask = (p.flags & 2) ? 0u : 0xFFu;  // diagnostic bit 2: no copies at all
-        const uint32_t smem0 = smem_u32(smem);
+        const int grid = (int)gridDim.x;
+        const int *__restrict__ nbr = p.nbr;
+        const int pos0 = half * (BLOCK_M / HALVES) + sub;      // tile position of row slot i: pos0 + 4 i
 
-        const bool timing_g = (p.flags & 16) != 0 && blockIdx.x == 0 && gw == 0 && lane == 0;
-        long long tg_empty = 0, tg_stage = 0, tg_begin = clock64();
-        int tg_kb = 0;
-        // one K block: wait for the stage, issue this lane's (predicated) copies, arrive
-        auto copy_block = [&](uint32_t valid, const char *const *g_hi, const char *const *g_lo, int byte_off) {
-            const long long te0 = timing_g ? clock64() : 0;
-            mbar_wait(&bar_empty[stage], phase ^ 1);
-            if (timing_g) { tg_empty += clock64() - te0; ++tg_kb; }
-            const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
-            const uint32_t zst = (zeroed >> (stage * 8)) & 0xFFu;          // slots of this stage holding zeros
-            const uint32_t need = (valid | ~zst | (zskip_on ? 0u : 0xFFu)) & copy_mask;
-#pragma unroll
-            for (int i = 0; i < RI; ++i) {
-                if (need & (1u << i)) {
-                    const uint32_t nbytes = (valid >> i) & 1u ? 16u : 0u;     // src-size 0 -> 16 bytes of zeros
-                    cp_async16(sa + dst_off[i], g_hi[i] + byte_off, nbytes);
-                    cp_async16(sa + dst_off[i] + A_TILE_BYTES, g_lo[i] + byte_off, nbytes);
+        // ---- enumeration of the CTA's K blocks (same sequence in every role); this warp takes every STAGES-th ----
+        int e_tile = (int)blockIdx.x - grid;
+        uint32_t e_kbm = 0;
+        int e_g = 0, e_owned = 0, g_cur = 0;
+#define B2S_NEXT_OWNED(KB_OUT, TILE_OUT)                                                      \
+        do {                                                                                  \
+            KB_OUT = -1;                                                                      \
+            for (;;) {                                                                        \
+                if (e_kbm == 0) {                                                             \
+                    e_tile += grid;                                                           \
+                    if (e_tile >= num_tiles) break;                                           \
+                    e_kbm = tile_kbm(e_tile);                                                 \
+                }                                                                             \
+                const int kb_ = __ffs(e_kbm) - 1;                                             \
+                e_kbm &= e_kbm - 1;                                                           \
+                const bool mine_ = (e_g & (OWN - 1)) == my_own;                               \
+                ++e_g;                                                                        \
+                if (mine_) { TILE_OUT = e_tile; KB_OUT = kb_; e_owned = e_g - 1; break; }     \
+            }                                                                                 \
+        } while (0)
+        // rows of a tile handled by this lane: index of the row's first table entry (row * K; 0 for a missing row, whose
+        // bit in `ok` is clear)
+#define B2S_LOAD_ROWS(TILE, RK, OK)                                                           \
+        do {                                                                                  \
+            OK = 0;                                                                           \
+            _Pragma("unroll") for (int i = 0; i < RI; ++i) {                                  \
+                const int pos_ = (TILE) * BLOCK_M + pos0 + i * 4;                             \
+                const bool live_ = pos_ < n_out;                                              \
+                const int row_ = !live_ ? 0 : (p.perm ? __ldg(&p.perm[pos_]) : pos_);         \
+                RK[i] = row_ * K;                                                             \
+                OK |= (live_ ? 1u : 0u) << i;                                                 \
+            }                                                                                 \
+        } while (0)
+        // table entries of K block KB for the lane's RI rows (k clamped into the table; KV = 0 when k is past the last
+        // offset of a partly filled pack)
+#define B2S_LOAD_NBR(KB, RK, NB, KV)                                                          \
+        do {                                                                                  \
+            const int k_ = (KB) * PACK + ko;                                                  \
+            KV = k_ < K ? 0xFFFFFFFFu : 0u;                                                   \
+            const int *t_ = nbr + (k_ < K ? k_ : K - 1);                                      \
+            _Pragma("unroll") for (int i = 0; i < RI; ++i) NB[i] = __ldg(t_ + RK[i]);         \
+        } while (0)
+
+        int rows_cur[RI], rows_pf[RI], nb_cur[RI], nb_nxt[RI];
+        uint32_t ok_cur = 0, ok_pf = 0, kv_cur = 0, kv_nxt = 0;
+        int cur_tile = -1, nxt_tile = -1, pf_tile = -1;
+        int kb_cur;
+        B2S_NEXT_OWNED(kb_cur, cur_tile);
+        g_cur = e_owned;
+        if (kb_cur >= 0) {
+            B2S_LOAD_ROWS(cur_tile, rows_cur, ok_cur);
+            B2S_LOAD_NBR(kb_cur, rows_cur, nb_cur, kv_cur);
+            pf_tile = cur_tile + grid;
+            if (pf_tile < num_tiles) B2S_LOAD_ROWS(pf_tile, rows_pf, ok_pf);
+        }
+        unsigned long long zeroed_all = 0;   // bit stage*RI + i: this lane's chunk of row slot i in that stage holds zeros
+        while (kb_cur >= 0) {
+            // ---- prefetch the table entries of the next owned K block ----
+            int kb_nxt;
+            B2S_NEXT_OWNED(kb_nxt, nxt_tile);
+            const bool switch_tile = kb_nxt >= 0 && nxt_tile != cur_tile;
+            if (kb_nxt >= 0) {
+                if (switch_tile) {
+                    if (nxt_tile != pf_tile) { B2S_LOAD_ROWS(nxt_tile, rows_pf, ok_pf); pf_tile = nxt_tile; }   // rare: a tile was skipped
+                    B2S_LOAD_NBR(kb_nxt, rows_pf, nb_nxt, kv_nxt);
+                } else {
+                    B2S_LOAD_NBR(kb_nxt, rows_cur, nb_nxt, kv_nxt);
                 }
             }
-            zeroed = (zeroed & ~(0xFFu << (stage * 8))) | ((~valid & 0xFFu) << (stage * 8));
-            cp_async_mbar_arrive_noinc(&bar_full[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        };
-
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            // stage the tile's neighbour table in shared memory (coalesced), shared by the gather warps
-            const long long ts0 = timing_g ? clock64() : 0;
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");     // previous tile's readers are done
-            {
-                const int row0 = tile * BLOCK_M;
-                const int valid_n = min(BLOCK_M, n_out - row0) * K;
-                const int *src = p.nbr + (size_t)row0 * K;
-                if (!(p.flags & 8)) {                  // (diagnostic bit 8: skip the table staging)
-                    // fixed trip count (K <= 27) so the loads are all in flight together instead of one L2 round
-                    // trip per iteration
-                    constexpr int NLD = (BLOCK_M * 27 + 32 * GW - 1) / (32 * GW);
-                    int v[NLD];
+            // ---- current K block: which slots carry a row, which must be written (a row, or zeros over a stale row) ----
+            uint32_t valid = 0;
 #pragma unroll
-                    for (int j = 0; j < NLD; ++j) {
-                        const int i = gw * 32 + lane + j * 32 * GW;
-                        v[j] = i < valid_n ? __ldg(&src[i]) : -1;
-                    }
+            for (int i = 0; i < RI; ++i) valid |= ((uint32_t)(~nb_cur[i]) >> 31) << i;
+            valid &= ok_cur & kv_cur;
+            const int my_stage = g_cur % STAGES;               // K block g lives in stage g % STAGES, its (g / STAGES)-th use
+            const uint32_t use_parity = (((uint32_t)g_cur / STAGES) & 1u) ^ 1u;
+            const uint32_t zeroed = (uint32_t)(zeroed_all >> (my_stage * RI)) & ((1u << RI) - 1u);
+            const uint32_t need = zskip_on ? (valid | (~zeroed & ((1u << RI) - 1u))) : 0xFFFFFFFFu;
+            const uint32_t sa = sa0 + (uint32_t)my_stage * STAGE_BYTES;
+            if (half == 0) B2S_TRACE(5, g_cur);
+            mbar_wait_warp(&bar_empty[my_stage], use_parity, poll1);
+            if (half == 0) B2S_TRACE(6, g_cur);
+            if (lo_delta == (long long)(CIN * ELEM_BYTES)) {
+                // interleaved rows [hi Cin | lo Cin]: the lo copy is the hi address + an immediate
 #pragma unroll
-                    for (int j = 0; j < NLD; ++j) {
-                        const int i = gw * 32 + lane + j * 32 * GW;
-                        if (i < BLOCK_M * K) s_nbr[i] = v[j];
-                    }
-                }
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * GW) : "memory");
-            if (timing_g) tg_stage += clock64() - ts0;
-            if constexpr (!PACKED) {
-                // addresses and validity are constant per kernel offset; the channel chunks are unrolled so that
-                // ch * 128 folds into the copy instructions' address immediates
-                for (int k = 0; k < K; ++k) {
-                    const char *g_hi[RI], *g_lo[RI];
-                    uint32_t valid = 0;
-#pragma unroll
-                    for (int i = 0; i < RI; ++i) {
-                        const int src = s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k];
-                        valid |= (src >= 0 ? 1u : 0u) << i;
-                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * p.in_stride + chunk * 8);
-                        g_lo[i] = g_hi[i] + lo_delta;
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < KCH; ++ch) copy_block(valid, g_hi, g_lo, ch * (BLOCK_K * ELEM_BYTES));
+                for (int i = 0; i < RI; ++i) {
+                    const char *g = src_base + (unsigned long long)(uint32_t)max(nb_cur[i], 0) * row_bytes;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %3, 0;\n\t"
+                        "@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t"
+                        "@p cp.async.cg.shared.global [%0+16384], [%1+%4], 16, %2;\n\t}"
+                        ::"r"(sa + ((i & 1) ? dst_odd : dst_even) + (uint32_t)i * 512u), "l"(g), "r"((valid >> i & 1u) << 4),
+                          "r"(need & (1u << i)), "n"(CIN * ELEM_BYTES) : "memory");
                 }
             } else {
-                // PACK offsets side by side: this lane's chunk belongs to offset kb*PACK + chunk/CPO and carries
-                // channels (chunk % CPO)*8 .. +7 of that neighbour's row
-                const int ko = (int)chunk / CPO;
-                const int cofs = ((int)chunk % CPO) * 8;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    const int k = kb * PACK + ko;
-                    const char *g_hi[RI], *g_lo[RI];
-                    uint32_t valid = 0;
 #pragma unroll
-                    for (int i = 0; i < RI; ++i) {
-                        const int src = k < K ? s_nbr[(gw * (4 * RI) + i * 4 + sub) * K + k] : -1;
-                        valid |= (src >= 0 ? 1u : 0u) << i;
-                        g_hi[i] = reinterpret_cast<const char *>(p.in_hi + (size_t)(src >= 0 ? src : 0) * p.in_stride + cofs);
-                        g_lo[i] = g_hi[i] + lo_delta;
-                    }
-                    copy_block(valid, g_hi, g_lo, 0);
+                for (int i = 0; i < RI; ++i) {
+                    const char *g = src_base + (unsigned long long)(uint32_t)max(nb_cur[i], 0) * row_bytes;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %3, 0;\n\t"
+                        "@p cp.async.cg.shared.global [%0], [%1], 16, %2;\n\t"
+                        "@p cp.async.cg.shared.global [%0+16384], [%4], 16, %2;\n\t}"
+                        ::"r"(sa + ((i & 1) ? dst_odd : dst_even) + (uint32_t)i * 512u), "l"(g), "r"((valid >> i & 1u) << 4),
+                          "r"(need & (1u << i)), "l"(g + lo_delta) : "memory");
                 }
             }
+            static_assert(A_TILE_BYTES == 16384, "lo plane of the A tile sits 16384 bytes after the hi plane");
+            zeroed_all = (zeroed_all & ~((unsigned long long)((1u << RI) - 1u) << (my_stage * RI))) |
+                         ((unsigned long long)(~valid & ((1u << RI) - 1u)) << (my_stage * RI));
+            if (p.flags & 128) mbar_arrive(&bar_full[my_stage]); else cp_async_mbar_arrive_noinc(&bar_full[my_stage]);
+            if (half == 0) B2S_TRACE(7, g_cur);
+            // ---- advance ----
+            g_cur = e_owned;
+            kb_cur = kb_nxt;
+            kv_cur = kv_nxt;
+#pragma unroll
+            for (int i = 0; i < RI; ++i) nb_cur[i] = nb_nxt[i];
+            if (switch_tile) {
+#pragma unroll
+                for (int i = 0; i < RI; ++i) rows_cur[i] = rows_pf[i];
+                ok_cur = ok_pf;
+                cur_tile = nxt_tile;
+                pf_tile = cur_tile + grid;                  // rows of the tile after this one, long before they are needed
+                if (pf_tile < num_tiles) B2S_LOAD_ROWS(pf_tile, rows_pf, ok_pf);
+            }
         }
+#undef B2S_NEXT_OWNED
+#undef B2S_LOAD_ROWS
+#undef B2S_LOAD_NBR
         asm volatile("cp.async.wait_all;" ::: "memory");
-        if (timing_g)
-            printf("[sparse_tc<%d,%d>] gather warp 0: %d K blocks, total %lld cyc (%.0f/kb), wait empty %lld (%.0f/kb), "
-                   "nbr-table staging %lld (%.0f/kb)\n", CIN, COUT, tg_kb, clock64() - tg_begin,
-                   (double)(clock64() - tg_begin) / (tg_kb + 1), tg_empty, (double)tg_empty / (tg_kb + 1), tg_stage,
-                   (double)tg_stage / (tg_kb + 1));
     } else if (warp >= 4 + GW) {
         // ===================== epilogue =====================
         const int ew = warp - (4 + GW);                // == warp % 4: TMEM lane quarter
@@ -341,27 +476,33 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         const bool timing_e = (p.flags & 16) != 0 && blockIdx.x == 0 && ew == 0 && lane == 0;
         long long te_wait = 0, te_drain = 0, te_store = 0, te_begin = clock64();
         int te_chains = 0;
+        uint32_t kbm_next = (int)blockIdx.x < num_tiles ? tile_kbm(blockIdx.x) : 0u;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const uint32_t kbm = kbm_next;
+            if (tile + (int)gridDim.x < num_tiles) kbm_next = tile_kbm(tile + gridDim.x);
+            // output row of this lane's accumulator row (TMEM lane ew*32 + lane)
+            const int pos = tile * BLOCK_M + ew * 32 + lane;
+            int my_row = -1;
+            if (pos < n_out) my_row = p.perm ? __ldg(&p.perm[pos]) : pos;
             float sum[N];
 #pragma unroll
             for (int j = 0; j < N; ++j) sum[j] = 0.f;
-            for (int g = 0; g < num_chains; ++g) {
+            for (int c = 0; c < num_chains; ++c) {
+                if (!(kbm & (CHAIN_BITS << (c * CHAIN_KB)))) continue;       // no K block of this chain was issued
                 const long long e0 = timing_e ? clock64() : 0;
-                mbar_wait(&bar_tfull[acc], acc_phase);
+                mbar_wait_warp(&bar_tfull[acc], acc_phase, poll1);
                 tc_fence_after();
                 const long long e1 = timing_e ? clock64() : 0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * ACC_W);
 #pragma unroll
                 for (int c0 = 0; c0 < N; c0 += 16) {
-                    uint32_t rr[16];
-                    tmem_ld16(taddr + c0, rr);            // A_hi*W_hi + A_lo*W_hi
+                    uint32_t ra[16], rb[16];
+                    tmem_ld16(taddr + c0, ra);            // A_hi*W_hi + A_lo*W_hi
+                    tmem_ld16(taddr + N + c0, rb);        // A_hi*W_lo
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
-                    tmem_ld16(taddr + N + c0, rr);        // A_hi*W_lo
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[c0 + j] = __fadd_rn(sum[c0 + j], __uint_as_float(rr[j]));
+                    for (int j = 0; j < 16; ++j)
+                        sum[c0 + j] = __fadd_rn(__fadd_rn(sum[c0 + j], __uint_as_float(ra[j])), __uint_as_float(rb[j]));
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -376,7 +517,6 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             // lanes of a row group write the hi segment, the next CP lanes the lo segment.
             constexpr int CW = N < 32 ? N : 32;                // channels per pass
             uint32_t *stg = s_stage[ew];
-            const int row_w0 = tile * BLOCK_M + ew * 32;       // first row of this warp
             bool range_bad = false;
             if (p.out_lo) {
                 constexpr int WP = CW / 2;                     // words per plane and row
@@ -408,8 +548,8 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     __syncwarp();
 #pragma unroll
                     for (int it = 0; it < 32 / RPI; ++it) {
-                        const int rr = row_w0 + it * RPI + sp;
-                        if (rr < n_out)
+                        const int rr = __shfl_sync(0xffffffffu, my_row, it * RPI + sp);
+                        if (rr >= 0)
                             *reinterpret_cast<uint4 *>(outp + (size_t)rr * p.out_stride + cc + coff) =
                                 *reinterpret_cast<const uint4 *>(stg + (it * RPI + sp) * 36 + (sq < CP ? 0 : 16) + (sq % CP) * 4);
                     }
@@ -436,8 +576,8 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                     __syncwarp();
 #pragma unroll
                     for (int it = 0; it < 32 / RPI; ++it) {
-                        const int rr = row_w0 + it * RPI + sp;
-                        if (rr < n_out)
+                        const int rr = __shfl_sync(0xffffffffu, my_row, it * RPI + sp);
+                        if (rr >= 0)
                             *reinterpret_cast<uint4 *>(outp + (size_t)rr * N + cc + sq * 4) =
                                 *reinterpret_cast<const uint4 *>(stg + (it * RPI + sp) * 36 + sq * 4);
                     }
@@ -453,23 +593,40 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+#ifdef B2S_DIAG
+    if ((p.flags & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long t0 = g_trace[2][0];
+        printf("[trace<%d,%d>] g: W(empty seen, tma issued) I(6 mmas issued, full[g+1] seen, commit) G(at wait, empty seen, arrived)\n", CIN, COUT);
+        for (int g = 32; g < 96; ++g)
+            printf("[trace] %3d  W %7lld %7lld  I %7lld %7lld %7lld  G %7lld %7lld %7lld\n", g, g_trace[0][g] - t0, g_trace[1][g] - t0,
+                   g_trace[2][g] - t0, g_trace[3][g] - t0, g_trace[4][g] - t0, g_trace[5][g] - t0, g_trace[6][g] - t0, g_trace[7][g] - t0);
+    }
+#endif
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
     }
 }
 
-template <int CIN, int COUT, int STAGES>
-int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
+template <int CIN, int COUT, int OWN>
+int launch_own(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
     constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * ELEM_BYTES;
     size_t smem = stage * STAGES + 1024;
-    B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, STAGES>), smem);
+    B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, OWN>), smem);
     int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles_cap < num_sms ? tiles_cap : num_sms;
-    k_sparse_conv_tc<CIN, COUT, STAGES><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
+    k_sparse_conv_tc<CIN, COUT, OWN><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
     B2S_LAUNCH_OK();
     return 0;
+}
+template <int CIN, int COUT>
+int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
+{
+    static int own = -1;      // B2S_SP_OWN = 1 | 4 (A/B switch of the gather ownership)
+    if (own < 0) { const char *e = getenv("B2S_SP_OWN"); own = (e && atoi(e) == 1) ? 1 : 4; }
+    return own == 4 ? launch_own<CIN, COUT, 4>(w_hi, w_lo, p, num_sms, stream)
+                    : launch_own<CIN, COUT, 1>(w_hi, w_lo, p, num_sms, stream);
 }
 
 }  // namespace
@@ -481,11 +638,11 @@ extern "C" int b2s_sparse_conv_tc_supported(int cin, int cout)
 
 // Weight layout: Cin = 64: [K][Cout][64]; Cin < 64 (8, 16, 32): packed [ceil(K / (64/Cin))][Cout][64] with column
 // (offset-in-pack * Cin + cin) and zero columns for offsets >= K (b2second/tc.py: pack_sparse_weights).
-extern "C" int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,
-                                  const b2s_half *w_hi, const b2s_half *w_lo, const int *nbr, int K,
-                                  const int *num_out_dev, int cap_out, const float *scale, const float *shift, int relu,
-                                  void *out_hi, b2s_half *out_lo, int out_stride, int cout, unsigned *status_dev,
-                                  void *stream_)
+extern "C" int b2s_sparse_conv_tc_plan(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,
+                                       const b2s_half *w_hi, const b2s_half *w_lo, const int *nbr, int K,
+                                       const int *num_out_dev, int cap_out, const int *perm, const unsigned *tile_mask,
+                                       const float *scale, const float *shift, int relu, void *out_hi, b2s_half *out_lo,
+                                       int out_stride, int cout, unsigned *status_dev, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE(b2s_sparse_conv_tc_supported(cin, cout),
@@ -496,16 +653,16 @@ extern "C" int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_
     B2S_REQUIRE(out_lo == nullptr || (out_stride >= cout && out_stride % 8 == 0 && ((uintptr_t)out_hi & 15) == 0 &&
                                       ((uintptr_t)out_lo & 15) == 0),
                 "b2s_sparse_conv_tc: output rows must be 16-byte aligned (out_stride multiple of 8 halves)");
+    B2S_REQUIRE((unsigned long long)rows_in * (unsigned long long)in_stride * ELEM_BYTES < (1ull << 32),
+                "b2s_sparse_conv_tc: feature planes of 4 GiB or more are not supported (32-bit row offsets)");
     if (cap_out == 0) return 0;
     const int num_sms = num_sms_current();
     CUtensorMap m_hi, m_lo;
     {
-        const bool packed = cin < BLOCK_K;
-        const int pack = packed ? BLOCK_K / cin : 1;
-        cuuint64_t row = packed ? BLOCK_K : (cuuint64_t)cin;     // halves per weight row
-        cuuint64_t nkb = packed ? (cuuint64_t)((K + pack - 1) / pack) : (cuuint64_t)K;
-        cuuint64_t dims[3] = {row, (cuuint64_t)cout, nkb};
-        cuuint64_t str[2] = {row * ELEM_BYTES, (cuuint64_t)cout * row * ELEM_BYTES};
+        const int pack = BLOCK_K / cin;
+        cuuint64_t nkb = (cuuint64_t)((K + pack - 1) / pack);
+        cuuint64_t dims[3] = {BLOCK_K, (cuuint64_t)cout, nkb};
+        cuuint64_t str[2] = {BLOCK_K * ELEM_BYTES, (cuuint64_t)cout * BLOCK_K * ELEM_BYTES};
         cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)cout, 1};
         if (make_map(&m_hi, w_hi, 3, dims, str, box) || make_map(&m_lo, w_lo, 3, dims, str, box)) return -1;
     }
@@ -513,20 +670,32 @@ extern "C" int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_
     p.in_hi = reinterpret_cast<const __half *>(feat_hi); p.in_lo = reinterpret_cast<const __half *>(feat_lo);
     p.in_stride = in_stride; p.out_stride = out_stride; p.status = (int *)status_dev;
     p.nbr = nbr; p.n_out_dev = num_out_dev; p.cap_out = cap_out; p.K = K;
+    p.perm = perm; p.tile_mask = tile_mask;
     {
         static int fl = -1;
         if (fl < 0) { const char *e = getenv("B2S_SP_ZSKIP"); fl = e ? atoi(e) : 1; }
 #ifdef B2S_DIAG
-        p.flags = fl;           // bits 2/4/8 corrupt results: only in `make DIAG=1` builds
+        p.flags = fl;           // make DIAG=1: bit 2 no gather copies, 4 no weight loads, 8 no zero fills (results wrong)
 #else
-        p.flags = fl & (1 | 16);
+        p.flags = fl & (1 | 16 | 32);
 #endif
     }
     p.relu = relu; p.scale = scale; p.shift = shift; p.out_hi = out_hi; p.out_lo = reinterpret_cast<__half *>(out_lo);
-#define B2S_TC_CASE(CI, CO) if (cin == CI && cout == CO) return launch<CI, CO, 4>(m_hi, m_lo, p, num_sms, stream);
+#define B2S_TC_CASE(CI, CO) if (cin == CI && cout == CO) return launch<CI, CO>(m_hi, m_lo, p, num_sms, stream);
     B2S_TC_CASE(64, 64) B2S_TC_CASE(64, 32) B2S_TC_CASE(64, 16) B2S_TC_CASE(32, 64) B2S_TC_CASE(32, 32) B2S_TC_CASE(32, 16)
     B2S_TC_CASE(16, 64) B2S_TC_CASE(16, 32) B2S_TC_CASE(16, 16) B2S_TC_CASE(8, 64) B2S_TC_CASE(8, 32) B2S_TC_CASE(8, 16)
 #undef B2S_TC_CASE
     b2s_set_error("b2s_sparse_conv_tc: Cin=%d Cout=%d not built", cin, cout);
     return -2;
+}
+
+extern "C" int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,
+                                  const b2s_half *w_hi, const b2s_half *w_lo, const int *nbr, int K,
+                                  const int *num_out_dev, int cap_out, const float *scale, const float *shift, int relu,
+                                  void *out_hi, b2s_half *out_lo, int out_stride, int cout, unsigned *status_dev,
+                                  void *stream_)
+{
+    return b2s_sparse_conv_tc_plan(feat_hi, feat_lo, in_stride, rows_in, cin, w_hi, w_lo, nbr, K, num_out_dev, cap_out,
+                                   nullptr, nullptr, scale, shift, relu, out_hi, out_lo, out_stride, cout, status_dev,
+                                   stream_);
 }

@@ -52,6 +52,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef B2S_MBAR_SUSPEND_HINT
+#define B2S_MBAR_SUSPEND_HINT 0x989680u
+#endif
 // bounded wait: ~seconds of spinning, then trap (a protocol bug must not hang the device)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -61,11 +64,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 28); ++it) {
         uint32_t done;
+        // suspend-time hint (as CUTLASS's ClusterBarrier::wait passes): without it the default time limit is short and
+        // every waiting thread re-polls the barrier unit in a tight loop
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(B2S_MBAR_SUSPEND_HINT) : "memory");
         if (done) return;
     }
     __trap();

@@ -138,3 +138,109 @@ def test_drop_in_sparse_sequential_runs_on_tensor_cores(product, oracle):
         net(product.SparseConvTensor(feats.cuda(), idx.cuda(), shape, batch))
     with torch.no_grad():                                          # nothing to record: allowed
         net(product.SparseConvTensor(feats.cuda(), idx.cuda(), shape, batch))
+
+
+def _clustered_sparse(rng, shape, batch, n, cin):
+    """surface-like occupancy (a noisy sheet per frame) so that rows have structured, differing neighbourhoods."""
+    D, H, W = shape
+    pts = set()
+    while len(pts) < n:
+        b = int(rng.integers(batch)); y = int(rng.integers(H)); x = int(rng.integers(W))
+        z = int(np.clip(round(D / 2 + 2 * np.sin(x / 5.0) + rng.normal(0, 0.7)), 0, D - 1))
+        pts.add((b, z, y, x))
+    idx = np.array(sorted(pts), dtype=np.int32)
+    feats = rng.standard_normal((idx.shape[0], cin)).astype(np.float32)
+    return torch.from_numpy(feats), torch.from_numpy(idx)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("cin,cout", [(64, 64), (32, 32), (16, 32), (4, 16)])
+@pytest.mark.parametrize("subm", [True, False])
+@pytest.mark.parametrize("n", [20000, 300, 1])
+def test_tile_plan_properties_and_bit_identity(product, cin, cout, subm, n):
+    """b2s_sparse_tile_plan: perm is a permutation that only moves rows inside 8192-row chunks, tile_mask is exactly the
+    OR of the tile's row masks (sorted and unsorted); b2s_sparse_conv_tc_plan gives BIT-IDENTICAL rows with no plan, with
+    masks only and with grouped rows (fixed chain boundaries + exact zeros for missing neighbours)."""
+    from b2second import tc
+    L = product._lib
+    lib = L.load()
+    rng = np.random.default_rng(cin + cout + subm + n)
+    shape, batch = (9, 48, 40), 3
+    feats, idx = _clustered_sparse(rng, shape, batch, n, cin)
+    x = product.SparseConvTensor(feats.cuda(), idx.cuda(), shape, batch)
+    k = [3, 3, 3]
+    s, p = ([1, 1, 1], [1, 1, 1]) if subm else ([2, 2, 2], [1, 1, 1])
+    rb = product.ops.build_rulebook(x, k, s, p, [1, 1, 1], subm)
+    n_out = rb.num_out
+    assert n_out > 0
+    nbr = rb.nbr.contiguous()
+    ksz = L.i3(k)
+    cap = n_out + 77                                  # capacity above the live row count
+    nbr_cap = torch.full((cap, 27), -1, dtype=torch.int32, device="cuda"); nbr_cap[:n_out] = nbr[:n_out]
+    ntiles = (cap + 127) // 128
+    row_mask = ((nbr_cap[:n_out] >= 0).long() << torch.arange(27, device="cuda")).sum(1)        # [n_out]
+    plans = {}
+    for sort in (0, 1):
+        perm = torch.full((cap,), -7, dtype=torch.int32, device="cuda")
+        tmask = torch.full((ntiles,), -1, dtype=torch.int32, device="cuda")
+        L.check(lib.b2s_sparse_tile_plan(L.ptr(nbr_cap), 27, ksz, L.ptr(rb.num_out_dev), cap, sort, L.ptr(perm),
+                                         L.ptr(tmask), L.stream()), "b2s_sparse_tile_plan")
+        torch.cuda.synchronize()
+        order = perm[:n_out].long() if sort else torch.arange(n_out, device="cuda")
+        if sort:
+            assert torch.equal(torch.sort(order).values, torch.arange(n_out, device="cuda"))       # a permutation
+            assert torch.equal(order // 8192, torch.arange(n_out, device="cuda") // 8192)           # chunk-local
+            assert bool((perm[n_out:] == -7).all())                                                 # nothing past the rows
+        else:
+            assert bool((perm == -7).all())
+        live_tiles = (n_out + 127) // 128
+        pad = torch.zeros(live_tiles * 128, dtype=torch.long, device="cuda"); pad[:n_out] = row_mask[order]
+        want = pad.view(live_tiles, 128)
+        acc = want[:, 0].clone()
+        for j in range(1, 128):
+            acc |= want[:, j]
+        assert torch.equal(tmask[:live_tiles].long() & 0x7FFFFFF, acc), "tile masks (sort=%d)" % sort
+        plans[sort] = (perm if sort else None, tmask)
+    if n >= 20000 and subm:
+        # grouping must pay: fewer (tile, offset) blocks than storage order
+        def blocks(t):
+            return int(sum(bin(int(v) & 0x7FFFFFF).count("1") for v in t[:(n_out + 127) // 128].tolist()))
+        assert blocks(plans[1][1]) <= blocks(plans[0][1])
+    # ---- convolution: identical bits with every plan ----
+    w = (torch.randn(27, cin, cout) * 0.1).cuda()
+    cin_tc = tc.sparse_tc_cin(cin)
+    wp = tc.pack_sparse_weights(w)
+    ws = tc.pow2_scale(wp)
+    w_hi, w_lo = tc.split_f16(wp, ws)
+    n_in = feats.shape[0]
+    fbuf = torch.zeros(n_in, 2, cin_tc, dtype=torch.float16, device="cuda")
+    f_hi, f_lo, fstride = fbuf[:, 0], fbuf[:, 1], 2 * cin_tc
+    feats_d = feats.cuda()
+    n_in_dev = torch.tensor([n_in], dtype=torch.int32, device="cuda")
+    L.check(lib.b2s_split_f16(L.ptr(feats_d), L.ptr(f_hi), L.ptr(f_lo), L.ptr(n_in_dev), n_in, cin, cin_tc, fstride,
+                              L.stream()), "b2s_split_f16")
+    scale_d = (torch.rand(cout) + 0.5).cuda() / ws
+    shift_d = (torch.randn(cout) * 0.1).cuda()
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    outs = []
+    for perm, tmask in [(None, None), (None, plans[0][1]), plans[1]]:
+        obuf = torch.full((cap, 2, cout), 7.0, dtype=torch.float16, device="cuda")
+        L.check(lib.b2s_sparse_conv_tc_plan(L.ptr(f_hi), L.ptr(f_lo), fstride, n_in, cin_tc, L.ptr(w_hi), L.ptr(w_lo),
+                                            L.ptr(nbr_cap), 27, L.ptr(rb.num_out_dev), cap, L.ptr(perm), L.ptr(tmask),
+                                            L.ptr(scale_d), L.ptr(shift_d), 1, L.ptr(obuf[:, 0]), L.ptr(obuf[:, 1]),
+                                            2 * cout, cout, L.ptr(status), L.stream()), "b2s_sparse_conv_tc_plan")
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        assert bool((obuf[n_out:] == 7.0).all())          # rows past the live count untouched
+        outs.append(obuf[:n_out].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    # and they are the right values
+    ref = torch.zeros(n_out, cout, device="cuda", dtype=torch.float64)
+    fd = feats_d.double()
+    for kk in range(27):
+        src = nbr_cap[:n_out, kk].long()
+        ok = src >= 0
+        ref[ok] += fd[src[ok]] @ w[kk].double()
+    ref = torch.relu(ref * (scale_d * ws).double() + shift_d.double())
+    got = outs[0][:, 0].double() + outs[0][:, 1].double()
+    assert float((got - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
