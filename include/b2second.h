@@ -127,11 +127,13 @@ int b2s_hash_build(const int *coors, const int *num_rows_dev, int cap_rows, cons
                    void *stream);
 
 /* submanifold conv rulebook: nbr[row][k] = input row at coor + (k - k//2)*dil, or -1.
- * k index row-major over (kz,ky,kx); K = kz*ky*kx. */
+ * k index row-major over (kz,ky,kx); K = kz*ky*kx.
+ * row_mask (optional, all three rulebook builders): [rows] bit k = nbr[row][k] exists -- what b2s_sparse_tile_plan needs,
+ * written while the table is built so that the plan does not have to read the table again. */
 int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape,
                       const int *ksize /*host[3]*/, const int *dilation /*host[3]*/,
                       const unsigned long long *hash_keys, const int *hash_vals, int hash_cap,
-                      int *nbr /*[cap_rows,K]*/, void *stream);
+                      int *nbr /*[cap_rows,K]*/, unsigned *row_mask /*[cap_rows] or NULL*/, void *stream);
 
 size_t b2s_rulebook_conv_workspace_bytes(int batch, const int *out_shape /*host[3]*/);
 /* strided ("regular") sparse conv rulebook.  Output rows are emitted sorted ascending by flat
@@ -143,7 +145,8 @@ int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int cap_in, in
                       const int *hash_vals_in, int hash_cap_in, int *coors_out /*[cap_out,4]*/,
                       int *num_out_dev, int cap_out, int *nbr /*[cap_out,K]*/,
                       unsigned long long *hash_keys_out, int *hash_vals_out, int hash_cap_out,
-                      void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream);
+                      void *workspace, size_t workspace_bytes, unsigned *row_mask /*[cap_out] or NULL*/,
+                      unsigned *status_dev, void *stream);
 
 /* SubM rulebook of the level b2s_rulebook_conv has JUST produced, read off the occupancy structure that call left in
  * `workspace` (same batch / shape, nothing else run on the workspace in between): coordinate -> row is a bit test +
@@ -151,7 +154,7 @@ int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int cap_in, in
  * the produced level is built this way.  nbr as b2s_rulebook_subm. */
 int b2s_rulebook_subm_ranked(const int *coors, const int *num_rows_dev, int cap_rows, int batch, const int *shape,
                              const int *ksize, const int *dilation, const void *workspace, size_t workspace_bytes,
-                             int *nbr, void *stream);
+                             int *nbr, unsigned *row_mask /*[cap_rows] or NULL*/, void *stream);
 
 /* pair-list view of a neighbour table (spconv's indice_pairs [K,2,L] + indice_pair_num [K]) --
  * only for parity checks / API completeness; the conv kernels consume `nbr` directly. */
@@ -191,8 +194,9 @@ int b2s_sparse_conv_tc(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_
  *                 the planes) inside chunks of 8192 rows, stable -- roughly halves the (tile, offset) blocks of
  *                 SECOND's middle encoder; sort = 0: tiles in storage order, perm untouched (may be NULL).
  * The convolution result does not depend on the plan (bit-identical with and without). */
-int b2s_sparse_tile_plan(const int *nbr, int K, const int *ksize /*[3] or NULL*/, const int *num_out_dev, int cap_out,
-                         int sort, int *perm /*[cap_out]*/, unsigned *tile_mask /*[ceil(cap_out/128)]*/, void *stream);
+int b2s_sparse_tile_plan(const int *nbr, const unsigned *row_mask /*from the rulebook builder, or NULL: read nbr*/, int K,
+                         const int *ksize /*[3] or NULL*/, const int *num_out_dev, int cap_out, int sort,
+                         int *perm /*[cap_out]*/, unsigned *tile_mask /*[ceil(cap_out/128)]*/, void *stream);
 /* b2s_sparse_conv_tc with a tile plan: perm / tile_mask from b2s_sparse_tile_plan (either may be NULL: identity order /
  * every offset). */
 int b2s_sparse_conv_tc_plan(const b2s_half *feat_hi, const b2s_half *feat_lo, int in_stride, int rows_in, int cin,

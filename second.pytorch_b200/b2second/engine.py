@@ -137,7 +137,7 @@ class InferenceEngine:
         rulebooks = {}
         max_ws = 0
         thin_ok = os.environ.get("B2S_THIN_TC", "1") != "0"      # A/B switch: thin layers on the FMA core
-        plan_mode = int(os.environ.get("B2S_SP_PLAN", "3"))
+        plan_mode = int(os.environ.get("B2S_SP_PLAN", "4"))
         for j, ls in enumerate(s.layers):
             K = ls["K"]
             lyr = dict(ls)
@@ -174,12 +174,14 @@ class InferenceEngine:
                 level = new
             # tile plan of the rulebook (csrc/sparse_plan.cu): which kernel offsets each 128-row tile needs, and an order
             # of the rows that makes that set small.  B2S_SP_PLAN: 0 off, 1 masks only, 2 rows grouped for SubM
-            # rulebooks (shared by 2-3 layers), 3 (default) rows grouped for every 27-offset rulebook
+            # rulebooks (shared by 2-3 layers) + masks for the strided ones, 3 rows grouped for every 27-offset rulebook,
+            # 4 (default) SubM rulebooks only (a strided conv uses its table once: the plan costs more than it saves)
             rb = lyr["rb"]
-            if "tile_mask" not in rb and plan_mode > 0:
+            if "tile_mask" not in rb and plan_mode > 0 and (plan_mode != 4 or ls["subm"]):
                 cap_rb = lyr["out_level"].cap
                 rb["tile_mask"] = torch.zeros((cap_rb + 127) // 128, dtype=torch.int32, device=dev)
-                rb["sort"] = bool(K > 3 and (plan_mode >= 3 or (plan_mode == 2 and ls["subm"])))
+                rb["row_mask"] = torch.zeros(cap_rb, dtype=torch.int32, device=dev)    # written by the rulebook builder
+                rb["sort"] = bool(K > 3 and (plan_mode == 3 or (plan_mode in (2, 4) and ls["subm"])))
                 rb["perm"] = torch.zeros(cap_rb, dtype=torch.int32, device=dev) if rb["sort"] else None
             # tensor-pipe core (csrc/sparse_conv_tc.cu): the library says which (Cin, Cout) it was built for;
             # 3-/4-feature input layers are zero-padded to 8 channels.  Everything else: fp32 FMA core.
@@ -459,12 +461,12 @@ class InferenceEngine:
                         L.check(lib.b2s_rulebook_subm_ranked(
                             L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, self.B, L.i3(lin.shape),
                             L.i3(lyr["kernel_size"]), L.i3(lyr["dilation"]), L.ptr(self.rb_ws), self.rb_ws_bytes,
-                            L.ptr(lyr["rb"]["nbr"]), st), "b2s_rulebook_subm_ranked")
+                            L.ptr(lyr["rb"]["nbr"]), L.ptr(lyr["rb"].get("row_mask")), st), "b2s_rulebook_subm_ranked")
                     elif lyr["subm"]:
                         L.check(lib.b2s_rulebook_subm(L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, L.i3(lin.shape),
                                                       L.i3(lyr["kernel_size"]), L.i3(lyr["dilation"]), L.ptr(lin.keys),
-                                                      L.ptr(lin.vals), lin.hcap, L.ptr(lyr["rb"]["nbr"]), st),
-                                "b2s_rulebook_subm")
+                                                      L.ptr(lin.vals), lin.hcap, L.ptr(lyr["rb"]["nbr"]),
+                                                      L.ptr(lyr["rb"].get("row_mask")), st), "b2s_rulebook_subm")
                     else:
                         L.check(lib.b2s_rulebook_conv(
                             L.ptr(lin.coors), L.ptr(lin.n_dev), lin.cap, self.B, L.i3(lin.shape), L.i3(lout.shape),
@@ -472,11 +474,12 @@ class InferenceEngine:
                             L.ptr(lin.keys), L.ptr(lin.vals), lin.hcap, L.ptr(lout.coors), L.ptr(lout.n_dev), lout.cap,
                             L.ptr(lyr["rb"]["nbr"]), L.ptr(lout.keys) if lyr["want_hash"] else None,
                             L.ptr(lout.vals) if lyr["want_hash"] else None, lout.hcap,
-                            L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(self.status), st), "b2s_rulebook_conv")
+                            L.ptr(self.rb_ws), self.rb_ws_bytes, L.ptr(lyr["rb"].get("row_mask")), L.ptr(self.status), st),
+                            "b2s_rulebook_conv")
                     if lyr["tc"] and "tile_mask" in lyr["rb"]:
                         rb = lyr["rb"]
                         L.check(lib.b2s_sparse_tile_plan(
-                            L.ptr(rb["nbr"]), lyr["K"], L.i3(lyr["kernel_size"]), L.ptr(lout.n_dev), lout.cap,
+                            L.ptr(rb["nbr"]), L.ptr(rb["row_mask"]), lyr["K"], L.i3(lyr["kernel_size"]), L.ptr(lout.n_dev), lout.cap,
                             1 if rb["sort"] else 0, L.ptr(rb["perm"]), L.ptr(rb["tile_mask"]), st),
                             "b2s_sparse_tile_plan")
                 self._mark("sparse_conv%d" % lyr["index"])

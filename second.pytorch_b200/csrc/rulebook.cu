@@ -61,7 +61,7 @@ __global__ void k_hash_build(const int *__restrict__ coors, const int *__restric
 // with -1 by the caller.  One thread per (row, k < K/2).
 __global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows,
                            ConvGeom g, const unsigned long long *__restrict__ keys,
-                           const int *__restrict__ vals, int mask, int *nbr)
+                           const int *__restrict__ vals, int mask, int *nbr, unsigned *row_mask)
 {
     const int n = min(*n_dev, cap_rows);
     const int half = g.K / 2;            // offsets 0..half-1 are looked up, `half` is the centre
@@ -69,7 +69,11 @@ __global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict_
     for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
          gid += (long long)gridDim.x * blockDim.x) {
         int row = (int)(gid / (half + 1)), k = (int)(gid % (half + 1));
-        if (k == half) { nbr[(size_t)row * g.K + half] = row; continue; }
+        if (k == half) {
+            nbr[(size_t)row * g.K + half] = row;
+            if (row_mask) atomicOr(&row_mask[row], 1u << half);
+            continue;
+        }
         int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
         int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
         int z = c.y + (kz - g.k[0] / 2) * g.d[0];
@@ -81,6 +85,10 @@ __global__ void k_subm_nbr(const int *__restrict__ coors, const int *__restrict_
         if (j >= 0 && j < n) {
             nbr[(size_t)row * g.K + k] = j;
             nbr[(size_t)j * g.K + (g.K - 1 - k)] = row;
+            if (row_mask) {                      // which offsets each row has (input of b2s_sparse_tile_plan)
+                atomicOr(&row_mask[row], 1u << k);
+                atomicOr(&row_mask[j], 1u << (g.K - 1 - k));
+            }
         }
     }
 }
@@ -247,7 +255,7 @@ __global__ void k_conv_emit(const unsigned *__restrict__ bitmap, const int *__re
 // one thread per (output row, k): neighbour lookup in the input hash
 __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restrict__ n_out_dev, int cap_out,
                            ConvGeom g, const unsigned long long *__restrict__ keys_in,
-                           const int *__restrict__ vals_in, int mask_in, int *nbr)
+                           const int *__restrict__ vals_in, int mask_in, int *nbr, unsigned *row_mask)
 {
     const int n = min(*n_out_dev, cap_out);
     const long long total = (long long)n * g.K;
@@ -269,6 +277,7 @@ __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restr
             r = b2s_hash_find(keys_in, vals_in, mask_in,
                               b2s_flat_key(c.x, ic[0], ic[1], ic[2], g.in_shape[0], g.in_shape[1], g.in_shape[2]));
         nbr[gid] = r;
+        if (row_mask && r >= 0) atomicOr(&row_mask[row], 1u << k);
     }
 }
 
@@ -279,7 +288,7 @@ __global__ void k_conv_nbr(const int *__restrict__ coors_out, const int *__restr
 // level's 14 us mark pass, ncu launch list round 1); nbr is pre-filled with -1 by the caller.
 __global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *__restrict__ n_in_dev, int cap_in,
                                    ConvGeom g, const unsigned *__restrict__ bitmap,
-                                   const int *__restrict__ wrow0, int cap_out, int *nbr)
+                                   const int *__restrict__ wrow0, int cap_out, int *nbr, unsigned *row_mask)
 {
     const int n = min(*n_in_dev, cap_in);
     for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
@@ -308,7 +317,10 @@ __global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *
                     const unsigned bit = (unsigned)(key & 31);
                     const int row_out = wrow0[w] + __popc(bitmap[w] & ((1u << bit) - 1u));
                     const int k = (okk[0][a] * g.k[1] + okk[1][b]) * g.k[2] + okk[2][e];
-                    if (row_out < cap_out) nbr[(size_t)row_out * g.K + k] = row;
+                    if (row_out < cap_out) {
+                        nbr[(size_t)row_out * g.K + k] = row;
+                        if (row_mask) atomicOr(&row_mask[row_out], 1u << k);
+                    }
                 }
     }
 }
@@ -317,7 +329,8 @@ __global__ void k_conv_scatter_nbr(const int *__restrict__ coors_in, const int *
 // is still in the workspace: coordinate -> row is a bit test + rank, no hash probing.  Symmetric like k_subm_nbr: one
 // thread per (row, k < K/2) writes both directions.
 __global__ void k_subm_ranked(const int *__restrict__ coors, const int *__restrict__ n_dev, int cap_rows, ConvGeom g,
-                              const unsigned *__restrict__ bitmap, const int *__restrict__ wrow0, int *nbr)
+                              const unsigned *__restrict__ bitmap, const int *__restrict__ wrow0, int *nbr,
+                              unsigned *row_mask)
 {
     const int n = min(*n_dev, cap_rows);
     const int half = g.K / 2;
@@ -325,7 +338,11 @@ __global__ void k_subm_ranked(const int *__restrict__ coors, const int *__restri
     for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < total;
          gid += (long long)gridDim.x * blockDim.x) {
         int row = (int)(gid / (half + 1)), k = (int)(gid % (half + 1));
-        if (k == half) { nbr[(size_t)row * g.K + half] = row; continue; }
+        if (k == half) {
+            nbr[(size_t)row * g.K + half] = row;
+            if (row_mask) atomicOr(&row_mask[row], 1u << half);
+            continue;
+        }
         int kx = k % g.k[2], ky = (k / g.k[2]) % g.k[1], kz = k / (g.k[2] * g.k[1]);
         int4 c = *reinterpret_cast<const int4 *>(coors + (size_t)row * 4);
         int z = c.y + (kz - g.k[0] / 2) * g.d[0];
@@ -340,6 +357,10 @@ __global__ void k_subm_ranked(const int *__restrict__ coors, const int *__restri
         if (j < n) {
             nbr[(size_t)row * g.K + k] = j;
             nbr[(size_t)j * g.K + (g.K - 1 - k)] = row;
+            if (row_mask) {
+                atomicOr(&row_mask[row], 1u << k);
+                atomicOr(&row_mask[j], 1u << (g.K - 1 - k));
+            }
         }
     }
 }
@@ -433,7 +454,7 @@ extern "C" int b2s_hash_build(const int *coors, const int *num_rows_dev, int cap
 
 extern "C" int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int cap_rows, const int *shape,
                                  const int *ksize, const int *dilation, const unsigned long long *hash_keys,
-                                 const int *hash_vals, int hash_cap, int *nbr, void *stream_)
+                                 const int *hash_vals, int hash_cap, int *nbr, unsigned *row_mask, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
@@ -442,8 +463,9 @@ extern "C" int b2s_rulebook_subm(const int *coors, const int *num_rows_dev, int 
     B2S_REQUIRE((g.k[0] & 1) && (g.k[1] & 1) && (g.k[2] & 1), "b2s_rulebook_subm: kernel sizes must be odd");
     if (cap_rows > 0) {
         B2S_CUDA_OK(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)cap_rows * g.K, stream));
+        if (row_mask) B2S_CUDA_OK(cudaMemsetAsync(row_mask, 0, sizeof(unsigned) * (size_t)cap_rows, stream));
         k_subm_nbr<<<bounded_grid((long long)cap_rows * (g.K / 2 + 1), kThreads), kThreads, 0, stream>>>(
-            coors, num_rows_dev, cap_rows, g, hash_keys, hash_vals, hash_cap - 1, nbr);
+            coors, num_rows_dev, cap_rows, g, hash_keys, hash_vals, hash_cap - 1, nbr, row_mask);
         B2S_LAUNCH_OK();
     }
     return 0;
@@ -460,7 +482,8 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
                                  const unsigned long long *hash_keys_in, const int *hash_vals_in,
                                  int hash_cap_in, int *coors_out, int *num_out_dev, int cap_out, int *nbr,
                                  unsigned long long *hash_keys_out, int *hash_vals_out, int hash_cap_out,
-                                 void *workspace, size_t workspace_bytes, unsigned *status_dev, void *stream_)
+                                 void *workspace, size_t workspace_bytes, unsigned *row_mask, unsigned *status_dev,
+                                 void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
@@ -484,6 +507,7 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
     size_t need = carve(&w, (char *)workspace, batch, out_shape);
     B2S_REQUIRE(workspace_bytes >= need, "b2s_rulebook_conv: workspace too small (%zu < %zu)", workspace_bytes, need);
     B2S_CUDA_OK(cudaMemsetAsync(w.bitmap, 0, sizeof(unsigned) * (size_t)(w.nwords + w.nsw), stream));
+    if (row_mask && cap_out > 0) B2S_CUDA_OK(cudaMemsetAsync(row_mask, 0, sizeof(unsigned) * (size_t)cap_out, stream));
     if (want_hash) {
         B2S_CUDA_OK(cudaMemsetAsync(hash_keys_out, 0xFF, sizeof(unsigned long long) * (size_t)hash_cap_out, stream));
         B2S_CUDA_OK(cudaMemsetAsync(hash_vals_out, 0xFF, sizeof(int) * (size_t)hash_cap_out, stream));
@@ -520,10 +544,10 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
         }
         if (use_scatter && cap_in > 0) {
             k_conv_scatter_nbr<<<bounded_grid(cap_in, kThreads), kThreads, 0, stream>>>(
-                coors_in, num_in_dev, cap_in, g, w.bitmap, w.wrow0, cap_out, nbr);
+                coors_in, num_in_dev, cap_in, g, w.bitmap, w.wrow0, cap_out, nbr, row_mask);
         } else {
             k_conv_nbr<<<bounded_grid((long long)cap_out * g.K, kThreads), kThreads, 0, stream>>>(
-                coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr);
+                coors_out, num_out_dev, cap_out, g, hash_keys_in, hash_vals_in, hash_cap_in - 1, nbr, row_mask);
         }
         B2S_LAUNCH_OK();
     }
@@ -534,7 +558,7 @@ extern "C" int b2s_rulebook_conv(const int *coors_in, const int *num_in_dev, int
 // occupancy bitmap + per-word first rows are still there, so no hash table is needed for the level.
 extern "C" int b2s_rulebook_subm_ranked(const int *coors, const int *num_rows_dev, int cap_rows, int batch,
                                         const int *shape, const int *ksize, const int *dilation, const void *workspace,
-                                        size_t workspace_bytes, int *nbr, void *stream_)
+                                        size_t workspace_bytes, int *nbr, unsigned *row_mask, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
@@ -546,8 +570,9 @@ extern "C" int b2s_rulebook_subm_ranked(const int *coors, const int *num_rows_de
     B2S_REQUIRE(workspace_bytes >= need, "b2s_rulebook_subm_ranked: workspace too small (%zu < %zu)", workspace_bytes, need);
     if (cap_rows > 0) {
         B2S_CUDA_OK(cudaMemsetAsync(nbr, 0xFF, sizeof(int) * (size_t)cap_rows * g.K, stream));
+        if (row_mask) B2S_CUDA_OK(cudaMemsetAsync(row_mask, 0, sizeof(unsigned) * (size_t)cap_rows, stream));
         k_subm_ranked<<<bounded_grid((long long)cap_rows * (g.K / 2 + 1), kThreads), kThreads, 0, stream>>>(
-            coors, num_rows_dev, cap_rows, g, w.bitmap, w.wrow0, nbr);
+            coors, num_rows_dev, cap_rows, g, w.bitmap, w.wrow0, nbr, row_mask);
         B2S_LAUNCH_OK();
     }
     return 0;

@@ -18,7 +18,7 @@
 //
 // Warp roles (16 warps):
 //   warp 0      TMA producer for the weight tile of each K block (bulk tensor load, SWIZZLE_128B)
-//   warp 1      MMA issuer (one elected lane, software-pipelined)
+//   warp 1      MMA issuer (one elected lane; see the comment at the role)
 //   warp 2      TMEM allocator
 //   warps 4-11  gather producers.  Gather warp w OWNS pipeline stage w % 4 and the tile's row half w / 4: it handles
 //               every 4th K block, all 16-byte cp.async copies of its 64 rows (hi and lo planes) into the K-major
@@ -43,10 +43,11 @@ namespace {
 
 using namespace b2s_tc;
 constexpr int STAGES = 4;                 // pipeline stages; gather warp w owns stage w % STAGES
-constexpr int GW = 8;                     // gather warps (warps 4 .. 4+GW-1); epilogue = the 4 warps after them
+// GW gather warps (warps 4 .. 4+GW-1), the epilogue is the 4 warps after them.  GW = 16 (24 warps) needs the register
+// file rebalanced between the roles with setmaxnreg (inside each role's branch, where ptxas honours it): 768 threads
+// start with 80 registers each; the gather warps drop to 64 and the epilogue warps (64 running sums + staging) rise to 144.
 // gather ownership: OWN = 4: warp w owns every 4th K block (pairs of warps share a K block, 64 rows each);
 //                   OWN = 1: all 8 warps work on every K block (16 rows each)
-constexpr int kThreads = 32 * (4 + GW + 4);
 constexpr int GROUP = 3;                  // kernel offsets per accumulation chain (Cin = 64)
 constexpr int ACC_SLOTS = 4;
 
@@ -78,7 +79,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint64_t *bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity, bool lane0_only)
 {
     if (lane0_only) {
-        if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+        if ((threadIdx.x & 31) == 0) mbar_wait_sleep(bar, parity);
         __syncwarp();
     } else {
         mbar_wait(bar, parity);
@@ -92,6 +93,17 @@ __device__ long long g_trace[10][128];
 #else
 #define B2S_TRACE(ROLE, G) do { } while (0)
 #endif
+
+// read-only load the compiler may not move (volatile asm keeps its place among the other volatile asm statements: the
+// copies, the barrier operations).  The neighbour-table entries of the NEXT owned K block must be in flight while the
+// current one is waited for and copied; as plain __ldg the compiler scheduled them next to their first use, and a third
+// of the gather warps' samples were long-scoreboard stalls on them (ncu source counters, round 2).
+__device__ __forceinline__ int ld_nc_volatile(const int *ptr)
+{
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
+}
 
 struct SpParams {
     const __half *in_hi, *in_lo;
@@ -127,12 +139,13 @@ __device__ __forceinline__ uint32_t kb_mask_of(uint32_t offsets, int num_kb)
 }
 
 // CIN in {8, 16, 32, 64}; COUT (= UMMA N) in {16, 32, 64}
-template <int CIN, int COUT, int OWN>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int CIN, int COUT, int OWN, int GW>
+__global__ void __launch_bounds__(32 * (4 + GW + 4), 1)
 k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                  const SpParams p)
 {
     constexpr int N = COUT;
+    static_assert(GW == 8 || GW == 16, "thread layout");
     constexpr int HALVES = GW / OWN;          // gather warps sharing one K block (each takes BLOCK_M / HALVES rows)
     constexpr int RI = BLOCK_M / HALVES / 4;  // 4-row copy iterations per gather warp and K block
     static_assert(GW % OWN == 0 && RI * 4 * HALVES == BLOCK_M && (OWN & (OWN - 1)) == 0 && RI * STAGES <= 64, "gather warp layout");
@@ -164,7 +177,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     const int K = p.K;
     const int num_kb = (K + PACK - 1) / PACK;
     const int num_chains = (num_kb + CHAIN_KB - 1) / CHAIN_KB;
-    const bool poll1 = (p.flags & 32) == 0;                 // B2S_SP_ZSKIP bit 32: every lane polls (the round-1 behaviour)
+    const bool poll1 = (p.flags & 32) != 0;                 // B2S_SP_ZSKIP bit 32: lane 0 polls with a sleeping wait (measured 1-3 % slower)
     const uint32_t all_offsets = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
     auto tile_kbm = [&](int tile) -> uint32_t {
         return kb_mask_of<PACK>(p.tile_mask ? __ldg(&p.tile_mask[tile]) & all_offsets : all_offsets, num_kb);
@@ -219,93 +232,123 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        // Software-pipelined single-lane issue: the barriers of the NEXT K block (and, at a chain end, of the next
-        // accumulator) are waited for before the current K block's last two MMAs are issued, so the tensor queue
-        // does not drain between the short 8-MMA bursts.
+        // ONE thread feeds the tensor pipe, and everything it executes besides the MMAs is serial latency during which
+        // the tensor queue drains.  (1) a K block is one asm sequence -- 8 MMAs, the commits and, issued after the first
+        // two MMAs but consumed after the commits, NON-BLOCKING tests of the next K block's full barrier and the next
+        // accumulator's empty barrier (blocking waits only when a test fails: a blocking wait placed between the MMA
+        // bursts cost ~200-400 cycles even on a long-complete barrier, clock64 trace of round 2); (2) the loop is
+        // unrolled over the pipeline stages so descriptors and barrier addresses are loop invariants; (3) per-tile
+        // bookkeeping (which K block closes an accumulation chain) is a mask computed once per tile.
+        // Tried and measured, not faster: two issuer threads alternating K blocks (hand-over by tcgen05.commit +
+        // fence: the commit -> mbarrier -> waiter latency, ~350 cycles, is paid per K block), software-pipelining the
+        // bookkeeping into the gap after the first two MMAs, 16 gather warps with setmaxnreg (B2S_SP_GW=16).
         constexpr uint32_t idesc = make_idesc_f16(N), idesc2 = make_idesc_f16(2 * N);
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t smem0 = smem_u32(smem);
         const int num_tiles_u = __shfl_sync(0xffffffffu, num_tiles, 0);
         if (elect_one_sync() && blockIdx.x < (unsigned)num_tiles_u) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
+            // bit set = this K block is the last one of its accumulation chain present in the tile
+            auto chain_ends = [&](uint32_t kbm_) -> uint32_t {
+                uint32_t ce_ = 0;
+                for (int c = 0; c < num_chains; ++c) {
+                    const uint32_t m_ = kbm_ & (CHAIN_BITS << (c * CHAIN_KB));
+                    if (m_) ce_ |= 0x80000000u >> __clz(m_);
+                }
+                return ce_;
+            };
+            const uint32_t bar_full0 = smem_u32(&bar_full[0]), bar_empty0 = smem_u32(&bar_empty[0]);
+            const uint32_t bar_tfull0 = smem_u32(&bar_tfull[0]), bar_tempty0 = smem_u32(&bar_tempty[0]);
+            uint32_t phase = 0;                                 // parity of the full barriers in this round of the stages
+            uint32_t acc = 0, acc_phase = 0;
             const bool timing = (p.flags & 16) != 0;
-            const bool commit_first = (p.flags & 512) != 0, spin = (p.flags & 256) != 0;
-            long long t_full = 0, t_tempty = 0, t_begin = clock64();
+            long long t_wait = 0, t_begin = clock64();
             int n_kb = 0;
             mbar_wait(&bar_tempty[0], 1);
             mbar_wait(&bar_full[0], 0);
             tc_fence_after();
-            uint32_t kbm_next = tile_kbm(blockIdx.x);
-            for (int tile = blockIdx.x; tile < num_tiles_u; tile += gridDim.x) {
-                const bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
-                uint32_t kbm = kbm_next;
-                if (!last_tile) kbm_next = tile_kbm(tile + gridDim.x);
-                bool fresh = true;                              // the next MMA opens an accumulation chain
-                while (kbm) {
-                    const int kb = __ffs(kbm) - 1;
-                    kbm &= kbm - 1;
-                    const bool chain_end = (kbm & (CHAIN_BITS << ((kb / CHAIN_KB) * CHAIN_KB))) == 0;
-                    const uint32_t tmem_d = tmem_u + (uint32_t)(acc * ACC_W);
-                    int accn = acc + 1;
-                    uint32_t acc_phase_n = acc_phase;
-                    if (accn == ACC_SLOTS) { accn = 0; acc_phase_n ^= 1; }
-                    const uint32_t sa = smem0 + (uint32_t)stage * STAGE_BYTES;
+            int tile = blockIdx.x;
+            uint32_t kbm = tile_kbm(tile);
+            uint32_t ce = chain_ends(kbm);
+            bool last_tile = tile + (int)gridDim.x >= num_tiles_u;
+            uint32_t kbm_next = last_tile ? 0u : tile_kbm(tile + gridDim.x);
+            uint32_t fresh = 1;                                 // the next MMA opens an accumulation chain
+            for (;;) {
+#pragma unroll
+                for (int st = 0; st < STAGES; ++st) {
+                    const uint32_t low = kbm & (0u - kbm);
+                    kbm ^= low;
+                    const uint32_t chain_end = (ce & low) ? 1u : 0u;
+                    const bool tile_end = kbm == 0;
+                    const bool last = tile_end && last_tile;
+                    const uint32_t sa = smem0 + (uint32_t)st * STAGE_BYTES;
                     const uint64_t a_hi = make_desc_sw128(sa), a_lo = make_desc_sw128(sa + A_TILE_BYTES);
                     const uint64_t b_hl = make_desc_sw128(sa + 2 * A_TILE_BYTES);   // [W_hi; W_lo], 2N rows
-#pragma unroll
-                    for (int kk = 0; kk < 3; ++kk) {
-                        const uint64_t koff = (uint64_t)((kk * UMMA_K * ELEM_BYTES) >> 4);
-                        umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, (kk != 0 || !fresh) ? 1u : 0u);   // cols [0,2N)
-                        umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);                                // cols [0,N)
-                    }
-                    int stn = stage + 1;
-                    uint32_t phn = phase;
-                    if (stn == STAGES) { stn = 0; phn ^= 1; }
-                    const bool last = last_tile && kbm == 0;
+                    const uint32_t accn = (acc + 1) & (ACC_SLOTS - 1);
+                    const uint32_t acc_phase_n = acc_phase ^ (accn == 0 ? 1u : 0u);
                     B2S_TRACE(2, n_kb);
-                    if (!last && !commit_first) {
-                        const long long w0 = timing ? clock64() : 0;
-                        if (spin) mbar_wait_spin(&bar_full[stn], phn); else mbar_wait(&bar_full[stn], phn);
-                        B2S_TRACE(3, n_kb);
-                        const long long w1 = timing ? clock64() : 0;
-                        if (chain_end) mbar_wait(&bar_tempty[accn], acc_phase_n ^ 1);
-                        tc_fence_after();
-                        if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; }
-                    }
-                    {
-                        const uint64_t koff = (uint64_t)((3 * UMMA_K * ELEM_BYTES) >> 4);
-                        umma_f16(tmem_d, a_hi + koff, b_hl + koff, idesc2, 1);
-                        umma_f16(tmem_d, a_lo + koff, b_hl + koff, idesc, 1);
-                    }
-                    umma_commit(&bar_empty[stage]);
+                    uint32_t r_full, r_tempty;
+                    // per K step: A_hi x [W_hi;W_lo] into columns [0,2N), A_lo x W_hi into [0,N)
+                    asm volatile(
+                        "{\n\t"
+                        ".reg .pred pacc, ptrue, pf, pt, pce;\n\t"
+                        ".reg .b64 ah, al, bb;\n\t"
+                        "setp.eq.b32 pacc, %6, 0;\n\t"
+                        "setp.eq.b32 ptrue, 0, 0;\n\t"
+                        "setp.ne.b32 pce, %13, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], %3, %5, %8, pacc;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], %4, %5, %7, ptrue;\n\t"
+                        "mbarrier.test_wait.parity.shared::cta.b64 pf, [%9], %10;\n\t"
+                        "mbarrier.test_wait.parity.shared::cta.b64 pt, [%11], %12;\n\t"
+                        "add.u64 ah, %3, 2;\n\t add.u64 al, %4, 2;\n\t add.u64 bb, %5, 2;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], ah, bb, %8, ptrue;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], al, bb, %7, ptrue;\n\t"
+                        "add.u64 ah, %3, 4;\n\t add.u64 al, %4, 4;\n\t add.u64 bb, %5, 4;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], ah, bb, %8, ptrue;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], al, bb, %7, ptrue;\n\t"
+                        "add.u64 ah, %3, 6;\n\t add.u64 al, %4, 6;\n\t add.u64 bb, %5, 6;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], ah, bb, %8, ptrue;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%2], al, bb, %7, ptrue;\n\t"
+                        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%14];\n\t"
+                        "@pce tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%15];\n\t"
+                        "selp.u32 %0, 1, 0, pf;\n\t"
+                        "selp.u32 %1, 1, 0, pt;\n\t"
+                        "}"
+                        : "=r"(r_full), "=r"(r_tempty)
+                        : "r"(tmem_u + acc * (uint32_t)ACC_W), "l"(a_hi), "l"(a_lo), "l"(b_hl), "r"(fresh), "r"(idesc), "r"(idesc2),
+                          "r"(bar_full0 + 8u * (uint32_t)((st + 1) % STAGES)), "r"(st + 1 == STAGES ? phase ^ 1u : phase),
+                          "r"(bar_tempty0 + 8u * accn), "r"(acc_phase_n ^ 1u), "r"(chain_end),
+                          "r"(bar_empty0 + 8u * (uint32_t)st), "r"(bar_tfull0 + 8u * acc)
+                        : "memory");
+                    static_assert(((UMMA_K * ELEM_BYTES) >> 4) == 2, "K-step advance of the descriptors inside the asm block");
+                    static_assert((ACC_SLOTS & (ACC_SLOTS - 1)) == 0, "accumulator ring index uses a mask");
                     B2S_TRACE(4, n_kb);
                     ++n_kb;
-                    fresh = false;
-                    if (chain_end) {
-                        umma_commit(&bar_tfull[acc]);
-                        acc = accn; acc_phase = acc_phase_n;
-                        fresh = true;
-                    }
-                    if (!last && commit_first) {
+                    fresh = chain_end;
+                    if (chain_end) { acc = accn; acc_phase = acc_phase_n; }
+                    if (last) goto issuer_done;
+                    if (!(r_full & (chain_end ? r_tempty : 1u))) {
                         const long long w0 = timing ? clock64() : 0;
-                        if (spin) mbar_wait_spin(&bar_full[stn], phn); else mbar_wait(&bar_full[stn], phn);
-                        B2S_TRACE(3, n_kb - 1);
-                        const long long w1 = timing ? clock64() : 0;
-                        if (chain_end) mbar_wait(&bar_tempty[acc], acc_phase ^ 1);
-                        tc_fence_after();
-                        if (timing) { t_full += w1 - w0; t_tempty += clock64() - w1; }
+                        if (!r_full) mbar_wait(&bar_full[(st + 1) % STAGES], st + 1 == STAGES ? phase ^ 1u : phase);
+                        if (chain_end && !r_tempty) mbar_wait(&bar_tempty[acc], acc_phase ^ 1u);
+                        if (timing) t_wait += clock64() - w0;
                     }
-                    stage = stn; phase = phn;
+                    B2S_TRACE(3, n_kb - 1);
+                    tc_fence_after();
+                    if (tile_end) {
+                        tile += gridDim.x;
+                        kbm = kbm_next;
+                        ce = chain_ends(kbm);
+                        last_tile = tile + (int)gridDim.x >= num_tiles_u;
+                        if (!last_tile) kbm_next = tile_kbm(tile + gridDim.x);
+                    }
                 }
+                phase ^= 1u;
             }
+        issuer_done:
             if (timing && blockIdx.x == 0)
-                printf("[sparse_tc<%d,%d>] issuer: %d K blocks in %d tiles, total %lld cyc (%.0f/kb), wait full %lld (%.0f/kb), "
-                       "wait tempty+fence %lld (%.0f/kb)\n", CIN, COUT, n_kb, (num_tiles_u + (int)gridDim.x - 1) / (int)gridDim.x,
-                       clock64() - t_begin, (double)(clock64() - t_begin) / (n_kb + 1), t_full, (double)t_full / (n_kb + 1),
-                       t_tempty, (double)t_tempty / (n_kb + 1));
+                printf("[sparse_tc<%d,%d>] issuer: %d K blocks in %d tiles, total %lld cyc (%.0f/kb), blocking waits %lld (%.0f/kb)\n",
+                       CIN, COUT, n_kb, (num_tiles_u + (int)gridDim.x - 1) / (int)gridDim.x, clock64() - t_begin,
+                       (double)(clock64() - t_begin) / (n_kb + 1), t_wait, (double)t_wait / (n_kb + 1));
         }
         __syncwarp();
     } else if (warp >= 4 && warp < 4 + GW) {
@@ -315,6 +358,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         // The loop body is written for instruction count: a gather warp is ONE instruction stream, ~8 cycles per
         // dependent instruction, and the first version of this loop (lambdas, branches around the copies) compiled to
         // ~740 instructions per K block for 32 copies -- the gather warps, not memory, bounded the kernel.
+        if constexpr (GW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         const int gw = warp - 4;
         const int my_own = gw % OWN;                           // this warp takes K blocks g with g % OWN == my_own
         const int half = gw / OWN;                             // rows half*(128/HALVES) .. of the tile
@@ -376,7 +420,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             const int k_ = (KB) * PACK + ko;                                                  \
             KV = k_ < K ? 0xFFFFFFFFu : 0u;                                                   \
             const int *t_ = nbr + (k_ < K ? k_ : K - 1);                                      \
-            _Pragma("unroll") for (int i = 0; i < RI; ++i) NB[i] = __ldg(t_ + RK[i]);         \
+            _Pragma("unroll") for (int i = 0; i < RI; ++i) NB[i] = ld_nc_volatile(t_ + RK[i]); \
         } while (0)
 
         int rows_cur[RI], rows_pf[RI], nb_cur[RI], nb_nxt[RI];
@@ -470,6 +514,7 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
         asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp >= 4 + GW) {
         // ===================== epilogue =====================
+        if constexpr (GW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
         const int ew = warp - (4 + GW);                // == warp % 4: TMEM lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -596,10 +641,10 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
 #ifdef B2S_DIAG
     if ((p.flags & 64) && blockIdx.x == 0 && threadIdx.x == 0) {
         const long long t0 = g_trace[2][0];
-        printf("[trace<%d,%d>] g: W(empty seen, tma issued) I(6 mmas issued, full[g+1] seen, commit) G(at wait, empty seen, arrived)\n", CIN, COUT);
+        printf("[trace<%d,%d>] g: W(empty seen, tma issued) I(at waits, full seen, all waits done, MMAs+commits issued) G(at wait, empty seen, arrived)\n", CIN, COUT);
         for (int g = 32; g < 96; ++g)
-            printf("[trace] %3d  W %7lld %7lld  I %7lld %7lld %7lld  G %7lld %7lld %7lld\n", g, g_trace[0][g] - t0, g_trace[1][g] - t0,
-                   g_trace[2][g] - t0, g_trace[3][g] - t0, g_trace[4][g] - t0, g_trace[5][g] - t0, g_trace[6][g] - t0, g_trace[7][g] - t0);
+            printf("[trace] %3d  W %7lld %7lld  I %7lld %7lld %7lld %7lld  G %7lld %7lld %7lld\n", g, g_trace[0][g] - t0, g_trace[1][g] - t0,
+                   g_trace[2][g] - t0, g_trace[2][g] - t0, g_trace[3][g] - t0, g_trace[4][g] - t0, g_trace[5][g] - t0, g_trace[6][g] - t0, g_trace[7][g] - t0);
     }
 #endif
     if (warp == 2) {
@@ -608,25 +653,25 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
     }
 }
 
-template <int CIN, int COUT, int OWN>
-int launch_own(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
+template <int CIN, int COUT, int GW>
+int launch_gw(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
     constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * ELEM_BYTES;
     size_t smem = stage * STAGES + 1024;
-    B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, OWN>), smem);
+    B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, 4, GW>), smem);
     int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles_cap < num_sms ? tiles_cap : num_sms;
-    k_sparse_conv_tc<CIN, COUT, OWN><<<grid, kThreads, smem, stream>>>(w_hi, w_lo, p);
+    k_sparse_conv_tc<CIN, COUT, 4, GW><<<grid, 32 * (4 + GW + 4), smem, stream>>>(w_hi, w_lo, p);
     B2S_LAUNCH_OK();
     return 0;
 }
 template <int CIN, int COUT>
 int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
-    static int own = -1;      // B2S_SP_OWN = 1 | 4 (A/B switch of the gather ownership)
-    if (own < 0) { const char *e = getenv("B2S_SP_OWN"); own = (e && atoi(e) == 1) ? 1 : 4; }
-    return own == 4 ? launch_own<CIN, COUT, 4>(w_hi, w_lo, p, num_sms, stream)
-                    : launch_own<CIN, COUT, 1>(w_hi, w_lo, p, num_sms, stream);
+    static int gw = -1;       // B2S_SP_GW = 8 | 16 gather warps (A/B switch)
+    if (gw < 0) { const char *e = getenv("B2S_SP_GW"); gw = (e && atoi(e) == 16) ? 16 : 8; }
+    return gw == 8 ? launch_gw<CIN, COUT, 8>(w_hi, w_lo, p, num_sms, stream)
+                   : launch_gw<CIN, COUT, 16>(w_hi, w_lo, p, num_sms, stream);
 }
 
 }  // namespace

@@ -26,6 +26,7 @@ constexpr int kClasses = 16;
 struct PlanGeom {
     int K;
     unsigned below, above, before, after;   // offset masks of the four class groups
+    unsigned all;                           // (1 << K) - 1
 };
 
 // offset mask of the 32 rows row0 .. row0+31 (lane = row): K coalesced 32-int loads + ballots, then a funnel shift
@@ -65,8 +66,8 @@ __device__ __forceinline__ int row_class(unsigned m, const PlanGeom &g)
 //   sort == 0: tile_mask only (rows stay in storage order, perm untouched / may be NULL)
 //   sort == 1: stable grouping by class inside the chunk -> perm, tile_mask over the grouped order
 __global__ void __launch_bounds__(kThreads, 1)
-k_tile_plan(const int *__restrict__ nbr, const int *__restrict__ n_dev, int cap, PlanGeom g, int sort, int *perm,
-            unsigned *tile_mask)
+k_tile_plan(const int *__restrict__ nbr, const unsigned *__restrict__ row_mask, const int *__restrict__ n_dev, int cap,
+            PlanGeom g, int sort, int *perm, unsigned *tile_mask)
 {
     extern __shared__ unsigned s_dyn[];
     unsigned *s_mask = s_dyn;                                        // [kChunkRows] offset mask per row
@@ -78,25 +79,36 @@ k_tile_plan(const int *__restrict__ nbr, const int *__restrict__ n_dev, int cap,
     for (long long chunk0 = (long long)blockIdx.x * kChunkRows; chunk0 < n; chunk0 += (long long)gridDim.x * kChunkRows) {
         const int rows_here = (int)min((long long)kChunkRows, (long long)n - chunk0);
         // ---- pass 1: row masks (+ per-warp class counts) ----
-        int my_cnt = 0;                                              // lane c < 16: rows of class c in this warp's span
+        if (sort) {                                                  // s_cnt[c][w]: rows of class c in warp w's span
+            for (int i = threadIdx.x; i < kClasses * (kWarps + 1); i += kThreads) (&s_cnt[0][0])[i] = 0;
+            __syncthreads();
+        }
+        unsigned pre[kRowsPerWarp / 32];                             // masks handed over by the rulebook builder: one load each
+        if (row_mask) {
+#pragma unroll
+            for (int q = 0; q < kRowsPerWarp / 32; ++q) {
+                const int i = warp * kRowsPerWarp + q * 32 + lane;
+                pre[q] = i < rows_here ? __ldg(&row_mask[chunk0 + i]) & g.all : 0u;
+            }
+        }
+#pragma unroll
         for (int s = 0; s < kRowsPerWarp; s += 32) {
             const int local = warp * kRowsPerWarp + s;
             unsigned m = 0;
-            if (local < rows_here) m = warp_row_masks(nbr, chunk0 + local, n, g.K, s_bits[warp]);
+            if (row_mask) m = pre[s / 32];
+            else if (local < rows_here) m = warp_row_masks(nbr, chunk0 + local, n, g.K, s_bits[warp]);
             const bool live = local + lane < rows_here;
             if (!live) m = 0;
             s_mask[local + lane] = m;
             if (sort) {
-                const int c = row_class(m, g);
-#pragma unroll
-                for (int cc = 0; cc < kClasses; ++cc) {
-                    const unsigned b = __ballot_sync(0xffffffffu, live && c == cc);
-                    if (lane == cc) my_cnt += __popc(b);
-                }
+                // one match instead of 16 ballots: lanes of the same class find each other, the lowest one counts them
+                const int c = live ? row_class(m, g) : kClasses + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, c);
+                if (live && (peers & ((1u << lane) - 1u)) == 0u) s_cnt[c][warp] += __popc(peers);
+                __syncwarp();
             }
         }
         if (sort) {
-            if (lane < kClasses) s_cnt[lane][warp] = my_cnt;
             __syncthreads();
             // exclusive scan over (class major, warp minor): 16 x 32 entries, one warp
             if (warp == 0) {
@@ -115,20 +127,18 @@ k_tile_plan(const int *__restrict__ nbr, const int *__restrict__ n_dev, int cap,
             }
             __syncthreads();
             // ---- pass 2: stable scatter of the local row numbers ----
-            int running = lane < kClasses ? s_cnt[lane][warp] : 0;   // lane c: next position of class c for this warp
+            // s_cnt[c][warp] is now this warp's next free position of class c (only this warp touches its column)
             for (int s = 0; s < kRowsPerWarp; s += 32) {
                 const int local = warp * kRowsPerWarp + s + lane;
                 const bool live = local < rows_here;
-                const int c = row_class(s_mask[local], g);
-                int pos = 0;
-#pragma unroll
-                for (int cc = 0; cc < kClasses; ++cc) {
-                    const unsigned b = __ballot_sync(0xffffffffu, live && c == cc);
-                    const int base = __shfl_sync(0xffffffffu, running, cc);
-                    if (live && c == cc) pos = base + __popc(b & ((1u << lane) - 1u));
-                    if (lane == cc) running += __popc(b);
-                }
-                if (live) s_order[pos] = (unsigned short)local;
+                const int c = live ? row_class(s_mask[local], g) : kClasses + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, c);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (live && lane == leader) { base = s_cnt[c][warp]; s_cnt[c][warp] = base + __popc(peers); }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (live) s_order[base + __popc(peers & ((1u << lane) - 1u))] = (unsigned short)local;
+                __syncwarp();
             }
             __syncthreads();
             for (int i = threadIdx.x; i < rows_here; i += kThreads) perm[chunk0 + i] = (int)(chunk0 + s_order[i]);
@@ -153,8 +163,8 @@ k_tile_plan(const int *__restrict__ nbr, const int *__restrict__ n_dev, int cap,
 
 }  // namespace
 
-extern "C" int b2s_sparse_tile_plan(const int *nbr, int K, const int *ksize, const int *num_out_dev, int cap_out, int sort,
-                                    int *perm, unsigned *tile_mask, void *stream_)
+extern "C" int b2s_sparse_tile_plan(const int *nbr, const unsigned *row_mask, int K, const int *ksize, const int *num_out_dev,
+                                    int cap_out, int sort, int *perm, unsigned *tile_mask, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     B2S_REQUIRE(K >= 1 && K <= 27 && cap_out >= 0, "b2s_sparse_tile_plan: K must be 1..27");
@@ -163,6 +173,7 @@ extern "C" int b2s_sparse_tile_plan(const int *nbr, int K, const int *ksize, con
     PlanGeom g;
     g.K = K;
     g.below = g.above = g.before = g.after = 0u;
+    g.all = K >= 32 ? 0xffffffffu : ((1u << K) - 1u);
     int kz = K, ky = 1, kx = 1;
     if (ksize) { kz = ksize[0]; ky = ksize[1]; kx = ksize[2]; }
     B2S_REQUIRE(kz >= 1 && ky >= 1 && kx >= 1 && kz * ky * kx == K, "b2s_sparse_tile_plan: ksize does not multiply to K");
@@ -183,7 +194,8 @@ extern "C" int b2s_sparse_tile_plan(const int *nbr, int K, const int *ksize, con
     }
     int grid = b2s_cdiv(cap_out, kChunkRows);
     if (grid > 148 * 2) grid = 148 * 2;
-    k_tile_plan<<<grid, kThreads, smem, stream>>>(nbr, num_out_dev, cap_out, g, sort ? 1 : 0, perm, tile_mask);
+    B2S_REQUIRE(nbr != nullptr || row_mask != nullptr, "b2s_sparse_tile_plan: nbr or row_mask required");
+    k_tile_plan<<<grid, kThreads, smem, stream>>>(nbr, row_mask, num_out_dev, cap_out, g, sort ? 1 : 0, perm, tile_mask);
     B2S_LAUNCH_OK();
     return 0;
 }

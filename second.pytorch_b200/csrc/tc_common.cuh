@@ -52,9 +52,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-#ifndef B2S_MBAR_SUSPEND_HINT
-#define B2S_MBAR_SUSPEND_HINT 0x989680u
-#endif
 // bounded wait: ~seconds of spinning, then trap (a protocol bug must not hang the device)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
@@ -64,13 +61,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 #pragma unroll 1
     for (uint32_t it = 0; it < (1u << 28); ++it) {
         uint32_t done;
-        // suspend-time hint (as CUTLASS's ClusterBarrier::wait passes): without it the default time limit is short and
-        // every waiting thread re-polls the barrier unit in a tight loop
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// the same wait with a suspend-time hint (the form CUTLASS's ClusterBarrier::wait uses): the thread sleeps in the
+// barrier unit (SASS: TRYWAIT + NANOSLEEP.SYNCS) instead of re-polling.  Measured: fewer shared-memory operations from
+// the many waiting roles of the sparse kernel, but a later wake-up -- the dense conv kernels were 4 % slower with it.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity)
+{
+    uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 28); ++it) {
+        uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(B2S_MBAR_SUSPEND_HINT) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
         if (done) return;
     }
     __trap();

@@ -33,13 +33,13 @@ SIGNATURES = {
                              c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "b2s_hash_build": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b2s_rulebook_subm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                  c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p]),
     "b2s_rulebook_conv_workspace_bytes": (c_size_t, [c_int, c_void_p]),
     "b2s_rulebook_conv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                  c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+                                  c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "b2s_rulebook_subm_ranked": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_void_p, c_void_p]),
     "b2s_rulebook_pairs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2s_sparse_conv": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                 c_int, c_void_p, c_int, c_void_p]),
@@ -53,7 +53,8 @@ SIGNATURES = {
     "b2s_sparse_conv_tc_supported": (c_int, [c_int, c_int]),
     "b2s_sparse_conv_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                    c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "b2s_sparse_tile_plan": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2s_sparse_tile_plan": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                     c_void_p]),
     "b2s_sparse_conv_tc_plan": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                         c_int, c_int, c_void_p, c_void_p]),

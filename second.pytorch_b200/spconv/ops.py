@@ -27,7 +27,7 @@ def _pow2_at_least(n):
 
 class Rulebook:
     """output-stationary rulebook: ``nbr[o,k]`` = input row feeding output row ``o`` via offset ``k`` (-1: none)."""
-    __slots__ = ("out_indices", "nbr", "num_out", "num_out_dev", "out_hash", "K", "out_shape", "subm")
+    __slots__ = ("out_indices", "nbr", "num_out", "num_out_dev", "out_hash", "K", "out_shape", "subm", "row_mask")
 
     # tuple-style access keeps code written against upstream's (outids, indices, pairs, pair_num, shape) working
     def __iter__(self):
@@ -51,9 +51,10 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
     rb.subm = bool(subm)
     if subm:
         nbr = torch.empty(max(n_in, 1), K, dtype=torch.int32, device=dev)
+        rb.row_mask = torch.empty(max(n_in, 1), dtype=torch.int32, device=dev)      # bit k: nbr[row][k] exists
         _lib.check(lib.b2s_rulebook_subm(_lib.ptr(idx), _lib.ptr(n_in_dev), n_in, _lib.i3(x.spatial_shape),
                                          _lib.i3(ksize), _lib.i3(dilation), _lib.ptr(keys), _lib.ptr(vals), cap,
-                                         _lib.ptr(nbr), _lib.stream()), "b2s_rulebook_subm")
+                                         _lib.ptr(nbr), _lib.ptr(rb.row_mask), _lib.stream()), "b2s_rulebook_subm")
         rb.out_indices = idx
         rb.nbr = nbr[:n_in]
         rb.num_out = n_in
@@ -68,6 +69,7 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
     hash_cap_out = _pow2_at_least(2 * cap_out)
     coors_out = torch.empty(cap_out, 4, dtype=torch.int32, device=dev)
     nbr = torch.empty(cap_out, K, dtype=torch.int32, device=dev)
+    row_mask = torch.empty(cap_out, dtype=torch.int32, device=dev)                  # bit k: nbr[row][k] exists
     num_out_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     keys_out = torch.empty(hash_cap_out, dtype=torch.int64, device=dev)
     vals_out = torch.empty(hash_cap_out, dtype=torch.int32, device=dev)
@@ -79,12 +81,13 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
         _lib.ptr(idx), _lib.ptr(n_in_dev), n_in, x.batch_size, _lib.i3(x.spatial_shape), oshape, _lib.i3(ksize),
         _lib.i3(stride), _lib.i3(padding), _lib.i3(dilation), _lib.ptr(keys), _lib.ptr(vals), cap,
         _lib.ptr(coors_out), _lib.ptr(num_out_dev), cap_out, _lib.ptr(nbr), _lib.ptr(keys_out), _lib.ptr(vals_out),
-        hash_cap_out, _lib.ptr(ws), ws_bytes, _lib.ptr(status), _lib.stream()), "b2s_rulebook_conv")
+        hash_cap_out, _lib.ptr(ws), ws_bytes, _lib.ptr(row_mask), _lib.ptr(status), _lib.stream()), "b2s_rulebook_conv")
     n_out, st = int(num_out_dev.item()), int(status.item())   # the one sync of the module-by-module path
     if st:
         raise RuntimeError("b2s_rulebook_conv: " + _lib.status_message(st))
     rb.out_indices = coors_out[:n_out]
     rb.nbr = nbr[:n_out]
+    rb.row_mask = row_mask
     rb.num_out = n_out
     rb.num_out_dev = num_out_dev
     rb.out_hash = (keys_out, vals_out, hash_cap_out)

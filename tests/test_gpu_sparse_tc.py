@@ -183,9 +183,17 @@ def test_tile_plan_properties_and_bit_identity(product, cin, cout, subm, n):
     for sort in (0, 1):
         perm = torch.full((cap,), -7, dtype=torch.int32, device="cuda")
         tmask = torch.full((ntiles,), -1, dtype=torch.int32, device="cuda")
-        L.check(lib.b2s_sparse_tile_plan(L.ptr(nbr_cap), 27, ksz, L.ptr(rb.num_out_dev), cap, sort, L.ptr(perm),
+        L.check(lib.b2s_sparse_tile_plan(L.ptr(nbr_cap), None, 27, ksz, L.ptr(rb.num_out_dev), cap, sort, L.ptr(perm),
                                          L.ptr(tmask), L.stream()), "b2s_sparse_tile_plan")
+        # same plan from the row masks the rulebook builder wrote (no second pass over the table)
+        perm2 = torch.full((cap,), -7, dtype=torch.int32, device="cuda")
+        tmask2 = torch.full((ntiles,), -1, dtype=torch.int32, device="cuda")
+        rm_cap = torch.zeros(cap, dtype=torch.int32, device="cuda"); rm_cap[:n_out] = rb.row_mask[:n_out]
+        L.check(lib.b2s_sparse_tile_plan(None, L.ptr(rm_cap), 27, ksz, L.ptr(rb.num_out_dev), cap, sort, L.ptr(perm2),
+                                         L.ptr(tmask2), L.stream()), "b2s_sparse_tile_plan")
         torch.cuda.synchronize()
+        assert torch.equal(rb.row_mask[:n_out].long(), row_mask), "row masks from the rulebook builder"
+        assert torch.equal(perm, perm2) and torch.equal(tmask[:(n_out + 127) // 128], tmask2[:(n_out + 127) // 128])
         order = perm[:n_out].long() if sort else torch.arange(n_out, device="cuda")
         if sort:
             assert torch.equal(torch.sort(order).values, torch.arange(n_out, device="cuda"))       # a permutation
