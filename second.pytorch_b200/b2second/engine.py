@@ -786,8 +786,18 @@ class InferenceEngine:
                     self.points[off:off + run_rows].copy_(f, non_blocking=True)
             off += run_rows
             i = j
-        offs = torch.tensor(np.cumsum([0] + sizes), dtype=torch.int32)
-        self.offsets.copy_(offs.pin_memory(), non_blocking=True)
+        # frame offsets through a pinned staging buffer that is allocated once (a fresh pin_memory() per call is a
+        # cudaHostAlloc on the serving path); two slots, so the copy of the previous call is never overwritten in flight
+        if getattr(self, "_offs_host", None) is None:
+            self._offs_host = [torch.zeros(self.B + 1, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._offs_evt = [torch.cuda.Event(), torch.cuda.Event()]
+            self._offs_slot = 0
+        slot = self._offs_slot
+        self._offs_slot ^= 1
+        self._offs_evt[slot].synchronize()                 # (no-op unless two calls ago is still copying)
+        self._offs_host[slot].copy_(torch.from_numpy(np.cumsum([0] + sizes).astype(np.int32)))
+        self.offsets.copy_(self._offs_host[slot], non_blocking=True)
+        self._offs_evt[slot].record()
         return total
 
     def load_points_cropped(self, frames, planes):

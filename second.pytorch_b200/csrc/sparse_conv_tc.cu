@@ -42,7 +42,9 @@
 namespace {
 
 using namespace b2s_tc;
-constexpr int STAGES = 4;                 // pipeline stages; gather warp w owns stage w % STAGES
+// pipeline stages: 4 x (32 KB of gathered rows + 256 N bytes of weights).  Five stages for the narrow layers (N <= 32 fits)
+// were tried in round 2: not faster (the ring is not what bounds the kernel) and not validated -- kept at 4 everywhere.
+__host__ __device__ constexpr int stages_for(int n) { return n > 0 ? 4 : 4; }
 // GW gather warps (warps 4 .. 4+GW-1), the epilogue is the 4 warps after them.  GW = 16 (24 warps) needs the register
 // file rebalanced between the roles with setmaxnreg (inside each role's branch, where ptxas honours it): 768 threads
 // start with 80 registers each; the gather warps drop to 64 and the epilogue warps (64 running sums + staging) rise to 144.
@@ -145,10 +147,12 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                  const SpParams p)
 {
     constexpr int N = COUT;
+    constexpr int STAGES = stages_for(COUT);
+    static_assert(STAGES == 4, "only the 4-stage ring is validated");
     static_assert(GW == 8 || GW == 16, "thread layout");
     constexpr int HALVES = GW / OWN;          // gather warps sharing one K block (each takes BLOCK_M / HALVES rows)
     constexpr int RI = BLOCK_M / HALVES / 4;  // 4-row copy iterations per gather warp and K block
-    static_assert(GW % OWN == 0 && RI * 4 * HALVES == BLOCK_M && (OWN & (OWN - 1)) == 0 && RI * STAGES <= 64, "gather warp layout");
+    static_assert(GW % OWN == 0 && RI * 4 * HALVES == BLOCK_M && (OWN & (OWN - 1)) == 0 && RI * STAGES <= 128, "gather warp layout");
     static_assert(CIN <= BLOCK_K && BLOCK_K % CIN == 0, "one K block holds whole kernel offsets");
     constexpr int PACK = BLOCK_K / CIN;                       // kernel offsets per K block
     constexpr int CPO = 8 / PACK;                             // 16-byte chunks per offset inside a 128-byte row
@@ -435,7 +439,8 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             pf_tile = cur_tile + grid;
             if (pf_tile < num_tiles) B2S_LOAD_ROWS(pf_tile, rows_pf, ok_pf);
         }
-        unsigned long long zeroed_all = 0;   // bit stage*RI + i: this lane's chunk of row slot i in that stage holds zeros
+        // bit (stage % 4)*RI + i of word stage / 4: this lane's chunk of row slot i in that stage holds zeros
+        unsigned long long zeroed_w0 = 0, zeroed_w1 = 0;
         while (kb_cur >= 0) {
             // ---- prefetch the table entries of the next owned K block ----
             int kb_nxt;
@@ -456,7 +461,8 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
             valid &= ok_cur & kv_cur;
             const int my_stage = g_cur % STAGES;               // K block g lives in stage g % STAGES, its (g / STAGES)-th use
             const uint32_t use_parity = (((uint32_t)g_cur / STAGES) & 1u) ^ 1u;
-            const uint32_t zeroed = (uint32_t)(zeroed_all >> (my_stage * RI)) & ((1u << RI) - 1u);
+            const int zsh = (my_stage & 3) * RI;
+            const uint32_t zeroed = (uint32_t)((my_stage < 4 ? zeroed_w0 : zeroed_w1) >> zsh) & ((1u << RI) - 1u);
             const uint32_t need = zskip_on ? (valid | (~zeroed & ((1u << RI) - 1u))) : 0xFFFFFFFFu;
             const uint32_t sa = sa0 + (uint32_t)my_stage * STAGE_BYTES;
             if (half == 0) B2S_TRACE(5, g_cur);
@@ -489,8 +495,11 @@ k_sparse_conv_tc(const __grid_constant__ CUtensorMap map_w_hi, const __grid_cons
                 }
             }
             static_assert(A_TILE_BYTES == 16384, "lo plane of the A tile sits 16384 bytes after the hi plane");
-            zeroed_all = (zeroed_all & ~((unsigned long long)((1u << RI) - 1u) << (my_stage * RI))) |
-                         ((unsigned long long)(~valid & ((1u << RI) - 1u)) << (my_stage * RI));
+            {
+                const unsigned long long clr = ~((unsigned long long)((1u << RI) - 1u) << zsh);
+                const unsigned long long set = (unsigned long long)(~valid & ((1u << RI) - 1u)) << zsh;
+                if (my_stage < 4) zeroed_w0 = (zeroed_w0 & clr) | set; else zeroed_w1 = (zeroed_w1 & clr) | set;
+            }
             if (p.flags & 128) mbar_arrive(&bar_full[my_stage]); else cp_async_mbar_arrive_noinc(&bar_full[my_stage]);
             if (half == 0) B2S_TRACE(7, g_cur);
             // ---- advance ----
@@ -657,7 +666,7 @@ template <int CIN, int COUT, int GW>
 int launch_gw(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
     constexpr size_t stage = 2 * A_TILE_BYTES + 2 * (size_t)COUT * BLOCK_K * ELEM_BYTES;
-    size_t smem = stage * STAGES + 1024;
+    size_t smem = stage * stages_for(COUT) + 1024;
     B2S_SMEM_OPT_IN((k_sparse_conv_tc<CIN, COUT, 4, GW>), smem);
     int tiles_cap = (p.cap_out + BLOCK_M - 1) / BLOCK_M;
     int grid = tiles_cap < num_sms ? tiles_cap : num_sms;

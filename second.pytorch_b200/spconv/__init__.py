@@ -337,11 +337,12 @@ class SparseConvolution(SparseModule):
             o_hi, o_lo = obuf[:, 0], obuf[:, 1]
             if n_out > 0:
                 status = torch.zeros(1, dtype=torch.int32, device=dev)
-                _lib.check(lib.b2s_sparse_conv_tc(
+                perm, tmask = ops.tile_plan(rb)        # SubM rulebooks: K blocks no row of a tile needs are skipped
+                _lib.check(lib.b2s_sparse_conv_tc_plan(
                     _lib.ptr(hi), _lib.ptr(lo), stride, hi.shape[0], cin_tc, _lib.ptr(w_hi), _lib.ptr(w_lo),
-                    _lib.ptr(rb.nbr), K, _lib.ptr(rb.num_out_dev), n_out, _lib.ptr(scale_tc), _lib.ptr(shift),
-                    1 if relu else 0, _lib.ptr(o_hi), _lib.ptr(o_lo), 2 * self.out_channels, self.out_channels,
-                    _lib.ptr(status), _lib.stream()), "b2s_sparse_conv_tc")
+                    _lib.ptr(rb.nbr), K, _lib.ptr(rb.num_out_dev), n_out, _lib.ptr(perm), _lib.ptr(tmask),
+                    _lib.ptr(scale_tc), _lib.ptr(shift), 1 if relu else 0, _lib.ptr(o_hi), _lib.ptr(o_lo),
+                    2 * self.out_channels, self.out_channels, _lib.ptr(status), _lib.stream()), "b2s_sparse_conv_tc_plan")
                 out._status = status
             out._hilo = (o_hi[:n_out], o_lo[:n_out], 2 * self.out_channels)
             out._keep = obuf

@@ -27,7 +27,7 @@ def _pow2_at_least(n):
 
 class Rulebook:
     """output-stationary rulebook: ``nbr[o,k]`` = input row feeding output row ``o`` via offset ``k`` (-1: none)."""
-    __slots__ = ("out_indices", "nbr", "num_out", "num_out_dev", "out_hash", "K", "out_shape", "subm", "row_mask")
+    __slots__ = ("out_indices", "nbr", "num_out", "num_out_dev", "out_hash", "K", "out_shape", "subm", "row_mask", "ksize", "plan")
 
     # tuple-style access keeps code written against upstream's (outids, indices, pairs, pair_num, shape) working
     def __iter__(self):
@@ -49,6 +49,8 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
     rb = Rulebook()
     rb.K = K
     rb.subm = bool(subm)
+    rb.ksize = [int(k) for k in ksize]
+    rb.plan = None
     if subm:
         nbr = torch.empty(max(n_in, 1), K, dtype=torch.int32, device=dev)
         rb.row_mask = torch.empty(max(n_in, 1), dtype=torch.int32, device=dev)      # bit k: nbr[row][k] exists
@@ -93,6 +95,25 @@ def build_rulebook(x, ksize, stride, padding, dilation, subm):
     rb.out_hash = (keys_out, vals_out, hash_cap_out)
     rb.out_shape = out_shape
     return rb
+
+
+def tile_plan(rb):
+    """tile plan of a rulebook for b2s_sparse_conv_tc_plan: (perm, tile_mask), built once per rulebook from the row masks
+    the builder wrote.  Rows are grouped for SubM rulebooks (an ``indice_key`` shares them between layers); a strided
+    conv uses its table once, so it gets no plan (None, None) -- the same policy as the fused engine."""
+    if rb.plan is None:
+        if not rb.subm or rb.K <= 3 or rb.num_out <= 0 or getattr(rb, "row_mask", None) is None:
+            rb.plan = (None, None)
+        else:
+            lib = _lib.load()
+            dev = rb.nbr.device
+            perm = torch.empty(rb.num_out, dtype=torch.int32, device=dev)
+            tmask = torch.empty((rb.num_out + 127) // 128, dtype=torch.int32, device=dev)
+            _lib.check(lib.b2s_sparse_tile_plan(None, _lib.ptr(rb.row_mask), rb.K, _lib.i3(rb.ksize), _lib.ptr(rb.num_out_dev),
+                                                rb.num_out, 1, _lib.ptr(perm), _lib.ptr(tmask), _lib.stream()),
+                       "b2s_sparse_tile_plan")
+            rb.plan = (perm, tmask)
+    return rb.plan
 
 
 def pairs_from_nbr(rb, length=None):

@@ -19,4 +19,5 @@ rm -f gpurun_out/${TAG}_full.ncu-rep
 B2S_PROFILE=1 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:'k_conv3x3_tc2|k_sparse_conv_tc|k_conv_tc' -c 24 -o gpurun_out/${TAG}_tc -f python $ARGS > gpurun_out/${TAG}_tc.log 2>&1
 echo "tc rc=$?"
+rm -f gpurun_out/${TAG}_tc.ncu-rep   # (65 MB: gpurun copies back at most 64 MiB in total; keep the rep only when run by hand)
 ls -la gpurun_out/${TAG}_*
