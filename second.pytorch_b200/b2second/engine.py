@@ -762,7 +762,31 @@ class InferenceEngine:
         total = sum(sizes)
         assert total <= self.P_cap, "more points (%d) than the engine's capacity (%d)" % (total, self.P_cap)
         # frames that lie back to back in memory (views of one pinned slab, or of one device tensor) go over in ONE copy:
-        # a serving loop that reads clouds into a pinned ring buffer pays one cudaMemcpyAsync per batch instead of B
+        # a serving loop that reads clouds into a pinned ring buffer pays one cudaMemcpyAsync per batch instead of B.
+        # The run structure only depends on where the frames lie: a serving loop cycles through a few slabs, so it is
+        # remembered per (pointers, sizes, strides) -- finding it anew is ~0.25 ms of Python per call for 32 frames.
+        key = (tuple(f.data_ptr() for f in frames), tuple(sizes), tuple(f.stride(0) for f in frames),
+               frames[0].dtype, frames[0].device) if frames else None
+        cache = getattr(self, "_run_cache", None)
+        if cache is None:
+            cache = self._run_cache = {}
+        runs = cache.get(key)
+        if runs is not None:
+            # (a remembered multi-frame run must still lie inside ONE storage: same addresses, different allocations)
+            for i, off, run_rows, whole in runs:
+                if whole and frames[i].untyped_storage().nbytes() < 4 * (frames[i].storage_offset() + run_rows * self.F):
+                    runs = None
+                    del cache[key]
+                    break
+        if runs is not None:
+            for i, off, run_rows, whole in runs:
+                if whole:
+                    src = torch.as_strided(frames[i], (run_rows, self.F), (self.F, 1))
+                    self.points[off:off + run_rows].copy_(src, non_blocking=True)
+                else:
+                    self.points[off:off + run_rows].copy_(frames[i], non_blocking=True)
+            return self._load_offsets(sizes, total)
+        runs = []
         off, i = 0, 0
         while i < len(frames):
             f = frames[i]
@@ -784,8 +808,14 @@ class InferenceEngine:
                     self.points[off:off + run_rows].copy_(src, non_blocking=True)
                 else:
                     self.points[off:off + run_rows].copy_(f, non_blocking=True)
+                runs.append((i, off, run_rows, j - i > 1))
             off += run_rows
             i = j
+        if len(cache) < 16 and all(f.dtype == torch.float32 for f in frames):
+            cache[key] = runs
+        return self._load_offsets(sizes, total)
+
+    def _load_offsets(self, sizes, total):
         # frame offsets through a pinned staging buffer that is allocated once (a fresh pin_memory() per call is a
         # cudaHostAlloc on the serving path); two slots, so the copy of the previous call is never overwritten in flight
         if getattr(self, "_offs_host", None) is None:
@@ -930,9 +960,13 @@ class InferenceEngine:
                 out.append({"box3d_lidar": snap[b, :n, :code], "scores": snap[b, :n, code],
                             "label_preds": labels[b, :n], "metadata": meta[b]})
             return out
-        host = self._rec_host[:, :-1].view(B, self.post_max, code + 2).clone()
+        # per-frame views through numpy: 3 B tensor views cost ~0.1 ms this way and ~0.8 ms as torch indexing ops (the
+        # Python between two steps is GPU idle time on the serving path)
+        host = self._rec_host.numpy()[:, :-1].reshape(B, self.post_max, code + 2).copy()
+        labels = host[..., code + 1].astype(np.int64)
+        fn = torch.from_numpy
         for b in range(B):
-            d = host[b, :cnt[b]]
-            out.append({"box3d_lidar": d[:, :code], "scores": d[:, code], "label_preds": d[:, code + 1].long(),
-                        "metadata": meta[b]})
+            n = cnt[b]
+            out.append({"box3d_lidar": fn(host[b, :n, :code]), "scores": fn(host[b, :n, code]),
+                        "label_preds": fn(labels[b, :n]), "metadata": meta[b]})
         return out
