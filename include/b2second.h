@@ -287,6 +287,17 @@ int b2s_rpn_bg_plan(const uint8_t *occupancy /*[B,H,W]*/, int batch, int H, int 
 int b2s_rpn_bg_fill(const int *bg_list, const int *bg_count_dev, int batch, int H, int W, int C, const b2s_half *f_hi,
                     const b2s_half *f_lo, b2s_half *out_hi, b2s_half *out_lo, int out_stride, void *stream);
 
+
+/* the tail of a single-scale RPNV2 in one kernel (csrc/rpn_tail.cu): y = relu(bn(deblock_1x1(x))) (128 -> 128) never
+ * leaves the SM, heads = [box | cls | dir](y) + bias come out as packed fp32 records [B, H, W, out_stride].  Operands as
+ * for b2s_conv2d_tc: x = halo-padded fp16 hi/lo planes [B, H+2, W+2, 128]; w1 [128][128], w2 [n_pad2 = 32][128] K-major
+ * hi/lo planes, pre-scaled by powers of two folded into scale1 / scale2; shift2 = the heads' bias.  Bit-identical to the
+ * two b2s_conv2d_tc launches it replaces (second/pytorch/models/rpn.py:264-299, 386-420). */
+int b2s_rpn_tail_tc(const b2s_half *in_hi, const b2s_half *in_lo, int B, int H, int W, int Cin, const b2s_half *w1_hi,
+                    const b2s_half *w1_lo, int Cmid, const float *scale1, const float *shift1, const b2s_half *w2_hi,
+                    const b2s_half *w2_lo, int cout2, int n_pad2, const float *scale2, const float *shift2, float *out,
+                    int out_stride, unsigned *status_dev, void *stream);
+
 /* ---- PointPillars feature net (single PFNLayer: Linear(F+5 -> Cout, no bias) + BN + ReLU + max) -- */
 int b2s_pfn(const float *points, int num_feat, const int *point_slots, const int *num_points_per_voxel,
             const int *coors, const int *num_rows_dev, int cap_rows, int max_points,

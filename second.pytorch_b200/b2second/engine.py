@@ -273,6 +273,16 @@ class InferenceEngine:
         plan = _tc.plan_rpn(rpn, H, W)
         self.tc_prog = plan
         self.tc_plan = plan["ops"]
+        # single-scale tail (one k = s = 1 deblock 128 -> 128 feeding the heads): one fused kernel, the deblock output
+        # never goes to HBM (csrc/rpn_tail.cu; bit-identical to the two launches).  B2S_RPN_TAIL=0: two launches.
+        ops = self.tc_plan
+        self.tc_tail_fused = bool(
+            os.environ.get("B2S_RPN_TAIL", "1") != "0" and len(ops) >= 2
+            and ops[-1]["kind"] == "heads" and ops[-2]["kind"] == "deblock" and ops[-1]["src"] == ops[-2]["dst"]
+            and sum(1 for o in ops if o["dst"] == ops[-2]["dst"]) == 1
+            and (ops[-2]["kh"], ops[-2]["kw"], ops[-2]["stride"], ops[-2]["out_mul"], ops[-2]["dst_coff"]) == (1, 1, 1, 1, 0)
+            and ops[-2]["cin"] == 128 and ops[-2]["cout"] == 128 and ops[-2]["relu"] and ops[-2]["planes"] == 2
+            and ops[-1]["cin"] == 128 and ops[-1]["n_pad"] == 32 and ops[-1]["planes"] == 1 and not ops[-1]["relu"])
         assert plan["in_channels"] == C, "BEV channels %d != RPN input %d" % (C, plan["in_channels"])
 
         def plane(h, w, c):
@@ -552,7 +562,8 @@ class InferenceEngine:
                                         L.ptr(self.bg_flags), L.ptr(self.bg_work), L.ptr(self.bg_list),
                                         L.ptr(self.bg_counts), st), "b2s_rpn_bg_plan")
         marked_tail = False
-        for oi, op in enumerate(self.tc_plan):
+        n_ops = len(self.tc_plan) - (2 if self.tc_tail_fused else 0)
+        for oi, op in enumerate(self.tc_plan[:n_ops]):
             if not op["v2"] and op["kind"] != "block" and not marked_tail:
                 self._mark("rpn_1x1")          # the 3x3 stack (k_conv3x3_tc2) is timed apart from the deblock/heads tail
                 marked_tail = True
@@ -581,6 +592,14 @@ class InferenceEngine:
                 L.ptr(self.status), st), "b2s_conv2d_tc_ex(%s)" % op["kind"])
         if not marked_tail:
             self._mark("rpn_1x1")
+        if self.tc_tail_fused:
+            d, h = self.tc_plan[-2], self.tc_plan[-1]
+            src = self.tc_bufs[d["src"]]
+            L.check(lib.b2s_rpn_tail_tc(
+                L.ptr(src[0]), L.ptr(src[1]), self.B, d["Hin"], d["Win"], d["cin"], L.ptr(d["w_hi"]), L.ptr(d["w_lo"]),
+                d["cout"], L.ptr(d["scale"]), L.ptr(d["shift"]), L.ptr(h["w_hi"]), L.ptr(h["w_lo"]), h["cout"], h["n_pad"],
+                L.ptr(h["scale"]), L.ptr(h["shift"]), L.ptr(self.tc_heads), self.tc_head_stride, L.ptr(self.status), st),
+                "b2s_rpn_tail_tc")
         S = self.tc_head_stride
         self._mark("decode_filter")
         offs = self.tc_prog["heads"]["offsets"]
@@ -682,7 +701,7 @@ class InferenceEngine:
             if lyr.get("in_split") is not None:
                 n += 1                           # b2s_split_f16
         if self.rpn_impl == "tc":
-            n += len(self.tc_plan)               # one tcgen05 conv kernel per RPN layer (heads = 1 launch)
+            n += len(self.tc_plan) - (1 if self.tc_tail_fused else 0)   # one tcgen05 kernel per RPN layer (fused tail: 1 for 2)
             if self.bg_idx:
                 # k_bg_layer per layer, k_bg_compact (+ k_bg_fill per layer unless the conv epilogue fills)
                 n += len(self.bg_idx) + 1 + (0 if self.bg_fused_fill else len(self.bg_idx))

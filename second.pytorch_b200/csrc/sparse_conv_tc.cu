@@ -677,10 +677,13 @@ int launch_gw(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &
 template <int CIN, int COUT>
 int launch(const CUtensorMap &w_hi, const CUtensorMap &w_lo, const SpParams &p, int num_sms, cudaStream_t stream)
 {
-    static int gw = -1;       // B2S_SP_GW = 8 | 16 gather warps (A/B switch)
+#ifdef B2S_SP_GW16
+    // A/B build (make EXTRA=-DB2S_SP_GW16): B2S_SP_GW=16 runs 16 gather warps with setmaxnreg (measured: not faster)
+    static int gw = -1;
     if (gw < 0) { const char *e = getenv("B2S_SP_GW"); gw = (e && atoi(e) == 16) ? 16 : 8; }
-    return gw == 8 ? launch_gw<CIN, COUT, 8>(w_hi, w_lo, p, num_sms, stream)
-                   : launch_gw<CIN, COUT, 16>(w_hi, w_lo, p, num_sms, stream);
+    if (gw == 16) return launch_gw<CIN, COUT, 16>(w_hi, w_lo, p, num_sms, stream);
+#endif
+    return launch_gw<CIN, COUT, 8>(w_hi, w_lo, p, num_sms, stream);
 }
 
 }  // namespace

@@ -67,3 +67,34 @@ def test_product_path_fails_loudly_without_cuda():
         x.dense()
     with pytest.raises(RuntimeError):
         spconv.utils.VoxelGeneratorV2([0.1] * 3, [0, 0, 0, 1, 1, 1], 5).generate(torch.zeros(4, 4).numpy(), 100)
+
+
+def test_argument_checks_run_before_any_cuda_call():
+    """host-side contract of the sparse-conv entry points: bad arguments are rejected with -2 and a message before any
+    CUDA call (so this runs without a GPU); the supported (Cin, Cout) table is a host query."""
+    from spconv import _lib
+    lib = _lib.load()
+    i3 = (ctypes.c_int * 3)
+    dummy = ctypes.c_void_p(256)                      # never dereferenced: every call below fails its argument check
+    # tile plan: K must be 1..27, ksize must multiply to K, tile_mask (and perm when sorting) are required
+    assert lib.b2s_sparse_tile_plan(dummy, None, 28, None, dummy, 1000, 0, None, dummy, None) == -2
+    assert b"K must be 1..27" in lib.b2s_last_error()
+    assert lib.b2s_sparse_tile_plan(dummy, None, 27, i3(3, 3, 2), dummy, 1000, 0, None, dummy, None) == -2
+    assert b"ksize" in lib.b2s_last_error()
+    assert lib.b2s_sparse_tile_plan(dummy, None, 27, i3(3, 3, 3), dummy, 1000, 1, None, dummy, None) == -2
+    assert lib.b2s_sparse_tile_plan(dummy, None, 27, i3(3, 3, 3), dummy, 1000, 0, None, None, None) == -2
+    assert lib.b2s_sparse_tile_plan(None, None, 27, i3(3, 3, 3), dummy, 0, 0, None, dummy, None) == 0    # no rows: nothing to do
+    # tensor-pipe conv: channel table, K range, 16-byte row alignment, 32-bit row offsets
+    assert [lib.b2s_sparse_conv_tc_supported(c, 64) for c in (8, 16, 32, 64, 4, 128)] == [1, 1, 1, 1, 0, 0]
+    assert [lib.b2s_sparse_conv_tc_supported(64, c) for c in (16, 32, 64, 8, 128)] == [1, 1, 1, 0, 0]
+
+    def conv(cin=64, cout=64, K=27, in_stride=128, rows_in=1000, feat=256, out_stride=128):
+        return lib.b2s_sparse_conv_tc_plan(ctypes.c_void_p(feat), ctypes.c_void_p(feat + 128), in_stride, rows_in, cin, dummy,
+                                           dummy, dummy, K, dummy, 1000, None, None, None, None, 1, dummy,
+                                           ctypes.c_void_p(512), out_stride, cout, None, None)
+    assert conv(cin=48) == -2 and b"built for Cin" in lib.b2s_last_error()
+    assert conv(K=0) == -2 and conv(K=28) == -2
+    assert conv(in_stride=60) == -2 and b"16-byte aligned" in lib.b2s_last_error()
+    assert conv(feat=260) == -2
+    assert conv(out_stride=60) == -2
+    assert conv(rows_in=1 << 25, in_stride=128) == -2 and b"4 GiB" in lib.b2s_last_error()

@@ -170,3 +170,51 @@ def test_fp16_range_guard_raises_status(product):
     torch.cuda.synchronize()
     assert int(status.item()) & 16
     assert bool(torch.isfinite(o_hi.float()).all()) and float(o_hi.float().max()) == 65504.0
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("B,H,W", [(2, 20, 33), (1, 200, 176), (3, 8, 16), (1, 5, 7)])
+def test_fused_rpn_tail_is_bit_identical_to_two_launches(product, B, H, W):
+    """b2s_rpn_tail_tc (deblock 1x1 + BN + ReLU -> packed heads in one kernel, the deblock output stays in shared memory)
+    against the two b2s_conv2d_tc launches it replaces: same MMA sequences, same epilogue arithmetic => identical bits;
+    and both against torch fp32 (rpn.py:264-299, 386-420)."""
+    from b2second import tc
+    L = product._lib
+    lib = L.load()
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + H)
+    cin, cmid, cout = 128, 128, 20
+    x = torch.randn(B, cin, H, W, device="cuda", generator=g)
+    w1 = torch.randn(cmid, cin, device="cuda", generator=g) * (2.0 / cin) ** 0.5          # [y channel, x channel]
+    scale1 = torch.rand(cmid, device="cuda", generator=g) + 0.5
+    shift1 = torch.randn(cmid, device="cuda", generator=g) * 0.1
+    w2 = torch.randn(cout, cmid, device="cuda", generator=g) * 0.1
+    bias2 = torch.randn(cout, device="cuda", generator=g) * 0.1
+    # two launches
+    y_hi, y_lo = run_tc(product, x, w1.unsqueeze(0).contiguous(), 1, cmid, 128, scale1, shift1, True, True, cmid)
+    hi, lo = tc.split_f16(pad_nhwc(x))
+    wp2 = tc._pad_rows(w2.unsqueeze(0).contiguous(), 32)
+    ws2 = tc.pow2_scale(wp2)
+    w2_hi, w2_lo = tc.split_f16(wp2, ws2)
+    scale2 = (torch.ones(cout, device="cuda") / ws2).contiguous()
+    two = torch.zeros(B, H, W, 32, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check(lib.b2s_conv2d_tc(L.ptr(y_hi), L.ptr(y_lo), B, H, W, cmid, L.ptr(w2_hi), L.ptr(w2_lo), 1, cout, 32,
+                              L.ptr(scale2), L.ptr(bias2), 0, L.ptr(two), None, 0, 32, L.ptr(status), L.stream()),
+            "b2s_conv2d_tc")
+    # one launch
+    wp1 = tc._pad_rows(w1.unsqueeze(0).contiguous(), 128)
+    ws1 = tc.pow2_scale(wp1)
+    w1_hi, w1_lo = tc.split_f16(wp1, ws1)
+    scale1_k = (scale1 / ws1).contiguous()
+    one = torch.full((B, H, W, 32), 7.0, device="cuda")
+    L.check(lib.b2s_rpn_tail_tc(L.ptr(hi), L.ptr(lo), B, H, W, cin, L.ptr(w1_hi), L.ptr(w1_lo), cmid, L.ptr(scale1_k),
+                                L.ptr(shift1), L.ptr(w2_hi), L.ptr(w2_lo), cout, 32, L.ptr(scale2), L.ptr(bias2),
+                                L.ptr(one), 32, L.ptr(status), L.stream()), "b2s_rpn_tail_tc")
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    assert torch.equal(one[..., :cout], two[..., :cout]), "fused tail differs from the two-launch path"
+    assert bool((one[..., cout:] == 7.0).all())                       # channels past Cout are not written
+    y = torch.relu(F.conv2d(x, w1.view(cmid, cin, 1, 1)) * scale1.view(1, -1, 1, 1) + shift1.view(1, -1, 1, 1))
+    ref = (F.conv2d(y, w2.view(cout, cmid, 1, 1)) + bias2.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    err = (one[..., :cout] - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), "max err %g" % err
