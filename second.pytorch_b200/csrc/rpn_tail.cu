@@ -16,7 +16,9 @@
 //   warp 1      MMA issuer (one elected lane): G1(i+1) is issued before G2(i), so the tensor pipe works on the next
 //               tile's first GEMM while the epilogue warps turn y(i) into the A operand
 //   warp 2      TMEM allocator (D1: 2 x 128 columns, D2: 32 columns)
-//   warps 4-7   epilogue: E1 = D1 -> BN/ReLU/split -> A2 (shared), E2 = D2 -> + bias -> fp32 records (global)
+//   warps 4-11  epilogue, two groups of four (TMEM lane quarter = warp % 4): E1 = D1 -> BN/ReLU/split -> A2 (shared), group g
+//               takes the 64 channels of K block g; E2 = D2 -> + bias -> fp32 records (global), group g takes 16 columns.
+//               (With one group the epilogue was the longest stage of the per-tile chain.)
 #include <cuda_fp16.h>
 
 #include "tc_common.cuh"
@@ -28,7 +30,7 @@ constexpr int TILE_H = 8, TILE_W = 16;    // BLOCK_M = 128 pixels
 constexpr int C = 128;                    // channels of x and y
 constexpr int KB = C / BLOCK_K;           // 2 K blocks of 64 channels
 constexpr int N1 = 128;                   // GEMM 1 N (= channels of y)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;              // 4 control warps + 2 x 4 epilogue warps
 constexpr uint32_t W1_KB_BYTES = 2 * N1 * BLOCK_K * ELEM_BYTES;        // hi + lo of one K block: 32 KB
 constexpr uint32_t X_STAGE_BYTES = 2 * A_TILE_BYTES;                   // hi + lo of one K block of x: 32 KB
 
@@ -74,9 +76,9 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
     if (warp == 1 && lane == 0) {
         mbar_init(&bar_w, 1);
         for (int i = 0; i < KB; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1full[i], 1); mbar_init(&bar_d1empty[i], 4); }
-        mbar_init(&bar_a2full, 4); mbar_init(&bar_a2empty, 1);
-        mbar_init(&bar_d2full, 1); mbar_init(&bar_d2empty, 4);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1full[i], 1); mbar_init(&bar_d1empty[i], 8); }
+        mbar_init(&bar_a2full, 8); mbar_init(&bar_a2empty, 1);
+        mbar_init(&bar_d2full, 1); mbar_init(&bar_d2empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -163,7 +165,9 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4;                                   // TMEM lane quarter; this thread owns tile pixel m
+        const int ew = (warp - 4) & 3;                             // TMEM lane quarter; this thread owns tile pixel m
+        const int grp = (warp - 4) >> 2;                           // 0 / 1: which half of the channels / columns
+        static_assert(KB == 2 && N2 == 32, "two epilogue groups: one K block of y and 16 head columns each");
         const int m = ew * 32 + lane;
         const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)(m & 7);
         bool range_bad = false;
@@ -176,8 +180,8 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
             mbar_wait(&bar_a2empty, (uint32_t)(i & 1) ^ 1u);       // GEMM 2 of the previous tile has read the A tile
             const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
             const uint32_t taddr = tlane + (uint32_t)(i & 1) * 128u;
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
+            {
+                const int kb = grp;
                 uint8_t *a2 = smem + OFF_A2 + kb * X_STAGE_BYTES;
 #pragma unroll
                 for (int c0 = 0; c0 < BLOCK_K; c0 += 16) {
@@ -215,8 +219,8 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
             const int hh = th * TILE_H + m / TILE_W, ww = tw * TILE_W + m % TILE_W;
             const bool ok = hh < p.H && ww < p.W;
             float *outp = p.out + (((size_t)b * p.H + hh) * p.W + ww) * p.out_stride;
-#pragma unroll
-            for (int c0 = 0; c0 < N2; c0 += 16) {
+            {
+                const int c0 = grp * 16;
                 uint32_t r[16];
                 tmem_ld16(tlane + 256 + c0, r);
                 tmem_ld_wait();
