@@ -5,10 +5,12 @@
 //
 // As two b2s_conv2d_tc launches y makes a round trip through HBM: 2 x 577 MB at 32 frames, the 1x1 stage was 0.41 ms of
 // a 5.4 ms step at 60-77 % of the HBM peak (profiles/, round 2).  Here y is produced into TMEM, gets its BN + ReLU +
-// hi/lo split in the epilogue warps' registers, is written to SHARED memory in the K-major SWIZZLE_128B layout the
-// second GEMM's A operand wants, and is consumed from there: per 128-pixel tile the kernel reads 64 KB of x and writes
-// 16 KB of head records, instead of 208 KB of traffic.  Both weight sets (80 KB as hi/lo planes) stay resident in
-// shared memory.  The MMA sequences, the epilogue arithmetic and the 3xF16 split are exactly those of k_conv_tc
+// hi/lo split in the epilogue warps' registers, goes BACK into tensor memory as packed fp16 pairs (tcgen05.st, lane =
+// pixel) and is the A operand of the second GEMM from there (tcgen05.mma with [a_tmem]): per 128-pixel tile the kernel
+// reads 64 KB of x and writes 16 KB of head records, instead of 208 KB of traffic.  Both weight sets (80 KB as hi/lo
+// planes) stay resident in shared memory and the rest of it is a 4-stage x ring (two tiles in flight).  (First version,
+// kept as B2S_RPN_TAIL_A=smem: y written to shared memory in the K-major SWIZZLE_128B layout -- that A tile costs 64 KB,
+// leaves an x ring of ONE tile, and the load latency of the next tile was exposed: 0.207 vs 0.172 ms.)  The MMA sequences, the epilogue arithmetic and the 3xF16 split are exactly those of k_conv_tc
 // (conv_tc.cu) for the two layers, so the records are BIT-IDENTICAL to the two-launch path (tested).
 //
 // CTA = 8 warps, persistent over 8 x 16-pixel tiles:
@@ -42,7 +44,25 @@ struct TailParams {
     int *status;
 };
 
-template <int N2>
+// A operand of GEMM 2 straight from tensor memory (tcgen05.mma with [a_tmem]); 32 bits hold two consecutive channels
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t *r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+
+// ATM = false: y goes to SHARED memory as the K-major SWIZZLE_128B A tile of GEMM 2 (64 KB), the x ring holds one tile.
+// ATM = true : y goes back to TENSOR memory (fp16 hi/lo pairs, lane = pixel) and GEMM 2 reads its A operand from there; the
+//              64 KB of shared memory become two more x stages, so the next tile's x is in flight during the whole tile.
+template <int N2, bool ATM>
 __global__ void __launch_bounds__(kThreads, 1)
 k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__ CUtensorMap map_x_lo,
            const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
@@ -51,14 +71,16 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
 {
     constexpr uint32_t W2_KB_BYTES = 2 * N2 * BLOCK_K * ELEM_BYTES;    // hi + lo of one K block of the head weights
     constexpr uint32_t OFF_W1 = 0, OFF_W2 = OFF_W1 + KB * W1_KB_BYTES, OFF_X = OFF_W2 + KB * W2_KB_BYTES;
-    constexpr uint32_t OFF_A2 = OFF_X + KB * X_STAGE_BYTES;            // y as the A operand: KB x (hi 16 KB | lo 16 KB)
+    constexpr int XS = ATM ? 2 * KB : KB;                              // x ring stages (one K block of one tile each)
+    constexpr uint32_t OFF_A2 = OFF_X + KB * X_STAGE_BYTES;            // (!ATM) y as the A operand: KB x (hi 16 KB | lo 16 KB)
     constexpr uint32_t TMEM_COLS = 512;                                // D1[0] at column 0, D1[1] at 128, D2 at 256 (N2)
+    constexpr uint32_t A2_HI_COL = 320, A2_LO_COL = 384;               // (ATM) y hi / lo: 32 columns per K block
     static_assert(N2 % 16 == 0 && N2 >= 16 && N2 <= 64 && (OFF_W2 % 1024) == 0 && (OFF_X % 1024) == 0 && (OFF_A2 % 1024) == 0,
                   "operand tiles are 1024-byte aligned (SWIZZLE_128B)");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t bar_w, bar_xfull[KB], bar_xempty[KB], bar_d1full[2], bar_d1empty[2], bar_a2full,
+    __shared__ __align__(8) uint64_t bar_w, bar_xfull[XS], bar_xempty[XS], bar_d1full[2], bar_d1empty[2], bar_a2full,
         bar_a2empty, bar_d2full, bar_d2empty;
     __shared__ uint32_t s_tmem_base;
     __shared__ float s_scale1[N1], s_shift1[N1], s_scale2[N2], s_shift2[N2];
@@ -75,7 +97,7 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         mbar_init(&bar_w, 1);
-        for (int i = 0; i < KB; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
+        for (int i = 0; i < XS; ++i) { mbar_init(&bar_xfull[i], 1); mbar_init(&bar_xempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_d1full[i], 1); mbar_init(&bar_d1empty[i], 8); }
         mbar_init(&bar_a2full, 8); mbar_init(&bar_a2empty, 1);
         mbar_init(&bar_d2full, 1); mbar_init(&bar_d2empty, 8);
@@ -102,18 +124,18 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
                 tma_load_3d(smem + OFF_W2 + kb * W2_KB_BYTES, &map_w2_hi, &bar_w, kb * BLOCK_K, 0, 0);
                 tma_load_3d(smem + OFF_W2 + kb * W2_KB_BYTES + W2_KB_BYTES / 2, &map_w2_lo, &bar_w, kb * BLOCK_K, 0, 0);
             }
-            uint32_t phase = 0;
+            int u = 0;                                                 // K blocks of x loaded so far: slot u % XS, its (u / XS)-th use
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, b = tile / (p.tiles_w * p.tiles_h);
                 const int h0 = th * TILE_H + 1, w0 = tw * TILE_W + 1;          // + 1: the one-pixel halo of the input planes
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&bar_xempty[kb], phase ^ 1);
-                    uint8_t *st = smem + OFF_X + kb * X_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&bar_xfull[kb], X_STAGE_BYTES);
-                    tma_load_4d(st, &map_x_hi, &bar_xfull[kb], kb * BLOCK_K, w0, h0, b);
-                    tma_load_4d(st + A_TILE_BYTES, &map_x_lo, &bar_xfull[kb], kb * BLOCK_K, w0, h0, b);
+                for (int kb = 0; kb < KB; ++kb, ++u) {
+                    const int slot = u % XS;
+                    mbar_wait(&bar_xempty[slot], (uint32_t)((u / XS) & 1) ^ 1u);
+                    uint8_t *st = smem + OFF_X + slot * X_STAGE_BYTES;
+                    mbar_arrive_expect_tx(&bar_xfull[slot], X_STAGE_BYTES);
+                    tma_load_4d(st, &map_x_hi, &bar_xfull[slot], kb * BLOCK_K, w0, h0, b);
+                    tma_load_4d(st + A_TILE_BYTES, &map_x_lo, &bar_xfull[slot], kb * BLOCK_K, w0, h0, b);
                 }
-                phase ^= 1;
             }
         }
     } else if (warp == 1) {
@@ -140,10 +162,11 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
                 const uint32_t d1 = tmem_u + (uint32_t)(i & 1) * 128u;
                 mbar_wait(&bar_d1empty[i & 1], (uint32_t)((i >> 1) & 1) ^ 1u);      // E1(i-2) has read this accumulator
                 for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(&bar_xfull[kb], (uint32_t)(i & 1));
+                    const int u = i * KB + kb, slot = u % XS;
+                    mbar_wait(&bar_xfull[slot], (uint32_t)((u / XS) & 1));
                     tc_fence_after();
-                    gemm(d1, smem0 + OFF_X + kb * X_STAGE_BYTES, smem0 + OFF_W1 + kb * W1_KB_BYTES, W1_KB_BYTES / 2, idesc1, kb);
-                    umma_commit(&bar_xempty[kb]);
+                    gemm(d1, smem0 + OFF_X + slot * X_STAGE_BYTES, smem0 + OFF_W1 + kb * W1_KB_BYTES, W1_KB_BYTES / 2, idesc1, kb);
+                    umma_commit(&bar_xempty[slot]);
                 }
                 umma_commit(&bar_d1full[i & 1]);
             };
@@ -156,8 +179,24 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
                 mbar_wait(&bar_d2empty, (uint32_t)(i & 1) ^ 1u);          // E2(i-1) has read D2
                 mbar_wait(&bar_a2full, (uint32_t)(i & 1));
                 tc_fence_after();
-                for (int kb = 0; kb < KB; ++kb)
-                    gemm(d2, smem0 + OFF_A2 + kb * X_STAGE_BYTES, smem0 + OFF_W2 + kb * W2_KB_BYTES, W2_KB_BYTES / 2, idesc2, kb);
+                if constexpr (ATM) {
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint32_t b_base = smem0 + OFF_W2 + kb * W2_KB_BYTES;
+                        const uint64_t b_hi = make_desc_sw128(b_base), b_lo = make_desc_sw128(b_base + W2_KB_BYTES / 2);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM_BYTES) >> 4);
+                            const uint32_t a_hi = tmem_u + A2_HI_COL + (uint32_t)(kb * (BLOCK_K / 2) + k * (UMMA_K / 2));
+                            const uint32_t a_lo = tmem_u + A2_LO_COL + (uint32_t)(kb * (BLOCK_K / 2) + k * (UMMA_K / 2));
+                            umma_f16_ts(d2, a_lo, b_hi + koff, idesc2, (kb | k) != 0);
+                            umma_f16_ts(d2, a_hi, b_lo + koff, idesc2, 1);
+                            umma_f16_ts(d2, a_hi, b_hi + koff, idesc2, 1);
+                        }
+                    }
+                } else {
+                    for (int kb = 0; kb < KB; ++kb)
+                        gemm(d2, smem0 + OFF_A2 + kb * X_STAGE_BYTES, smem0 + OFF_W2 + kb * W2_KB_BYTES, W2_KB_BYTES / 2, idesc2, kb);
+                }
                 umma_commit(&bar_a2empty);
                 umma_commit(&bar_d2full);
             }
@@ -186,6 +225,7 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
 #pragma unroll
                 for (int c0 = 0; c0 < BLOCK_K; c0 += 16) {
                     uint32_t r[16];
+                    uint32_t hi8[8], lo8[8];
                     tmem_ld16(taddr + kb * BLOCK_K + c0, r);
                     tmem_ld_wait();
 #pragma unroll
@@ -202,15 +242,25 @@ k_rpn_tail(const __grid_constant__ CUtensorMap map_x_hi, const __grid_constant__
                             hw[j] = __byte_perm(p0, p1, 0x5410);
                             lw[j] = __byte_perm(p0, p1, 0x7632);
                         }
-                        const uint32_t chunk = (uint32_t)(c0 / 8 + h8);
-                        const uint32_t off = row_off + ((chunk ^ sw) << 4);
-                        *reinterpret_cast<uint4 *>(a2 + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *reinterpret_cast<uint4 *>(a2 + A_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        if constexpr (ATM) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { hi8[h8 * 4 + j] = hw[j]; lo8[h8 * 4 + j] = lw[j]; }
+                        } else {
+                            const uint32_t chunk = (uint32_t)(c0 / 8 + h8);
+                            const uint32_t off = row_off + ((chunk ^ sw) << 4);
+                            *reinterpret_cast<uint4 *>(a2 + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *reinterpret_cast<uint4 *>(a2 + A_TILE_BYTES + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        }
+                    }
+                    if constexpr (ATM) {         // 16 channels = 8 packed columns of each plane, this lane's row
+                        tmem_st8(tlane + A2_HI_COL + (uint32_t)(kb * (BLOCK_K / 2) + c0 / 2), hi8);
+                        tmem_st8(tlane + A2_LO_COL + (uint32_t)(kb * (BLOCK_K / 2) + c0 / 2), lo8);
                     }
                 }
             }
+            if constexpr (ATM) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+            if constexpr (!ATM) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
             __syncwarp();
             if (lane == 0) { mbar_arrive(&bar_d1empty[i & 1]); mbar_arrive(&bar_a2full); }
             // ---- E2: records = D2 * scale2 + shift2 (bias) -> fp32 [B, H, W, out_stride]
@@ -293,10 +343,17 @@ extern "C" int b2s_rpn_tail_tc(const b2s_half *in_hi, const b2s_half *in_lo, int
     p.scale1 = scale1; p.shift1 = shift1; p.scale2 = scale2; p.shift2 = shift2;
     p.out = out; p.status = (int *)status_dev;
     constexpr size_t smem = KB * (W1_KB_BYTES + 2 * 32 * BLOCK_K * ELEM_BYTES) + 2 * KB * X_STAGE_BYTES + 1024;
-    B2S_SMEM_OPT_IN((k_rpn_tail<32>), smem);
     const int num_sms = num_sms_current();
     const int grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-    k_rpn_tail<32><<<grid, kThreads, smem, stream>>>(x_hi, x_lo, m1_hi, m1_lo, m2_hi, m2_lo, p);
+    static int atm = -1;        // B2S_RPN_TAIL_A = tmem (default) | smem: where GEMM 2 reads y from (see k_rpn_tail)
+    if (atm < 0) { const char *e = getenv("B2S_RPN_TAIL_A"); atm = (e && e[0] == 's') ? 0 : 1; }
+    if (atm) {
+        B2S_SMEM_OPT_IN((k_rpn_tail<32, true>), smem);
+        k_rpn_tail<32, true><<<grid, kThreads, smem, stream>>>(x_hi, x_lo, m1_hi, m1_lo, m2_hi, m2_lo, p);
+    } else {
+        B2S_SMEM_OPT_IN((k_rpn_tail<32, false>), smem);
+        k_rpn_tail<32, false><<<grid, kThreads, smem, stream>>>(x_hi, x_lo, m1_hi, m1_lo, m2_hi, m2_lo, p);
+    }
     B2S_LAUNCH_OK();
     return 0;
 }
