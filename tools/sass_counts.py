@@ -1,5 +1,5 @@
 """SASS evidence for the tcgen05 / TMA kernels: per kernel of libb2second.so the count of the mnemonics that prove the
-Blackwell-native path (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA tensor load, LDGSTS = cp.async,
+Blackwell-native path (UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / tcgen05.st, UTMALDG = TMA tensor load, LDGSTS = cp.async,
 ARRIVES.LDGSTSBAR / SYNCS = mbarrier traffic) and of the legacy ones that must be absent (HMMA, HGMMA).
 Usage: python tools/sass_counts.py [lib.so] > profiles/r2_sass_counts.txt"""
 import collections
@@ -11,7 +11,7 @@ import sys
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..",
                                                           "second.pytorch_b200", "csrc", "libb2second.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-WATCH = ["UTCHMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "ARRIVES.LDGSTSBAR", "SYNCS", "HMMA", "HGMMA",
+WATCH = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "ARRIVES.LDGSTSBAR", "SYNCS", "HMMA", "HGMMA",
          "FFMA", "LDG", "STG", "ATOMG", "RED"]
 cur, counts = None, collections.OrderedDict()
 for line in sass.splitlines():
@@ -34,7 +34,7 @@ for line in sass.splitlines():
             if op == w or op.startswith(w + "."):
                 counts[cur][w] += 1
 print("# cuobjdump -sass %s : mnemonic counts per kernel" % os.path.basename(lib))
-print("# tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG, cp.async -> LDGSTS; HMMA/HGMMA (legacy "
+print("# tcgen05.mma -> UTCHMMA, tcgen05.ld / st -> LDTM / STTM, cp.async.bulk.tensor -> UTMALDG, cp.async -> LDGSTS; HMMA/HGMMA (legacy "
       "mma.sync / wgmma) must be 0")
 print("%-44s " % "kernel" + " ".join("%9s" % w[:9] for w in WATCH))
 tot = collections.Counter()
