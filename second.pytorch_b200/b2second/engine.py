@@ -275,14 +275,7 @@ class InferenceEngine:
         self.tc_plan = plan["ops"]
         # single-scale tail (one k = s = 1 deblock 128 -> 128 feeding the heads): one fused kernel, the deblock output
         # never goes to HBM (csrc/rpn_tail.cu; bit-identical to the two launches).  B2S_RPN_TAIL=0: two launches.
-        ops = self.tc_plan
-        self.tc_tail_fused = bool(
-            os.environ.get("B2S_RPN_TAIL", "1") != "0" and len(ops) >= 2
-            and ops[-1]["kind"] == "heads" and ops[-2]["kind"] == "deblock" and ops[-1]["src"] == ops[-2]["dst"]
-            and sum(1 for o in ops if o["dst"] == ops[-2]["dst"]) == 1
-            and (ops[-2]["kh"], ops[-2]["kw"], ops[-2]["stride"], ops[-2]["out_mul"], ops[-2]["dst_coff"]) == (1, 1, 1, 1, 0)
-            and ops[-2]["cin"] == 128 and ops[-2]["cout"] == 128 and ops[-2]["relu"] and ops[-2]["planes"] == 2
-            and ops[-1]["cin"] == 128 and ops[-1]["n_pad"] == 32 and ops[-1]["planes"] == 1 and not ops[-1]["relu"])
+        self.tc_tail_fused = bool(os.environ.get("B2S_RPN_TAIL", "1") != "0" and _tc.fusable_tail(plan))
         assert plan["in_channels"] == C, "BEV channels %d != RPN input %d" % (C, plan["in_channels"])
 
         def plane(h, w, c):

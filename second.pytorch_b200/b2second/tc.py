@@ -215,6 +215,21 @@ def plan_rpn(rpn, H, W, dry=False):
             "heads": {"offsets": offs, "stride": stride_s, "H": h, "W": w}}
 
 
+def fusable_tail(plan):
+    """True when the program ends with ONE k = s = 1 deblock 128 -> 128 (+BN+ReLU) whose output only feeds the packed heads
+    (<= 32 channels): the shape b2s_rpn_tail_tc runs as a single kernel (car.fhd, car.lite; all.fhd packs 104 head
+    channels, the multi-scale RPNs concatenate several deblocks)."""
+    ops = plan["ops"]
+    if len(ops) < 2:
+        return False
+    d, h = ops[-2], ops[-1]
+    return bool(h["kind"] == "heads" and d["kind"] == "deblock" and h["src"] == d["dst"]
+                and sum(1 for o in ops if o["dst"] == d["dst"]) == 1
+                and (d["kh"], d["kw"], d["stride"], d["out_mul"], d["dst_coff"]) == (1, 1, 1, 1, 0)
+                and d["cin"] == 128 and d["cout"] == 128 and d["relu"] and d["planes"] == 2
+                and h["cin"] == 128 and h["n_pad"] == 32 and h["planes"] == 1 and not h["relu"])
+
+
 def background_layers(plan):
     """indices of the leading ops of an RPN program that form a chain of 3x3 stride-1 pad-1 128-out layers starting at
     the BEV input (the ops the weights-stationary kernel takes): background tiles are only tracked through those."""

@@ -169,3 +169,21 @@ def test_background_tiles_hold_the_empty_frame_response(name):
     inner = empty[0, :, 8:-8, 8:-8]
     assert float((inner - inner[:, :1, :1]).abs().max()) == 0.0
     assert float((empty[0, :, 0, 0] - inner[:, 0, 0]).abs().max()) > 0.0
+
+
+def test_fused_tail_is_taken_exactly_where_the_program_has_that_shape():
+    """b2s_rpn_tail_tc replaces the last two ops only for a single k = s = 1 deblock 128 -> 128 feeding <= 32 packed head
+    channels (car.fhd, car.lite); the dispatch is host logic (b2second.tc.fusable_tail) and pinned here for every BASELINE config."""
+    sp = loader.oracle_spconv()
+    want = {"car.fhd": True, "car.lite": True}        # all.fhd packs 104 head channels, the pillar RPNs are multi-scale
+    for name in config.BUILTIN:
+        cfg = config.get_config(name)
+        net = models.build_network(cfg, sp).eval()
+        plan = tc.plan_rpn(net.rpn, 32, 48)
+        assert tc.fusable_tail(plan) == want.get(name, False), name
+        if tc.fusable_tail(plan):
+            d, h = plan["ops"][-2], plan["ops"][-1]
+            # what the fused kernel is handed: the deblock as a 1x1 conv [1][128][128], the heads padded to 32 rows
+            assert tuple(d["w_hi"].shape) == (1, 128, 128) and tuple(h["w_hi"].shape) == (1, 32, 128)
+            assert d["shift"] is not None and h["shift"] is not None and h["cout"] % 4 == 0
+            assert plan["heads"]["stride"] >= h["cout"]
