@@ -25,13 +25,11 @@
 //               SWIZZLE_128B A tile, zero-fill for missing neighbours, completion signalled on the stage's mbarrier
 //               with cp.async.mbarrier.arrive.noinc.  The neighbour-table entries of the NEXT owned K block are
 //               loaded (straight from global / L1) before the current one is waited for.
-//               History: until round 2 all 8 warps worked on EVERY K block (16 rows each) behind a shared-memory copy
-//               of the tile's table.  clock64 showed the issuer waiting ~410 of ~900 cycles per K block for gather
-//               warps that were themselves busy ~670 cycles: one short dependent instruction chain per K block and
-//               warp (wait, 4 table reads, 8 copies, arrive), serialised K block after K block -- neither the copies
-//               (diagnostic: off) nor the 256 mbarrier arrivals (diagnostic: one per warp) were the cost.  Owning a
-//               stage gives a warp four K-block times for 32 independent copies.  (A TMA tile::gather4 producer
-//               was tried in round 1 -- tests/cuda/gather4_probe.cu -- 3x slower than cp.async.)
+//               History: in round 1 all 8 warps worked on EVERY K block (16 rows each) behind a shared-memory copy of
+//               the tile's table; that variant rebuilt with this round's copy loop is the OWN = 1 instantiation
+//               (1.5x slower than stage ownership).  A TMA tile::gather4 producer was tried in round 1
+//               (tests/cuda/gather4_probe.cu): 3x slower than cp.async.  What does and does not bound this kernel is
+//               in DESIGN.md section 7 (eleven measured variants, tools/experiments/README.md).
 //   warps 12-15 epilogue: drain per-chain partial sums from TMEM (round-to-nearest adds in registers, the
 //               tensor core's own accumulate is not RN -- see conv_tc.cu), BN scale/shift + ReLU, hi/lo split,
 //               coalesced row stores through a small staging tile
@@ -44,7 +42,7 @@ namespace {
 using namespace b2s_tc;
 // pipeline stages: 4 x (32 KB of gathered rows + 256 N bytes of weights).  Five stages for the narrow layers (N <= 32 fits)
 // were tried in round 2: not faster (the ring is not what bounds the kernel) and not validated -- kept at 4 everywhere.
-__host__ __device__ constexpr int stages_for(int n) { return n > 0 ? 4 : 4; }
+__host__ __device__ constexpr int stages_for(int /*n*/) { return 4; }
 // GW gather warps (warps 4 .. 4+GW-1), the epilogue is the 4 warps after them.  GW = 16 (24 warps) needs the register
 // file rebalanced between the roles with setmaxnreg (inside each role's branch, where ptxas honours it): 768 threads
 // start with 80 registers each; the gather warps drop to 64 and the epilogue warps (64 running sums + staging) rise to 144.
